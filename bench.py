@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Headline benchmark: particle-steps/s of one training application (forward + loss + backward) of
+the encode / M x message-passing / decode Interaction Network on a synthetic periodic box.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # N ranks, one box replica each + gradient all-reduce
+
+Workload (default `config2`): BASELINE.json configs[1] -- 32^3 = 32768 particles, k=16, latent 128,
+10 MP steps, acceleration + temperature-rate + momentum loss.  `--workload config3` is configs[2]
+(128^3 particles, k=32).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (particles, k, latent, mp_steps, box kind)
+    "config1": (4096, 16, 64, 5, "uniform"),
+    "config2": (32 ** 3, 16, 128, 10, "uniform"),
+    "config3": (128 ** 3, 32, 128, 10, "uniform"),
+    "tiny": (2048, 8, 32, 2, "uniform"),
+}
+W_ACC, W_TEMP, W_MOM = 1.0, 1.0, 0.1
+METRIC = "particle-steps/sec (fwd+bwd, 10 MP, L=128, k=32) at 1/2/4/8 B200; % roofline"
+UNIT = "particle-steps/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"bf16_sustained": d["bf16_tflops_sustained"], "bf16_burst": d["bf16_tflops"],
+                "hbm": d["hbm_gbs"], "source": "MEASURED_PEAKS.json"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def flops_edge_fwd(n, k, L):
+    """Algorithmic FLOPs of one processor edge phase (proc_edge = 2E(3LH + H^2 + HL), H = L)."""
+    return 2.0 * n * k * (3 * L * L + L * L + L * L)
+
+
+def flops_application(n, k, L, M, message):
+    fn, fe = 17, 4
+    enc_n = 2.0 * n * (fn * L + L * L + L * L)
+    enc_e = 2.0 * n * k * (fe * L + L * L + L * L)
+    proc_e = flops_edge_fwd(n, k, L)
+    proc_n = 2.0 * n * (2 * L * L + L * L + L * L)
+    dec = 2.0 * n * (L * L + L * L + 3 * L) + 2.0 * n * (L * L + L * L + L)
+    fwd = enc_n + enc_e + M * (proc_e + proc_n) + dec
+    if message == "edge":
+        return 3.0 * fwd
+    return fwd + 2.0 * (enc_n + M * proc_n + dec)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (sampled DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv = self._nv
+        names = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown",
+                 "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown",
+                 "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for label, attr in names.items():
+                    if mask & getattr(nv, attr, 0):
+                        self.reasons.add(label)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference leg (oracle port of the reference algorithm; the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_training_step_rate(k, L, M, steps, warmup, sample_n=8192, seed=0):
+    """Times the reference algorithm (reference-actual message='sender' semantics: gathers, cat,
+    Linear, ReLU, LayerNorm, index_add_, autograd backward) on the host cores with all threads.
+    The particle count is a bounded sample of the workload (cost is linear in N at fixed k, L, M)."""
+    from cosmology_gnn_simulation_b200 import synthetic
+    from oracle import knn_ref, model_ref
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    pos = synthetic.positions(sample_n, "uniform", 1.0, seed=seed)
+    t0 = time.perf_counter()
+    ext = knn_ref.knn_kdtree(pos, 1.0, k)                   # KD-tree over the 27N ghosts, one thread (F5)
+    knn_s = time.perf_counter() - t0
+    ei = torch.from_numpy(knn_ref.edge_index_from_ext(ext, sample_n))
+    p = torch.from_numpy(pos)
+    d = p[ei[0]] - p[ei[1]]
+    ea = torch.cat([d, d.norm(dim=-1, keepdim=True)], dim=-1)
+    gen = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(sample_n, 17, generator=gen)
+    ya, yt = torch.randn(sample_n, 3, generator=gen), torch.randn(sample_n, 1, generator=gen)
+    params = {k_: v.requires_grad_(True) for k_, v in model_ref.init_params(L, L, 2, M, 3, seed=seed).items()}
+    times = []
+    for it in range(warmup + steps):
+        for v in params.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        o = model_ref.forward(params, x, ei, ea, 2, M, message="sender")
+        ls = model_ref.loss(o["acceleration"], o["temp_rate"], ya, yt, 0.01, w_acc=W_ACC, w_temp=W_TEMP, w_mom=W_MOM)
+        ls["loss"].backward()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"rate": sample_n * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+            "sample_n": sample_n, "knn_rate": sample_n / knn_s, "knn_s": knn_s}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                              # rank 0 alone runs the CPU arm
+    n, k, L, M, kind = WORKLOADS[args.workload]
+    sample_n = min(n, 8192)
+    r = cpu_training_step_rate(k, L, M, args.steps, max(args.warmup, 1), sample_n=sample_n)
+    sample = (f"{sample_n} of {n} particles per step at the workload's k={k}, L={L}, M={M} "
+              f"(cost linear in N); graph build (KD-tree on 27N ghosts, 1 thread) timed apart: "
+              f"{r['knn_rate']:.3g} particles/s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, "sender", "fp32", args.gpus),
+        "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, message, precision, gpus):
+    n, k, L, M, kind = WORKLOADS[name]
+    return {"workload": f"{name}: training step, {n} particles ({kind} periodic box), k={k}, latent={L}, "
+                        f"{M} MP steps, acc+temp+momentum loss",
+            "particles_per_gpu": n, "k": k, "latent": L, "mp_steps": M, "message": message, "precision": precision,
+            "parallelism": f"dp{gpus} (one box replica per GPU, gradient all-reduce)" if gpus > 1 else "single GPU",
+            "l2": "inputs larger than L2 (edge latent stream alone exceeds 126 MB)" if n * k * L * 4 > 126e6
+                  else "L2 flushed between timed steps (256 MB write)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    from cosmology_gnn_simulation_b200 import _lib, ops, synthetic
+    from cosmology_gnn_simulation_b200 import distributed as cd
+    from cosmology_gnn_simulation_b200.data_utils import preprocess
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    import torch.distributed as dist
+
+    rank, world, local = cd.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    n, k, L, M, kind = WORKLOADS[args.workload]
+    message, precision = args.message, args.precision
+
+    box = synthetic.make_box(n, kind, seed=rank)
+    md = box["metadata"]
+    coords_host = box["Coordinates"].pin_memory()
+    energy_host = box["InternalEnergy"].pin_memory()
+    h2d_bytes = coords_host.numel() * 4 + energy_host.numel() * 4
+
+    torch.manual_seed(0)
+    model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision).to(dev)
+    bucket = cd.GradientBucket(model.parameters())
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev) if n * k * L * 4 <= 126e6 else None
+
+    def build_graph(coords, energy):
+        return preprocess(coords[:5], energy[:5], md, coords[5:6], energy[5:6], noise_std=0.0, num_neighbors=k,
+                          dt=md["dt"], box_size=md["box_size"], device=dev)
+
+    graph = build_graph(coords_host, energy_host)        # resident inputs for the device-timed region
+
+    def train_step(g):
+        for p in model.parameters():
+            p.grad = None
+        pred = model(g)
+        ls = combined_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
+        ls["loss"].backward()
+        bucket.all_reduce(average=True)
+        return ls
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (`value`) -------------------------------------------------
+    for _ in range(args.warmup):
+        train_step(graph)
+    barrier()
+    ops.EDGE_FWD_EVENTS = []
+    launches0 = _lib.launch_count()
+    step_ms = []
+    with ClockSampler(local) as clocks:
+        for _ in range(args.steps):
+            if flush is not None:
+                flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            train_step(graph)
+            e.record()
+            step_ms.append((s, e))
+        barrier()
+    launches = _lib.launch_count() - launches0
+    events, ops.EDGE_FWD_EVENTS = ops.EDGE_FWD_EVENTS, None
+    total_ms = sum(s.elapsed_time(e) for s, e in step_ms)
+    total_ms = cd.max_over_ranks(total_ms, dev)
+    value = world * n * args.steps / (total_ms * 1e-3)
+    edge_ms = sum(a.elapsed_time(b) for a, b in events) / max(len(events), 1)
+
+    # ---- end to end through the public API with host buffers (`e2e`) ---------------------------
+    def e2e_step():
+        c = coords_host.to(dev, non_blocking=True)
+        u = energy_host.to(dev, non_blocking=True)
+        g = build_graph(c, u)
+        ls = train_step(g)
+        return torch.stack([ls["loss"].detach(), ls["acc_loss"], ls["temp_rate_loss"], ls["momentum_loss"]]).cpu()
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = e2e_step()
+    barrier()
+    e2e_s = cd.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = world * n * args.steps / e2e_s
+
+    # ---- graph build alone (reported apart; not part of the model application) -----
+    pos_dev = graph.pos
+    for _ in range(2):
+        ops.knn_periodic(pos_dev, md["box_size"], k)
+    torch.cuda.synchronize(dev)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    reps = 5
+    for _ in range(reps):
+        nbr = ops.knn_periodic(pos_dev, md["box_size"], k)
+        ops.edge_features(pos_dev, nbr, md["box_size"])
+    e.record()
+    torch.cuda.synchronize(dev)
+    knn_ms = s.elapsed_time(e) / reps
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    fl = flops_edge_fwd(n, k, L)
+    achieved = fl / (edge_ms * 1e-3) / 1e12 if edge_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16 operands, f32 accumulate/storage)", "bf16": "bf16"}[precision],
+        "data": "synthetic",
+        "config": workload_config(args.workload, message, precision, world),
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
+                "includes": "H2D of the 6 frames, graph build (k-NN + features), forward, loss, backward, D2H of the 4 loss scalars"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "cgnn_mp_edge_fwd (processor edge phase, forward)",
+                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                     "flop_per_launch": fl, "ms_per_launch": edge_ms, "launches_timed": len(events),
+                     "peak_source": peaks["source"] + " (bf16 dense, sustained)",
+                     "share_of_step": edge_ms * M / (total_ms / args.steps)},
+        "model_tflops": flops_application(n, k, L, M, message) / (total_ms / args.steps * 1e-3) / 1e12,
+        "graph_build": {"ms": knn_ms, "particles_per_s": n / (knn_ms * 1e-3),
+                        "what": "cgnn_knn_periodic + cgnn_edge_features, device resident"},
+        "loss_check": [float(v) for v in last],
+    }
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_training_step_rate(k, L, M, steps=2, warmup=1, sample_n=min(n, 8192))
+        line["cpu_baseline"] = {
+            "value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": f"oracle port (reference-actual semantics), {r['sample_n']} of {n} particles per step, "
+                      f"k={k}, L={L}, M={M}, fwd+loss+bwd, 1 warm-up + 2 timed steps; k-NN oracle "
+                      f"(KD-tree on 27N ghosts, 1 thread) {r['knn_rate']:.3g} particles/s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cgnn", choices=["cgnn", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--message", default="sender", choices=["sender", "edge"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cgnn" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,328 @@
+"""Drop-in for the reference's `graph_network` module (graph_network.py:108-187).
+
+`EncodeProcessDecode` keeps the reference constructor, `forward(input_graph)` contract and
+`state_dict` key names, but its forward and backward run as hand-written sm_100a
+kernels behind the C ABI of `libcgnn.so` (include/cgnn.h):
+
+  encoder (graph_network.py:52-64)          -> cgnn_mlp_rows_fwd / _bwd
+  M x InteractionNetwork + residuals         -> cgnn_mp_edge_fwd, cgnn_aggregate_senders,
+    (graph_network.py:83-101,177-183)          cgnn_mp_node_fwd  (+ _bwd with in-tile recompute)
+  decoders (graph_network.py:151-152,158-164)-> cgnn_mlp_rows_fwd / _bwd
+
+The torch modules below only hold parameters (so `.parameters()`, `.to()`, `state_dict()`, lazy first
+layers and stock optimizers behave exactly like the reference); they are never called.  There is no
+CPU or PyTorch fallback: CPU inputs raise.
+
+`message` selects what is summed at the receivers (SURVEY finding F2):
+  "sender" (default) - what the reference actually computes: PyG's default message, the sender
+                        node latent; the edge stream then gets no gradient (its grads stay None).
+  "edge"             - the intended Interaction Network: the updated edge latent is the message.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import MlpParams
+
+__all__ = ["EncodeProcessDecode", "build_mlp"]
+
+
+def build_mlp(hidden_size: int, num_hidden_layers: int, output_size: int) -> nn.Module:
+    """Parameter holder with the reference's layout: Linear layers at Sequential indices 0,2,4,...
+    (first one lazy, graph_network.py:15-32).  The ReLUs are fused into the kernels."""
+    mods: List[nn.Module] = []
+    for depth in range(num_hidden_layers):
+        mods += [nn.LazyLinear(hidden_size) if depth == 0 else nn.Linear(hidden_size, hidden_size),
+                 nn.ReLU(inplace=True)]
+    mods.append(nn.Linear(hidden_size, output_size))
+    return nn.Sequential(*mods)
+
+
+class _NodeEdgePair(nn.Module):
+    """`node_model` / `edge_model` holder (registration order as graph_network.py:49-50,80-81)."""
+
+    def __init__(self, node_model: nn.Module, edge_model: nn.Module):
+        super().__init__()
+        self.node_model = node_model
+        self.edge_model = edge_model
+
+
+def _linears(seq: nn.Sequential) -> List[nn.Module]:
+    return [m for m in seq if isinstance(m, (nn.Linear, nn.LazyLinear))]
+
+
+def _materialize(seq: nn.Sequential, in_dim: int, like: torch.Tensor) -> None:
+    """Gives a still-lazy first layer its shape, as the reference's first forward would."""
+    first = _linears(seq)[0]
+    if isinstance(first, nn.LazyLinear) and first.has_uninitialized_params():
+        probe = torch.empty((1, in_dim), dtype=like.dtype, device=like.device)
+        first._infer_parameters(first, (probe,))     # initialises and turns the module into nn.Linear
+
+
+def _mlp_params(seq: nn.Sequential, norm: Optional[nn.LayerNorm]) -> MlpParams:
+    lin = _linears(seq)
+    return MlpParams([m.weight for m in lin], [m.bias for m in lin],
+                     None if norm is None else norm.weight, None if norm is None else norm.bias)
+
+
+class _Plan:
+    """Static description of one forward call, shared by forward and backward."""
+
+    def __init__(self, n_steps, message, precision, k, enc_node, enc_edge, proc_node, proc_edge, dec_acc,
+                 dec_temp, groups, edge_ckpt_every):
+        self.n_steps, self.message, self.precision, self.k = n_steps, message, precision, k
+        self.enc_node, self.enc_edge = enc_node, enc_edge
+        self.proc_node, self.proc_edge = proc_node, proc_edge
+        self.dec_acc, self.dec_temp = dec_acc, dec_temp
+        self.groups = groups                  # [(MlpParams, first index into the flat parameter list)]
+        self.edge_ckpt_every = edge_ckpt_every
+
+
+def _edge_stream_plan(n_steps: int, bytes_per_copy: int, device) -> int:
+    """Checkpoint spacing s for the edge latent stream in message="edge" training: keep e^t for
+    t % s == 0 and recompute the rest segment by segment in backward."""
+    free, _ = torch.cuda.mem_get_info(device)
+    budget = int(free * 0.6)
+    for s in range(1, n_steps + 1):
+        copies = (n_steps + s - 1) // s + (s - 1) + 3          # checkpoints + segment + (de, de', gs)
+        if copies * bytes_per_copy <= budget:
+            return s
+    raise RuntimeError(
+        f"cgnn: the edge latent stream does not fit: {bytes_per_copy / 2**30:.1f} GiB per copy, "
+        f"{free / 2**30:.1f} GiB free; shard the box over more GPUs or use message='sender'")
+
+
+class _EncodeProcessDecodeFn(torch.autograd.Function):
+    """Whole-model forward/backward over the C ABI; owns every saved activation."""
+
+    @staticmethod
+    def forward(ctx, plan: _Plan, senders, transpose_fn, x, edge_attr, *params):
+        p, M, k, prec = plan, plan.n_steps, plan.k, plan.precision
+        n, L = x.shape[0], plan.enc_node.out_dim
+        e_count = edge_attr.shape[0]
+        train = any(ctx.needs_input_grad[3:])
+        edge_mode = p.message == "edge"
+
+        h = ops.mlp_rows_fwd(p.enc_node, x, prec)
+        e = ops.mlp_rows_fwd(p.enc_edge, edge_attr, prec)
+        hs, aggs, e_ckpt = [h], [], {}
+        keep_e = train and edge_mode
+        s = plan.edge_ckpt_every if keep_e else 0
+        if keep_e and s == 0:
+            s = _edge_stream_plan(M, e_count * L * 4, x.device)
+        if keep_e:
+            e_ckpt[0] = e
+        for t in range(M):
+            agg = torch.empty((n, L), dtype=torch.float32, device=x.device)
+            # e^t is overwritten in place unless it is a checkpoint the backward will need
+            e_next = torch.empty_like(e) if (keep_e and t % s == 0) else e
+            if edge_mode:
+                ops.mp_edge_fwd(p.proc_edge[t], h, e, senders, k, e_next, agg, prec)
+            else:
+                ops.mp_edge_fwd(p.proc_edge[t], h, e, senders, k, e_next, None, prec)
+                ops.aggregate_senders(h, senders, k, agg)
+            # inference updates h in place: a node tile only reads its own rows of h
+            h_next = torch.empty_like(h) if train else h
+            ops.mp_node_fwd(p.proc_node[t], h, agg, h_next, prec)
+            h, e = h_next, e_next
+            if train:
+                hs.append(h)
+                aggs.append(agg)
+            if keep_e and (t + 1) % s == 0 and t + 1 < M:
+                e_ckpt[t + 1] = e
+        acc = ops.mlp_rows_fwd(p.dec_acc, h, prec)
+        temp = ops.mlp_rows_fwd(p.dec_temp, h, prec)
+
+        if train:
+            ctx.plan, ctx.senders, ctx.transpose_fn = plan, senders, transpose_fn
+            ctx.x, ctx.edge_attr = x, edge_attr
+            ctx.hs, ctx.aggs, ctx.e_ckpt, ctx.s = hs, aggs, e_ckpt, s
+            ctx.n_params = len(params)
+        return acc, temp
+
+    @staticmethod
+    def backward(ctx, d_acc, d_temp):
+        p: _Plan = ctx.plan
+        M, k, prec = p.n_steps, p.k, p.precision
+        senders = ctx.senders
+        hs, aggs = ctx.hs, ctx.aggs
+        edge_mode = p.message == "edge"
+        grads: List[Optional[torch.Tensor]] = [None] * ctx.n_params
+        index_of = {id(mp): first for mp, first in p.groups}
+
+        def put(mp: MlpParams, tensors):
+            first = index_of[id(mp)]
+            for i, g in enumerate(tensors):
+                grads[first + i] = g
+
+        n, L = hs[0].shape
+        d_acc = d_acc.contiguous() if d_acc is not None else torch.zeros((n, p.dec_acc.out_dim), device=hs[0].device)
+        d_temp = d_temp.contiguous() if d_temp is not None else torch.zeros((n, 1), device=hs[0].device)
+
+        g_acc, dh_a = ops.mlp_rows_bwd(p.dec_acc, hs[M], d_acc, True, prec)
+        g_temp, dh_t = ops.mlp_rows_bwd(p.dec_temp, hs[M], d_temp, True, prec)
+        put(p.dec_acc, g_acc)
+        put(p.dec_temp, g_temp)
+        dh = dh_a.add_(dh_t)
+        de = None
+        rowptr, perm = ctx.transpose_fn()
+
+        def step_backward(t, e_t, dh, de):
+            dh_new = torch.empty_like(dh)
+            dagg = torch.empty_like(dh)
+            put(p.proc_node[t], ops.mp_node_bwd(p.proc_node[t], hs[t], aggs[t], dh, dh_new, dagg, prec))
+            if edge_mode:
+                de_new = torch.empty_like(e_t)
+                gs = torch.empty_like(e_t)
+                put(p.proc_edge[t], ops.mp_edge_bwd(p.proc_edge[t], hs[t], e_t, senders, k, de, dagg, de_new,
+                                                    dh_new, gs, prec))
+                ops.scatter_to_senders(gs, False, rowptr, perm, k, dh_new)
+                return dh_new, de_new
+            ops.scatter_to_senders(dagg, True, rowptr, perm, k, dh_new)
+            return dh_new, None
+
+        if edge_mode:
+            s = ctx.s
+            t = M - 1
+            while t >= 0:
+                a = (t // s) * s
+                seg = {a: ctx.e_ckpt[a]}
+                for u in range(a, t):                         # recompute e^{a+1..t}
+                    nxt = torch.empty_like(seg[u])
+                    ops.mp_edge_fwd(p.proc_edge[u], hs[u], seg[u], senders, k, nxt, None, prec)
+                    seg[u + 1] = nxt
+                for u in range(t, a - 1, -1):
+                    dh, de = step_backward(u, seg[u], dh, de)
+                    seg.pop(u + 1, None)
+                ctx.e_ckpt.pop(a, None)
+                t = a - 1
+        else:
+            for t in range(M - 1, -1, -1):
+                dh, de = step_backward(t, None, dh, None)
+
+        need_dx, need_dea = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        g_en, dx = ops.mlp_rows_bwd(p.enc_node, ctx.x, dh, need_dx, prec)
+        put(p.enc_node, g_en)
+        dea = None
+        if edge_mode:
+            g_ee, dea = ops.mlp_rows_bwd(p.enc_edge, ctx.edge_attr, de, need_dea, prec)
+            put(p.enc_edge, g_ee)
+        ctx.hs = ctx.aggs = ctx.e_ckpt = None
+        return (None, None, None, dx, dea, *grads)
+
+
+class EncodeProcessDecode(nn.Module):
+    """Encode-process-decode Interaction Network (graph_network.py:108-164), B200-native.
+
+    Constructor arguments as the reference; the keyword-only extras select kernel behaviour:
+      num_neighbors  optional hint (k is otherwise read from the graph: E / N)
+      message        "sender" (reference-actual, default) | "edge" (intended Interaction Network)
+      precision      "fp32" (FP32 SIMT, <= 1e-5 parity) | "bf16x3" | "bf16" (tcgen05 tensor cores)
+    """
+
+    def __init__(self, latent_size: int, mlp_hidden_size: int, mlp_num_hidden_layers: int,
+                 num_message_passing_steps: int, output_size: int, *, num_neighbors: Optional[int] = None,
+                 message: str = "sender", precision: str = "fp32", edge_ckpt_every: int = 0):
+        super().__init__()
+        if message not in ("sender", "edge"):
+            raise ValueError("message must be 'sender' or 'edge'")
+        if precision not in ops.PREC:
+            raise ValueError(f"precision must be one of {sorted(ops.PREC)}")
+        self._latent_size = latent_size
+        self._mlp_hidden_size = mlp_hidden_size
+        self._mlp_num_hidden_layers = mlp_num_hidden_layers
+        self._num_message_passing_steps = num_message_passing_steps
+        self._output_size = output_size
+        self.num_neighbors = num_neighbors
+        self.message = message
+        self.precision = precision
+        self.edge_ckpt_every = edge_ckpt_every
+
+        def mlp_ln():
+            return nn.Sequential(build_mlp(mlp_hidden_size, mlp_num_hidden_layers, latent_size),
+                                 nn.LayerNorm(latent_size))
+
+        self.encoder = _NodeEdgePair(node_model=mlp_ln(), edge_model=mlp_ln())
+        self.processor = nn.ModuleList()
+        for _ in range(num_message_passing_steps):
+            edge_model = mlp_ln()                     # constructed first, registered second (as the reference)
+            node_model = mlp_ln()
+            self.processor.append(_NodeEdgePair(node_model=node_model, edge_model=edge_model))
+        self.decoder_acc = build_mlp(mlp_hidden_size, mlp_num_hidden_layers, output_size)
+        self.decoder_temp_rate = build_mlp(mlp_hidden_size, mlp_num_hidden_layers, 1)
+        self._graph_cache = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _materialize_all(self, node_in: int, edge_in: int, like: torch.Tensor) -> None:
+        L = self._latent_size
+        _materialize(self.encoder.node_model[0], node_in, like)
+        _materialize(self.encoder.edge_model[0], edge_in, like)
+        for blk in self.processor:
+            _materialize(blk.node_model[0], 2 * L, like)
+            _materialize(blk.edge_model[0], 3 * L, like)
+        _materialize(self.decoder_acc, L, like)
+        _materialize(self.decoder_temp_rate, L, like)
+
+    def _graph_tables(self, graph, n: int):
+        """int32 senders (ELL: edge e = receiver*k + rank) and a lazy sender-sorted transpose."""
+        senders = getattr(graph, "_cgnn_senders", None)
+        edge_index = graph.edge_index
+        if senders is None or senders.device != edge_index.device:
+            key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version)
+            hit = self._graph_cache.get("key") == key
+            if not hit:
+                self._graph_cache = {"key": key, "edge_index": edge_index,
+                                     "senders": ops.senders_from_edge_index(edge_index.contiguous(), n)}
+            senders = self._graph_cache["senders"]
+        k = senders.numel() // n
+        if senders.numel() != n * k or k < 1:
+            raise ValueError("cgnn: edge count is not a multiple of the node count")
+        if self.num_neighbors is not None and k != self.num_neighbors:
+            raise ValueError(f"graph has in-degree {k}, model was built with num_neighbors={self.num_neighbors}")
+        holder = {}
+
+        def transpose():
+            if "t" not in holder:
+                holder["t"] = ops.csr_transpose(senders, n)
+            return holder["t"]
+
+        return senders, k, transpose
+
+    def forward(self, input_graph) -> Dict[str, torch.Tensor]:
+        x, edge_attr = input_graph.x, input_graph.edge_attr
+        if edge_attr is None:
+            raise ValueError("edge_attr must not be None in InteractionNetwork")     # graph_network.py:86-87
+        if not x.is_cuda:
+            raise RuntimeError("cgnn EncodeProcessDecode runs on CUDA tensors only (no CPU path): "
+                               "move the graph and the model to the GPU")
+        glob = getattr(input_graph, "globals", None)
+        if glob is not None:                                                         # graph_network.py:168-173
+            x = torch.cat([x, glob.unsqueeze(0).expand(x.size(0), -1)], dim=-1)
+        x = x.float().contiguous()
+        edge_attr = edge_attr.float().contiguous()
+        self._materialize_all(x.shape[1], edge_attr.shape[1], x)
+        if next(self.parameters()).device != x.device:
+            raise RuntimeError("cgnn: model parameters and graph must live on the same CUDA device")
+
+        enc_node = _mlp_params(self.encoder.node_model[0], self.encoder.node_model[1])
+        enc_edge = _mlp_params(self.encoder.edge_model[0], self.encoder.edge_model[1])
+        proc_node = [_mlp_params(b.node_model[0], b.node_model[1]) for b in self.processor]
+        proc_edge = [_mlp_params(b.edge_model[0], b.edge_model[1]) for b in self.processor]
+        dec_acc = _mlp_params(self.decoder_acc, None)
+        dec_temp = _mlp_params(self.decoder_temp_rate, None)
+        flat: List[torch.Tensor] = []
+        groups = []
+        for mp in [enc_node, enc_edge, *proc_node, *proc_edge, dec_acc, dec_temp]:
+            groups.append((mp, len(flat)))
+            flat += mp.tensors()
+
+        n = x.shape[0]
+        senders, k, transpose = self._graph_tables(input_graph, n)
+        plan = _Plan(self._num_message_passing_steps, self.message, self.precision, k, enc_node, enc_edge,
+                     proc_node, proc_edge, dec_acc, dec_temp, groups, self.edge_ckpt_every)
+        acc, temp = _EncodeProcessDecodeFn.apply(plan, senders, transpose, x, edge_attr, *flat)
+        return {"acceleration": acc, "temp_rate": temp}

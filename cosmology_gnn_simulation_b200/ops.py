@@ -1,0 +1,258 @@
+"""Thin torch-tensor wrappers over the C ABI (include/cgnn.h).  Tensors in, tensors out; every call
+runs on the current CUDA stream of the tensors' device.  No CPU path."""
+from __future__ import annotations
+
+from ctypes import byref, c_void_p
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import CgnnMlp, CgnnMlpGrad, PREC, DISP, check, lib, ptr, require_cuda, stream_ptr, workspace
+
+
+# ------------------------------------------------------------------------------------------------
+# graph build (K1, K2)
+# ------------------------------------------------------------------------------------------------
+def knn_periodic(pos: torch.Tensor, box_size: float, k: int) -> torch.Tensor:
+    """Replaces `extend_positions_torch` + `torch_cluster.knn` (data_utils.py:148-149).
+    pos [N,3] fp32 CUDA -> ext index [N,k] int32 (c = shift*N + j), rows ascending in (d2, c)."""
+    require_cuda(pos, "pos", torch.float32)
+    n = pos.shape[0]
+    if pos.dim() != 2 or pos.shape[1] != 3:
+        raise ValueError("pos must be [N,3]")
+    out = torch.empty((n, k), dtype=torch.int32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        nbytes = lib().cgnn_knn_workspace_bytes(n)
+        ws = workspace.get(pos.device, "knn", nbytes)
+        check(lib().cgnn_knn_periodic(ptr(pos), n, float(box_size), int(k), ptr(out), ptr(ws), ws.numel(),
+                                      stream_ptr(pos.device)), "cgnn_knn_periodic")
+    return out
+
+
+def edge_features(pos: torch.Tensor, nbr_ext: torch.Tensor, box_size: float, disp: str = "raw",
+                  want_edge_index: bool = True):
+    """Replaces data_utils.py:150-164.  Returns (senders int32 [E], edge_index int64 [2,E] | None,
+    edge_attr fp32 [E,4])."""
+    require_cuda(pos, "pos", torch.float32)
+    require_cuda(nbr_ext, "nbr_ext", torch.int32)
+    n, k = nbr_ext.shape
+    e = n * k
+    senders = torch.empty(e, dtype=torch.int32, device=pos.device)
+    edge_index = torch.empty((2, e), dtype=torch.int64, device=pos.device) if want_edge_index else None
+    edge_attr = torch.empty((e, 4), dtype=torch.float32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        check(lib().cgnn_edge_features(ptr(pos), ptr(nbr_ext), n, k, float(box_size), DISP[disp], ptr(senders),
+                                       ptr(edge_index), ptr(edge_attr), stream_ptr(pos.device)),
+              "cgnn_edge_features")
+    return senders, edge_index, edge_attr
+
+
+def csr_transpose(senders: torch.Tensor, n: int):
+    """Sender-sorted transpose: (rowptr int32 [N+1], perm int32 [E])."""
+    require_cuda(senders, "senders", torch.int32)
+    e = senders.numel()
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=senders.device)
+    perm = torch.empty(e, dtype=torch.int32, device=senders.device)
+    with torch.cuda.device(senders.device):
+        nbytes = lib().cgnn_csr_transpose_workspace_bytes(n, e)
+        ws = workspace.get(senders.device, "csr", nbytes)
+        check(lib().cgnn_csr_transpose(ptr(senders), n, e, ptr(rowptr), ptr(perm), ptr(ws), ws.numel(),
+                                       stream_ptr(senders.device)), "cgnn_csr_transpose")
+    return rowptr, perm
+
+
+def senders_from_edge_index(edge_index: torch.Tensor, n: int) -> torch.Tensor:
+    """Validates the receiver-sorted fixed-in-degree layout and returns int32 senders.
+    Raises ValueError for any other graph layout (one 4-byte D2H read)."""
+    require_cuda(edge_index, "edge_index", torch.int64)
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError("edge_index must be [2,E]")
+    e = edge_index.shape[1]
+    if n <= 0 or e % n != 0 or e == 0:
+        raise ValueError(f"cgnn needs a fixed in-degree graph: E={e} is not a multiple of N={n}")
+    k = e // n
+    senders = torch.empty(e, dtype=torch.int32, device=edge_index.device)
+    bad = torch.empty(1, dtype=torch.int32, device=edge_index.device)
+    with torch.cuda.device(edge_index.device):
+        check(lib().cgnn_edge_index_to_senders(ptr(edge_index), n, k, ptr(senders), ptr(bad),
+                                               stream_ptr(edge_index.device)), "cgnn_edge_index_to_senders")
+    if int(bad.item()) != 0:
+        raise ValueError("cgnn needs the receiver-sorted k-NN layout produced by preprocess "
+                         "(edge_index[1] == arange(N).repeat_interleave(k), senders in [0,N))")
+    return senders
+
+
+# ------------------------------------------------------------------------------------------------
+# MLP descriptors
+# ------------------------------------------------------------------------------------------------
+class MlpParams:
+    """Flat view of one reference `build_mlp` (+LayerNorm): weights [out,in], biases, gamma/beta."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                 gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None):
+        self.weights = list(weights)
+        self.biases = list(biases)
+        self.gamma, self.beta = gamma, beta
+        nl = len(self.weights)
+        if not (1 <= nl <= _lib.MAX_LAYERS):
+            raise ValueError(f"cgnn supports 1..{_lib.MAX_LAYERS} Linear layers per MLP, got {nl}")
+        self.in_dim = self.weights[0].shape[1]
+        self.out_dim = self.weights[-1].shape[0]
+        self.hidden = self.weights[0].shape[0] if nl > 1 else self.out_dim
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            require_cuda(w, f"weight[{i}]", torch.float32)
+            require_cuda(b, f"bias[{i}]", torch.float32)
+            exp_in = self.in_dim if i == 0 else self.hidden
+            exp_out = self.out_dim if i == nl - 1 else self.hidden
+            if tuple(w.shape) != (exp_out, exp_in) or tuple(b.shape) != (exp_out,):
+                raise ValueError(f"layer {i}: expected weight {(exp_out, exp_in)}, got {tuple(w.shape)}")
+        if gamma is not None:
+            require_cuda(gamma, "ln.weight", torch.float32)
+            require_cuda(beta, "ln.bias", torch.float32)
+
+    def tensors(self) -> List[torch.Tensor]:
+        out = []
+        for w, b in zip(self.weights, self.biases):
+            out += [w, b]
+        if self.gamma is not None:
+            out += [self.gamma, self.beta]
+        return out
+
+    def c_struct(self) -> CgnnMlp:
+        m = CgnnMlp()
+        m.n_layers, m.in_dim, m.hidden, m.out_dim = len(self.weights), self.in_dim, self.hidden, self.out_dim
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            m.W[i] = w.data_ptr()
+            m.b[i] = b.data_ptr()
+        m.ln_gamma = None if self.gamma is None else self.gamma.data_ptr()
+        m.ln_beta = None if self.beta is None else self.beta.data_ptr()
+        return m
+
+    def new_grads(self):
+        """(CgnnMlpGrad, [grad tensors in `tensors()` order])"""
+        g = CgnnMlpGrad()
+        outs = []
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            gw, gb = torch.empty_like(w), torch.empty_like(b)
+            g.W[i], g.b[i] = gw.data_ptr(), gb.data_ptr()
+            outs += [gw, gb]
+        if self.gamma is not None:
+            gg, gb = torch.empty_like(self.gamma), torch.empty_like(self.beta)
+            g.ln_gamma, g.ln_beta = gg.data_ptr(), gb.data_ptr()
+            outs += [gg, gb]
+        return g, outs
+
+
+def _bwd_ws(mlp_c: CgnnMlp, device):
+    nbytes = lib().cgnn_mlp_bwd_workspace_bytes(byref(mlp_c))
+    if nbytes < 0:
+        check(-1, "cgnn_mlp_bwd_workspace_bytes")
+    return workspace.get(device, "mlp_bwd", nbytes)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3/K6 rows, K4/K5 message passing
+# ------------------------------------------------------------------------------------------------
+def mlp_rows_fwd(p: MlpParams, x: torch.Tensor, precision: str = "fp32") -> torch.Tensor:
+    require_cuda(x, "x", torch.float32)
+    out = torch.empty((x.shape[0], p.out_dim), dtype=torch.float32, device=x.device)
+    m = p.c_struct()
+    with torch.cuda.device(x.device):
+        check(lib().cgnn_mlp_rows_fwd(byref(m), ptr(x), x.shape[0], ptr(out), PREC[precision], stream_ptr(x.device)),
+              "cgnn_mlp_rows_fwd")
+    return out
+
+
+def mlp_rows_bwd(p: MlpParams, x: torch.Tensor, dout: torch.Tensor, need_dx: bool, precision: str = "fp32"):
+    require_cuda(dout, "dout", torch.float32)
+    m = p.c_struct()
+    g, grads = p.new_grads()
+    dx = torch.empty_like(x) if need_dx else None
+    with torch.cuda.device(x.device):
+        ws = _bwd_ws(m, x.device)
+        check(lib().cgnn_mlp_rows_bwd(byref(m), byref(g), ptr(x), x.shape[0], ptr(dout), ptr(dx), ptr(ws),
+                                      ws.numel(), PREC[precision], stream_ptr(x.device)), "cgnn_mlp_rows_bwd")
+    return grads, dx
+
+
+# When a list, every cgnn_mp_edge_fwd launch (the dominant kernel) is bracketed by CUDA events on the
+# launching stream and (start, end) is appended: bench.py reads the per-launch durations from here.
+EDGE_FWD_EVENTS = None
+
+
+def mp_edge_fwd(p: MlpParams, h, e_in, senders, k: int, e_out, agg_edge, precision: str = "fp32"):
+    m = p.c_struct()
+    with torch.cuda.device(h.device):
+        ev = None
+        if EDGE_FWD_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(h.device))
+        check(lib().cgnn_mp_edge_fwd(byref(m), ptr(h), ptr(e_in), ptr(senders), h.shape[0], k, ptr(e_out),
+                                     ptr(agg_edge), PREC[precision], stream_ptr(h.device)), "cgnn_mp_edge_fwd")
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(h.device))
+            EDGE_FWD_EVENTS.append(ev)
+
+
+def aggregate_senders(h, senders, k: int, agg):
+    with torch.cuda.device(h.device):
+        check(lib().cgnn_aggregate_senders(ptr(h), ptr(senders), h.shape[0], k, h.shape[1], ptr(agg),
+                                           stream_ptr(h.device)), "cgnn_aggregate_senders")
+
+
+def mp_node_fwd(p: MlpParams, h, agg, h_out, precision: str = "fp32"):
+    m = p.c_struct()
+    with torch.cuda.device(h.device):
+        check(lib().cgnn_mp_node_fwd(byref(m), ptr(h), ptr(agg), h.shape[0], ptr(h_out), PREC[precision],
+                                     stream_ptr(h.device)), "cgnn_mp_node_fwd")
+
+
+def mp_node_bwd(p: MlpParams, h, agg, dh_next, dh, dagg, precision: str = "fp32"):
+    m = p.c_struct()
+    g, grads = p.new_grads()
+    with torch.cuda.device(h.device):
+        ws = _bwd_ws(m, h.device)
+        check(lib().cgnn_mp_node_bwd(byref(m), byref(g), ptr(h), ptr(agg), ptr(dh_next), h.shape[0], ptr(dh),
+                                     ptr(dagg), ptr(ws), ws.numel(), PREC[precision], stream_ptr(h.device)),
+              "cgnn_mp_node_bwd")
+    return grads
+
+
+def mp_edge_bwd(p: MlpParams, h, e_in, senders, k: int, de_next, dagg, de, dh, gs, precision: str = "fp32"):
+    m = p.c_struct()
+    g, grads = p.new_grads()
+    with torch.cuda.device(h.device):
+        ws = _bwd_ws(m, h.device)
+        check(lib().cgnn_mp_edge_bwd(byref(m), byref(g), ptr(h), ptr(e_in), ptr(senders), h.shape[0], k,
+                                     ptr(de_next), ptr(dagg), ptr(de), ptr(dh), ptr(gs), ptr(ws), ws.numel(),
+                                     PREC[precision], stream_ptr(h.device)), "cgnn_mp_edge_bwd")
+    return grads
+
+
+def scatter_to_senders(src, per_receiver: bool, rowptr, perm, k: int, dh):
+    with torch.cuda.device(dh.device):
+        check(lib().cgnn_scatter_to_senders(ptr(src), int(per_receiver), ptr(rowptr), ptr(perm), dh.shape[0], k,
+                                            dh.shape[1], ptr(dh), stream_ptr(dh.device)), "cgnn_scatter_to_senders")
+
+
+# ------------------------------------------------------------------------------------------------
+# K6 loss
+# ------------------------------------------------------------------------------------------------
+def loss_fwd_bwd(acc, temp, y_acc, y_temp, graph_ptr, num_graphs: int, dt: float, w_acc: float, w_temp: float,
+                 w_mom: float, want_grads: bool = True):
+    """Returns (losses[4] device tensor = total, acc_mse, temp_mse, momentum; d_acc | None; d_temp | None)."""
+    for name, t in (("acc", acc), ("temp", temp), ("y_acc", y_acc), ("y_temp", y_temp)):
+        require_cuda(t, name, torch.float32)
+    n, out_dim = acc.shape
+    losses = torch.empty(4, dtype=torch.float32, device=acc.device)
+    d_acc = torch.empty_like(acc) if want_grads else None
+    d_temp = torch.empty_like(temp) if want_grads else None
+    with torch.cuda.device(acc.device):
+        nbytes = lib().cgnn_loss_workspace_bytes(n, num_graphs)
+        ws = workspace.get(acc.device, "loss", nbytes)
+        check(lib().cgnn_loss_fwd_bwd(ptr(acc), ptr(temp), ptr(y_acc), ptr(y_temp), ptr(graph_ptr), n, out_dim,
+                                      num_graphs, float(dt), float(w_acc), float(w_temp), float(w_mom),
+                                      ptr(losses), ptr(d_acc), ptr(d_temp), ptr(ws), ws.numel(),
+                                      stream_ptr(acc.device)), "cgnn_loss_fwd_bwd")
+    return losses, d_acc, d_temp

@@ -1,0 +1,167 @@
+/* cgnn.h -- C ABI of libcgnn.so: the B200 (sm_100a) Interaction-Network hot path.
+ *
+ * The reference (mattpan-peregrinus/Cosmology_GNN_Simulation) has no FFI of its own: its
+ * boundary is two Python modules.  Each entry point below names the reference lines it
+ * replaces.  All functions
+ *   - are extern "C", take plain device pointers + sizes + a cudaStream_t (passed as void*),
+ *   - return 0 on success or a negative cgnn_status; cgnn_last_error() gives the message,
+ *   - never allocate device memory: the caller owns every buffer, including workspaces whose
+ *     size is given by the matching *_workspace_bytes() query,
+ *   - are asynchronous on `stream` and deterministic (no floating-point atomics).
+ *
+ * Layouts: all matrices row-major and contiguous; node latents h[N][L], edge latents e[E][L]
+ * with E = N*k and edge id = receiver*k + rank (the reference's k-NN always yields this
+ * receiver-sorted fixed-in-degree layout, data_utils.py:149-152); weights are torch
+ * nn.Linear layout W[out][in]; indices int32 on the device.
+ */
+#ifndef CGNN_H
+#define CGNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    CGNN_OK = 0,
+    CGNN_ERR_INVALID = -1,     /* bad argument (shape, null pointer, unsupported size) */
+    CGNN_ERR_CUDA = -2,        /* a CUDA runtime call or launch failed */
+    CGNN_ERR_WORKSPACE = -3,   /* workspace too small */
+    CGNN_ERR_UNSUPPORTED = -4  /* configuration not implemented by this build */
+} cgnn_status;
+
+typedef void* cgnn_stream;    /* cudaStream_t */
+
+#define CGNN_MAX_LAYERS 4      /* Linear layers per MLP = mlp_num_hidden_layers + 1 */
+
+/* One `build_mlp` (+ optional LayerNorm) of the reference: graph_network.py:15-32,133-135. */
+typedef struct {
+    int32_t n_layers;                   /* number of Linear layers (>= 1) */
+    int32_t in_dim, hidden, out_dim;    /* widths: in -> hidden x (n_layers-1) -> out */
+    const float* W[CGNN_MAX_LAYERS];    /* W[l]: [out_l][in_l] */
+    const float* b[CGNN_MAX_LAYERS];    /* b[l]: [out_l] */
+    const float* ln_gamma;              /* [out_dim] or NULL: no LayerNorm (decoders) */
+    const float* ln_beta;
+} cgnn_mlp;
+
+/* Gradient destinations, same shapes as cgnn_mlp; written (=), not accumulated. */
+typedef struct {
+    float* W[CGNN_MAX_LAYERS];
+    float* b[CGNN_MAX_LAYERS];
+    float* ln_gamma;
+    float* ln_beta;
+} cgnn_mlp_grad;
+
+typedef enum { CGNN_MSG_SENDER = 0, CGNN_MSG_EDGE = 1 } cgnn_message;
+typedef enum { CGNN_DISP_RAW = 0, CGNN_DISP_MIN_IMAGE = 1 } cgnn_disp_mode;
+typedef enum {
+    CGNN_PREC_FP32 = 0,        /* FP32 SIMT FMA everywhere (<= 1e-5 parity mode) */
+    CGNN_PREC_BF16X3 = 1,      /* tcgen05 tensor cores, bf16 hi/lo split operands (3 MMAs), FP32 accum/storage */
+    CGNN_PREC_BF16 = 2         /* tcgen05, single bf16 pass (fastest; ~1e-2, outside the parity bar) */
+} cgnn_precision;
+
+const char* cgnn_last_error(void);
+const char* cgnn_version(void);
+/* number of kernels launched by this library in this process so far (for bench `gpu_launches`) */
+int64_t cgnn_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  periodic k-NN  -- replaces extend_positions_torch + torch_cluster.knn + index remap,
+ *     data_utils.py:148-152 (and :9-33).
+ * pos[N][3] fp32 in [0, box] (closed).  nbr_ext[N][k] int32 receives, for each query i, the k
+ * nearest of the 27N ghost-extended candidates c = s*N + j (s = shift index, x slowest), sorted
+ * ascending under the total order (d2, c), d2 the fp32 distance of SURVEY App. A.2.
+ * Requires 1 <= k <= 32 and 27*N >= k.
+ */
+int64_t cgnn_knn_workspace_bytes(int64_t n);
+int cgnn_knn_periodic(const float* pos, int64_t n, float box, int32_t k, int32_t* nbr_ext,
+                      void* workspace, int64_t workspace_bytes, cgnn_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  graph products -- replaces data_utils.py:150-164.
+ * From nbr_ext: senders[E] int32 (= c mod N); optional edge_index[2][E] int64
+ * (row 0 sender, row 1 receiver; pass NULL to skip); edge_attr[E][4] = (dx,dy,dz,|d|) with
+ * d = pos[sender] - pos[receiver] (RAW, the reference's behaviour) or the minimum image
+ * d = fl(pos[sender] + shift_s) - pos[receiver].
+ */
+int cgnn_edge_features(const float* pos, const int32_t* nbr_ext, int64_t n, int32_t k, float box,
+                       int32_t disp_mode, int32_t* senders, int64_t* edge_index, float* edge_attr,
+                       cgnn_stream stream);
+
+/* Sender-sorted transpose of the receiver-sorted graph (needed for the deterministic d/dh[sender]):
+ * rowptr[N+1], perm[E] = edge ids grouped by sender, ascending inside each group. */
+int64_t cgnn_csr_transpose_workspace_bytes(int64_t n, int64_t n_edges);
+int cgnn_csr_transpose(const int32_t* senders, int64_t n, int64_t n_edges, int32_t* rowptr,
+                       int32_t* perm, void* workspace, int64_t workspace_bytes, cgnn_stream stream);
+
+/* Checks that an edge_index[2][E] int64 has the receiver-sorted fixed-in-degree layout
+ * (row 1 == e / k, senders in [0,N)) and writes senders as int32.  *bad_flag (device int32) is
+ * set to 0, then to 1 if the layout does not hold. */
+int cgnn_edge_index_to_senders(const int64_t* edge_index, int64_t n, int32_t k, int32_t* senders,
+                               int32_t* bad_flag, cgnn_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3/K6  row-wise MLP (+LayerNorm) -- GraphIndependent.forward (graph_network.py:52-64) and the
+ * decoders (graph_network.py:151-152,158-159).   out[r] = [LN](MLP(x[r])).
+ */
+int cgnn_mlp_rows_fwd(const cgnn_mlp* mlp, const float* x, int64_t rows, float* out,
+                      int32_t precision, cgnn_stream stream);
+/* dx may be NULL.  Parameter gradients are written to `grad`. */
+int64_t cgnn_mlp_bwd_workspace_bytes(const cgnn_mlp* mlp);
+int cgnn_mlp_rows_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const float* x, int64_t rows,
+                      const float* dout, float* dx, void* workspace, int64_t workspace_bytes,
+                      int32_t precision, cgnn_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  one message-passing step, forward -- InteractionNetwork.forward + the residuals,
+ *     graph_network.py:83-101,177-183.
+ *  edge phase:  u_e = LN(MLP_e([h[s_e] | h[r_e] | e]));  e_out = e + u_e;
+ *               agg_edge[i] = sum over the k in-edges of i of u_e (rank order), or NULL to skip
+ *  sender aggregation (reference-actual message): agg[i] = sum_r h[senders[i*k+r]]
+ *  node phase:  u_n = LN(MLP_n([h | agg]));  h_out = h + u_n
+ */
+int cgnn_mp_edge_fwd(const cgnn_mlp* edge_mlp, const float* h, const float* e_in,
+                     const int32_t* senders, int64_t n, int32_t k, float* e_out, float* agg_edge,
+                     int32_t precision, cgnn_stream stream);
+int cgnn_aggregate_senders(const float* h, const int32_t* senders, int64_t n, int32_t k,
+                           int32_t latent, float* agg, cgnn_stream stream);
+int cgnn_mp_node_fwd(const cgnn_mlp* node_mlp, const float* h, const float* agg, int64_t n,
+                     float* h_out, int32_t precision, cgnn_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  one message-passing step, backward (activations recomputed inside the tile).
+ *  node phase: given dh_next = dL/dh^{t+1}:  dh = dh_next + dIn[:, :L];  dagg = dIn[:, L:]
+ *  edge phase (message = edge): given de_next = dL/de^{t+1} (NULL = zero) and dagg:
+ *      dU = de_next + dagg[receiver];  de = de_next + dIn[:, 2L:];
+ *      dh[receiver] += sum_rank dIn[:, L:2L];  gs[e] = dIn[:, :L]  (per-edge sender gradient)
+ *  sender scatter: dh[j] += sum over edges e with sender j (perm order) of src[e]   (src = gs,
+ *      stride L) or of dagg[e / k] (message = sender).
+ */
+int cgnn_mp_node_bwd(const cgnn_mlp* node_mlp, const cgnn_mlp_grad* grad, const float* h,
+                     const float* agg, const float* dh_next, int64_t n, float* dh, float* dagg,
+                     void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
+int cgnn_mp_edge_bwd(const cgnn_mlp* edge_mlp, const cgnn_mlp_grad* grad, const float* h,
+                     const float* e_in, const int32_t* senders, int64_t n, int32_t k,
+                     const float* de_next, const float* dagg, float* de, float* dh, float* gs,
+                     void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
+int cgnn_scatter_to_senders(const float* src, int32_t src_is_per_receiver, const int32_t* rowptr,
+                            const int32_t* perm, int64_t n, int32_t k, int32_t latent, float* dh,
+                            cgnn_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6  loss -- train.py:107-118,255-260.  Deterministic two-stage reductions.
+ *  losses[4] = {total, acc_mse, temp_mse, momentum};  writes the gradient seeds d_acc, d_temp
+ *  (of `total`) when non-NULL.  graph_ptr[G+1] int32 = node offsets of the batched graphs
+ *  (PyG `Batch.ptr`; NULL = one graph).
+ */
+int64_t cgnn_loss_workspace_bytes(int64_t n, int32_t num_graphs);
+int cgnn_loss_fwd_bwd(const float* acc, const float* temp, const float* y_acc, const float* y_temp,
+                      const int32_t* graph_ptr, int64_t n, int32_t out_dim, int32_t num_graphs, float dt,
+                      float w_acc, float w_temp, float w_mom, float* losses, float* d_acc,
+                      float* d_temp, void* workspace, int64_t workspace_bytes, cgnn_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGNN_H */

@@ -1,0 +1,378 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference fixtures.
+
+Tolerances (BASELINE.json north_star): neighbour lists bit-exact; FP32 mode rel-L2 <= 1e-5 for
+accelerations, dU/dt and gradients; tensor-core mode (bf16x3) rel-L2 <= 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_metadata, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-5
+TOL_TC = 1e-3
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1: k-NN, bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n,k", [
+    ("uniform", 300, 8), ("uniform", 4096, 16), ("uniform", 20000, 32), ("clustered", 5000, 16),
+    ("clustered", 20000, 32), ("lattice", 512, 8), ("lattice", 4096, 16), ("lattice", 3375, 32),
+    ("uniform", 1000, 1), ("uniform", 777, 5), ("uniform", 32768, 16),
+])
+def test_knn_bit_exact(kind, n, k):
+    from cosmology_gnn_simulation_b200 import ops, synthetic
+    from oracle import knn_ref
+    pos = synthetic.positions(n, kind, 1.0, seed=3)
+    got = ops.knn_periodic(torch.from_numpy(pos).to(_dev()), 1.0, k).cpu().numpy().astype(np.int64)
+    ref = knn_ref.knn_kdtree(pos, 1.0, k)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref), f"{(got != ref).any(axis=1).sum()} of {n} rows differ"
+
+
+def test_knn_edge_cases():
+    from cosmology_gnn_simulation_b200 import ops
+    from oracle import knn_ref
+    cases = [
+        (np.array([[0.1, 0.2, 0.3], [0.9, 0.9, 0.9]], dtype=np.float32), 16),          # 27N barely >= k
+        (np.array([[0.5, 0.5, 0.5]], dtype=np.float32), 27),                            # one particle, all images
+        (np.array([[0.5, 0.5, 0.5], [0.5, 0.5, 0.5], [1.0, 0.0, 1.0], [0.0, 0.0, 0.0]], dtype=np.float32), 4),
+        (np.array([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [np.nextafter(np.float32(1.0), np.float32(0.0))] * 3,
+                   [0.25, 0.75, 1.0]], dtype=np.float32), 8),                           # 0, box, box-ulp
+    ]
+    rng = np.random.default_rng(0)
+    void = rng.random((400, 3), dtype=np.float32) * 0.05                                # one tight clump, huge void
+    void[-1] = [0.6, 0.6, 0.6]
+    cases.append((void, 16))
+    for pos, k in cases:
+        got = ops.knn_periodic(torch.from_numpy(pos).to(_dev()), 1.0, k).cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, knn_ref.knn_brute(pos, 1.0, k))
+    # other box sizes
+    pos = (rng.random((3000, 3), dtype=np.float32) * np.float32(7.5)).astype(np.float32)
+    got = ops.knn_periodic(torch.from_numpy(pos).to(_dev()), 7.5, 16).cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, knn_ref.knn_kdtree(pos, 7.5, 16))
+
+
+def test_knn_rejects_bad_arguments():
+    from cosmology_gnn_simulation_b200 import ops
+    pos = torch.rand(10, 3, device=_dev())
+    with pytest.raises(RuntimeError, match="k <= 32"):
+        ops.knn_periodic(pos, 1.0, 33)
+    with pytest.raises(RuntimeError, match="27"):
+        ops.knn_periodic(pos[:1], 1.0, 28)
+
+
+def test_knn_large_properties():
+    """BASELINE config-3 size (2.1 M particles, k=32): size-independent properties."""
+    from cosmology_gnn_simulation_b200 import ops, synthetic
+    from oracle import knn_ref
+    n, k = 128 ** 3, 32
+    pos = synthetic.positions(n, "uniform", 1.0, seed=0)
+    d = torch.from_numpy(pos).to(_dev())
+    nbr = ops.knn_periodic(d, 1.0, k)
+    nbr2 = ops.knn_periodic(d, 1.0, k)
+    assert torch.equal(nbr, nbr2)                                        # deterministic
+    ext = nbr.long()
+    assert torch.equal(ext[:, 0], 13 * n + torch.arange(n, device=_dev()))   # rank 0 = self (zero shift)
+    assert int(ext.min()) >= 0 and int(ext.max()) < 27 * n
+    srt, _ = torch.sort(ext, dim=1)
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                       # no candidate twice
+    # distances ascending along each row
+    sid, j = ext // n, ext % n
+    shift = torch.stack([(sid // 9) - 1, (sid // 3) % 3 - 1, sid % 3 - 1], dim=-1).float()
+    dd = (d[j] + shift) - d[:, None, :]
+    d2 = (dd[..., 0] * dd[..., 0] + dd[..., 1] * dd[..., 1]) + dd[..., 2] * dd[..., 2]
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all())
+    # a random sample of rows against the exhaustive oracle restricted to those queries
+    rows = np.random.default_rng(1).choice(n, 64, replace=False)
+    extp, _ = knn_ref.extend_positions(pos, 1.0)
+    for r in rows:
+        q = pos[r]
+        df = (extp - q).astype(np.float32)
+        sq = (df * df).astype(np.float32)
+        dist = ((sq[:, 0] + sq[:, 1]).astype(np.float32) + sq[:, 2]).astype(np.float32)
+        kth = np.partition(dist, k - 1)[k - 1]
+        cand = np.nonzero(dist <= kth)[0]
+        order = np.lexsort((cand, dist[cand]))
+        assert np.array_equal(cand[order[:k]], ext[r].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 + preprocess
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["pre_uniform", "pre_clustered_noise"])
+def test_preprocess_matches_reference_fixture(name):
+    from cosmology_gnn_simulation_b200.data_utils import preprocess
+    g = load_golden(name)
+    md = golden_metadata(g)
+    coords, energy = torch.from_numpy(g["coords"]), torch.from_numpy(g["energy"])
+    torch.manual_seed(int(g["seed"]))
+    out = preprocess(coords[:5], energy[:5], md, coords[5:6].clone(), energy[5:6].clone(),
+                     noise_std=float(g["noise_std"]), num_neighbors=int(g["k"]), dt=md["dt"],
+                     box_size=md["box_size"])
+    assert np.array_equal(torch.rand(4).numpy(), g["rng_after"])
+    assert out.edge_index.is_cuda and out.edge_index.dtype == torch.int64
+    assert np.array_equal(out.edge_index.cpu().numpy(), g["edge_index"])          # bit-exact graph
+    for key in ["x", "y_acc", "y_temp_rate", "pos", "dt", "box_size"]:
+        assert np.array_equal(getattr(out, key).cpu().numpy(), g[key]), key
+    ea = out.edge_attr.cpu().numpy()
+    assert np.array_equal(ea[:, :3], g["edge_attr"][:, :3])                       # raw displacement: exact
+    # |d|: one fp32 sqrt of a 3-term sum, <= 2 ulp from ATen's CPU reduction
+    assert np.all(np.abs(ea[:, 3] - g["edge_attr"][:, 3]) <= 2.4e-7 * np.abs(g["edge_attr"][:, 3]))
+    assert torch.equal(out._cgnn_senders.long(), out.edge_index[0])
+
+
+def test_min_image_edge_mode_and_transpose():
+    from cosmology_gnn_simulation_b200 import ops, synthetic
+    n, k = 5000, 16
+    pos = torch.from_numpy(synthetic.positions(n, "uniform", 1.0, seed=9)).to(_dev())
+    nbr = ops.knn_periodic(pos, 1.0, k)
+    s_raw, ei, ea_raw = ops.edge_features(pos, nbr, 1.0, "raw")
+    s_min, _, ea_min = ops.edge_features(pos, nbr, 1.0, "min_image", want_edge_index=False)
+    assert torch.equal(s_raw, s_min)
+    assert float(ea_min[:, 3].max()) < 0.5 * 3 ** 0.5 and float(ea_raw[:, 3].max()) > 0.5
+    assert torch.equal(ei[1], torch.arange(n, device=_dev()).repeat_interleave(k))
+    # sender-sorted transpose: a permutation of the edges, grouped by sender, ascending inside a row
+    rowptr, perm = ops.csr_transpose(s_raw, n)
+    assert int(rowptr[0]) == 0 and int(rowptr[-1]) == n * k
+    assert torch.equal(torch.sort(perm.long())[0], torch.arange(n * k, device=_dev()))
+    snd_of_perm = s_raw.long()[perm.long()]
+    assert bool((snd_of_perm[1:] >= snd_of_perm[:-1]).all())
+    same = snd_of_perm[1:] == snd_of_perm[:-1]
+    assert bool((perm[1:][same] > perm[:-1][same]).all())
+    counts = torch.bincount(s_raw.long(), minlength=n)
+    assert torch.equal(rowptr[1:].long() - rowptr[:-1].long(), counts)
+    # generic edge_index -> senders path, and rejection of a non-ELL graph
+    assert torch.equal(ops.senders_from_edge_index(ei, n), s_raw)
+    bad = ei.clone()
+    bad[1, 5] = 3
+    with pytest.raises(ValueError, match="receiver-sorted"):
+        ops.senders_from_edge_index(bad, n)
+
+
+# ------------------------------------------------------------------------------------------------
+# model forward / backward
+# ------------------------------------------------------------------------------------------------
+def _load_model(g, **kw):
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    L, H, nh, M, out = [int(v) for v in g["cfg"]]
+    model = EncodeProcessDecode(L, H, nh, M, out, **kw)
+    model.load_state_dict({str(k): torch.from_numpy(g["sd/" + str(k)]) for k in g["sd_keys"]})
+    return model.to(_dev())
+
+
+def _graph_from(g, requires_grad=False):
+    from cosmology_gnn_simulation_b200.graph import Data
+    d = _dev()
+    x = torch.from_numpy(g["x"]).to(d).requires_grad_(requires_grad)
+    return Data(x=x, edge_index=torch.from_numpy(g["edge_index"]).to(d),
+                edge_attr=torch.from_numpy(g["edge_attr"]).to(d),
+                y_acc=torch.from_numpy(g["y_acc"]).to(d), y_temp_rate=torch.from_numpy(g["y_temp_rate"]).to(d))
+
+
+@pytest.mark.parametrize("name", ["model_tiny", "model_small", "model_deepmlp"])
+def test_model_matches_reference_fixture_fp32(name):
+    """Reference-actual semantics (message='sender'): outputs, loss, every gradient, grad-None census."""
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    g = load_golden(name)
+    model = _load_model(g, message="sender", precision="fp32")
+    graph = _graph_from(g, requires_grad=True)
+    pred = model(graph)
+    assert rel_l2(pred["acceleration"].detach().cpu(), g["acceleration"]) < TOL_FP32
+    assert rel_l2(pred["temp_rate"].detach().cpu(), g["temp_rate"]) < TOL_FP32
+    ls = combined_loss(pred, graph, float(g["dt"]), 1.0, 1.0, 0.1)
+    assert abs(ls["loss"].item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    assert abs(ls["acc_loss"].item() - float(g["acc_loss"])) < 1e-5 * abs(float(g["acc_loss"]))
+    assert abs(ls["temp_rate_loss"].item() - float(g["temp_loss"])) < 1e-5 * abs(float(g["temp_loss"]))
+    assert abs(ls["momentum_loss"].item() - float(g["mom_loss"])) < 1e-4 * abs(float(g["mom_loss"])) + 1e-12
+    ls["loss"].backward()
+    none = set(str(k) for k in g["grad_none"])
+    for k, p in model.named_parameters():
+        if k in none:
+            assert p.grad is None, k                     # dead edge stream, like the reference (F2)
+        else:
+            assert rel_l2(p.grad.cpu(), g["grad/" + k]) < TOL_FP32 * 5, k
+    assert rel_l2(graph.x.grad.cpu(), g["grad_x"]) < TOL_FP32 * 5
+
+
+@pytest.mark.parametrize("message", ["sender", "edge"])
+@pytest.mark.parametrize("cfg", [
+    dict(n=1000, k=16, L=64, H=64, nh=2, M=3),
+    dict(n=333, k=8, L=128, H=128, nh=2, M=2),
+    dict(n=257, k=5, L=32, H=96, nh=1, M=2),
+    dict(n=200, k=32, L=256, H=256, nh=2, M=1),
+])
+def test_model_matches_oracle_fp32(message, cfg):
+    _compare_with_oracle(message, cfg, "fp32", TOL_FP32)
+
+
+def _compare_with_oracle(message, cfg, precision, tol, ckpt=0, seed=0):
+    from cosmology_gnn_simulation_b200 import ops, synthetic
+    from cosmology_gnn_simulation_b200.graph import Data
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from oracle import knn_ref, model_ref
+    n, k, L, H, nh, M = cfg["n"], cfg["k"], cfg["L"], cfg["H"], cfg["nh"], cfg["M"]
+    pos = synthetic.positions(n, "uniform", 1.0, seed=seed)
+    ext = knn_ref.knn_kdtree(pos, 1.0, k)
+    ei = torch.from_numpy(knn_ref.edge_index_from_ext(ext, n))
+    p = torch.from_numpy(pos)
+    d = p[ei[0]] - p[ei[1]]
+    ea = torch.cat([d, d.norm(dim=-1, keepdim=True)], dim=-1)
+    gen = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(n, 17, generator=gen)
+    ya, yt = torch.randn(n, 3, generator=gen), torch.randn(n, 1, generator=gen)
+    params = model_ref.init_params(L, H, nh, M, 3, seed=seed)
+
+    # oracle in fp64: the truth both fp32 implementations are measured against
+    p64 = {k_: v.double().requires_grad_(True) for k_, v in params.items()}
+    x64 = x.double().requires_grad_(True)
+    ea64 = ea.double().requires_grad_(True)
+    o = model_ref.forward(p64, x64, ei, ea64, nh, M, message=message)
+    lo = model_ref.loss(o["acceleration"], o["temp_rate"], ya.double(), yt.double(), 0.01, w_mom=0.1)
+    lo["loss"].backward()
+
+    dev = _dev()
+    model = EncodeProcessDecode(L, H, nh, M, 3, message=message, precision=precision, edge_ckpt_every=ckpt)
+    model.load_state_dict(params)
+    model = model.to(dev)
+    xg = x.to(dev).requires_grad_(True)
+    eag = ea.to(dev).requires_grad_(True)
+    graph = Data(x=xg, edge_index=ei.to(dev), edge_attr=eag, y_acc=ya.to(dev), y_temp_rate=yt.to(dev))
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    pred = model(graph)
+    ls = combined_loss(pred, graph, 0.01, 1.0, 1.0, 0.1)
+    ls["loss"].backward()
+    assert rel_l2(pred["acceleration"].detach().cpu(), o["acceleration"].detach()) < tol
+    assert rel_l2(pred["temp_rate"].detach().cpu(), o["temp_rate"].detach()) < tol
+    assert abs(ls["loss"].item() - lo["loss"].item()) < 10 * tol * abs(lo["loss"].item())
+    gtol = tol * 5
+    for name, prm in model.named_parameters():
+        ref = p64[name].grad
+        if ref is None or float(ref.abs().max()) == 0.0:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
+        else:
+            assert prm.grad is not None, name
+            assert rel_l2(prm.grad.cpu(), ref) < gtol, (name, rel_l2(prm.grad.cpu(), ref))
+    assert rel_l2(xg.grad.cpu(), x64.grad) < gtol
+    if message == "edge":
+        assert rel_l2(eag.grad.cpu(), ea64.grad) < gtol
+    return model, graph
+
+
+def test_edge_stream_checkpointing_gives_identical_gradients():
+    """message='edge': recomputing e^t segment by segment must not change a single bit."""
+    cfg = dict(n=400, k=8, L=64, H=64, nh=2, M=5)
+    grads = []
+    for ckpt in (1, 2, 5):
+        model, _ = _compare_with_oracle("edge", cfg, "fp32", TOL_FP32, ckpt=ckpt)
+        grads.append([p.grad.clone() for p in model.parameters()])
+    for other in grads[1:]:
+        for a, b in zip(grads[0], other):
+            assert torch.equal(a, b)
+
+
+def test_forward_backward_deterministic_and_inference_path():
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    g = load_golden("model_small")
+    outs = []
+    for _ in range(2):
+        model = _load_model(g, message="edge")
+        graph = _graph_from(g)
+        pred = model(graph)
+        combined_loss(pred, graph, 0.01, 1.0, 1.0, 0.1)["loss"].backward()
+        outs.append((pred["acceleration"].detach().clone(), [p.grad.clone() for p in model.parameters()]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+    # no_grad / eval path (in-place latents) gives the same numbers as the training path
+    model = _load_model(g, message="sender").eval()
+    graph = _graph_from(g)
+    with torch.no_grad():
+        a = model(graph)["acceleration"]
+    b = model(graph)["acceleration"]
+    assert torch.equal(a, b.detach())
+    assert rel_l2(a.cpu(), g["acceleration"]) < TOL_FP32
+
+
+def test_batched_graphs_equal_separate_graphs():
+    from cosmology_gnn_simulation_b200 import synthetic
+    from cosmology_gnn_simulation_b200.data_utils import preprocess
+    from cosmology_gnn_simulation_b200.graph import Batch
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    from oracle import model_ref
+    graphs = []
+    for seed, n in ((1, 500), (2, 700)):
+        box = synthetic.make_box(n, "uniform", seed=seed)
+        md = box["metadata"]
+        graphs.append(preprocess(box["Coordinates"][:5], box["InternalEnergy"][:5], md, box["Coordinates"][5:6],
+                                 box["InternalEnergy"][5:6], num_neighbors=8, dt=md["dt"], box_size=md["box_size"]))
+    model = EncodeProcessDecode(32, 32, 2, 2, 3).to(_dev())
+    singles = [model(gr) for gr in graphs]
+    batch = Batch.from_data_list(graphs).to(_dev())
+    both = model(batch)
+    cat = torch.cat([s["acceleration"] for s in singles])
+    assert torch.equal(both["acceleration"], cat)
+    ls = combined_loss(both, batch, 0.01, 1.0, 1.0, 0.5)
+    ref = model_ref.loss(both["acceleration"].detach().cpu().double(), both["temp_rate"].detach().cpu().double(),
+                         batch.y_acc.cpu().double(), batch.y_temp_rate.cpu().double(), 0.01,
+                         batch=batch.batch.cpu(), num_graphs=2, w_mom=0.5)
+    for a, b in (("loss", "loss"), ("acc_loss", "acc_loss"), ("temp_rate_loss", "temp_rate_loss"),
+                 ("momentum_loss", "momentum_loss")):
+        assert abs(ls[a].item() - ref[b].item()) < 2e-5 * abs(ref[b].item()) + 1e-9, a
+
+
+def test_loss_gradients_match_autograd():
+    from cosmology_gnn_simulation_b200 import ops
+    from oracle import model_ref
+    n, G = 10000, 3
+    gen = torch.Generator().manual_seed(0)
+    acc = torch.randn(n, 3, generator=gen, dtype=torch.float64).requires_grad_(True)
+    temp = torch.randn(n, 1, generator=gen, dtype=torch.float64).requires_grad_(True)
+    ya, yt = torch.randn(n, 3, generator=gen, dtype=torch.float64), torch.randn(n, 1, generator=gen, dtype=torch.float64)
+    sizes = [3000, 5000, 2000]
+    batch = torch.repeat_interleave(torch.arange(G), torch.tensor(sizes))
+    ref = model_ref.loss(acc, temp, ya, yt, 0.01, batch=batch, num_graphs=G, w_acc=0.7, w_temp=1.3, w_mom=2.0)
+    ref["loss"].backward()
+    d = _dev()
+    ptr = torch.tensor([0, 3000, 8000, 10000], dtype=torch.int32, device=d)
+    losses, da, dt_ = ops.loss_fwd_bwd(acc.detach().float().to(d), temp.detach().float().to(d), ya.float().to(d),
+                                       yt.float().to(d), ptr, G, 0.01, 0.7, 1.3, 2.0)
+    assert abs(losses[0].item() - ref["loss"].item()) < 1e-5 * abs(ref["loss"].item())
+    assert abs(losses[3].item() - ref["momentum_loss"].item()) < 1e-4 * abs(ref["momentum_loss"].item())
+    assert rel_l2(da.cpu(), acc.grad) < 1e-5 and rel_l2(dt_.cpu(), temp.grad) < 1e-5
+
+
+def test_config1_one_step_inference_parity():
+    """BASELINE configs[0]: 4096 particles, k=16, latent 64, 5 MP steps, forward only."""
+    from cosmology_gnn_simulation_b200 import synthetic
+    from cosmology_gnn_simulation_b200.data_utils import preprocess
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from oracle import model_ref, preprocess_ref
+    box = synthetic.make_box(4096, "uniform", seed=0)
+    md = box["metadata"]
+    torch.manual_seed(0)
+    ref_g = preprocess_ref.preprocess(box["Coordinates"][:5], box["InternalEnergy"][:5], md, num_neighbors=16,
+                                      dt=md["dt"], box_size=md["box_size"], knn="kdtree")
+    torch.manual_seed(0)
+    g = preprocess(box["Coordinates"][:5], box["InternalEnergy"][:5], md, num_neighbors=16, dt=md["dt"],
+                   box_size=md["box_size"])
+    assert torch.equal(g.edge_index.cpu(), ref_g["edge_index"])
+    assert torch.equal(g.x.cpu(), ref_g["x"])
+    params = model_ref.init_params(64, 64, 2, 5, 3, seed=0)
+    model = EncodeProcessDecode(64, 64, 2, 5, 3)
+    model.load_state_dict(params)
+    model = model.to(_dev()).eval()
+    with torch.no_grad():
+        pred = model(g)
+    ref = model_ref.forward({k: v.double() for k, v in params.items()}, ref_g["x"].double(), ref_g["edge_index"],
+                            ref_g["edge_attr"].double(), 2, 5, message="sender")
+    assert rel_l2(pred["acceleration"].cpu(), ref["acceleration"]) < TOL_FP32
+    assert rel_l2(pred["temp_rate"].cpu(), ref["temp_rate"]) < TOL_FP32

@@ -1,0 +1,95 @@
+"""CPU: host-side logic of the boundary modules (no kernels)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from cosmology_gnn_simulation_b200.graph import Batch, Data
+from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+from cosmology_gnn_simulation_b200 import data_utils
+
+
+def test_state_dict_keys_match_reference():
+    for name in ["model_tiny", "model_deepmlp"]:
+        g = load_golden(name)
+        L, H, nh, M, out = [int(v) for v in g["cfg"]]
+        m = EncodeProcessDecode(L, H, nh, M, out)
+        assert list(m.state_dict().keys()) == [str(k) for k in g["sd_keys"]]
+        # optimizer can be built before the first forward, like train.py:173-183
+        torch.optim.Adam(m.parameters(), lr=1e-3)
+        sd = {str(k): torch.from_numpy(g["sd/" + str(k)]) for k in g["sd_keys"]}
+        m.load_state_dict(sd)
+        for k, v in m.state_dict().items():
+            assert np.array_equal(v.numpy(), g["sd/" + k])
+
+
+def test_lazy_first_layers_materialise_with_reference_shapes():
+    m = EncodeProcessDecode(128, 128, 2, 2, 3)
+    m._materialize_all(17, 4, torch.empty(1))
+    sd = m.state_dict()
+    assert tuple(sd["encoder.node_model.0.0.weight"].shape) == (128, 17)
+    assert tuple(sd["encoder.edge_model.0.0.weight"].shape) == (128, 4)
+    assert tuple(sd["processor.1.edge_model.0.0.weight"].shape) == (128, 384)
+    assert tuple(sd["processor.1.node_model.0.0.weight"].shape) == (128, 256)
+    assert tuple(sd["decoder_acc.4.weight"].shape) == (3, 128)
+    assert tuple(sd["decoder_temp_rate.4.weight"].shape) == (1, 128)
+
+
+def test_batch_offsets_and_ptr():
+    def g(n, k):
+        return Data(x=torch.randn(n, 17), edge_index=torch.stack([torch.randint(0, n, (n * k,)),
+                    torch.arange(n).repeat_interleave(k)]), edge_attr=torch.randn(n * k, 4),
+                    y_acc=torch.randn(n, 3), y_temp_rate=torch.randn(n, 1), pos=torch.rand(n, 3),
+                    dt=torch.tensor([0.01]), box_size=torch.tensor([1.0]),
+                    _cgnn_senders=None, _cgnn_k=k)
+    a, b = g(5, 2), g(7, 2)
+    a._cgnn_senders = a.edge_index[0].int()
+    b._cgnn_senders = b.edge_index[0].int()
+    batch = Batch.from_data_list([a, b])
+    assert batch.num_graphs == 2 and batch.x.shape[0] == 12
+    assert batch.ptr.tolist() == [0, 5, 12]
+    assert torch.equal(batch.batch, torch.tensor([0] * 5 + [1] * 7))
+    assert torch.equal(batch.edge_index[1], torch.arange(12).repeat_interleave(2))
+    assert torch.equal(batch.edge_index[0][10:], b.edge_index[0] + 5)
+    assert torch.equal(batch._cgnn_senders.long(), batch.edge_index[0])
+    assert batch.dt.shape == (2,)
+
+
+def test_extend_positions_matches_reference_order():
+    pos = torch.rand(5, 3)
+    ext, mapping = data_utils.extend_positions_torch(pos, 2.0)
+    assert ext.shape == (135, 3) and mapping.shape == (135,)
+    assert torch.equal(ext[13 * 5:14 * 5], pos)                      # zero shift is block 13
+    assert torch.equal(ext[0:5], pos + torch.tensor([-2.0, -2.0, -2.0]))
+    assert torch.equal(ext[5:10], pos + torch.tensor([-2.0, -2.0, 0.0]))   # z fastest
+    assert torch.equal(mapping, torch.arange(5).repeat(27))
+
+
+def test_noise_generators_match_oracle_and_rng_consumption():
+    """The oracle's noise path is pinned by the reference fixture `pre_clustered_noise`
+    (tests/test_oracle_golden.py); the product generators must draw the same numbers."""
+    from oracle import preprocess_ref
+    g = load_golden("pre_clustered_noise")
+    coords = torch.from_numpy(g["coords"])[:5].permute(1, 0, 2)
+    energy = torch.from_numpy(g["energy"])[:5].permute(1, 0, 2)
+    for std in (0.0, 3e-4):
+        torch.manual_seed(3)
+        a = data_utils.generate_position_noise(coords, std, 1.0, 0.01)
+        b = data_utils.generate_temperature_noise(energy, std, torch.tensor(0.7), 0.01)
+        after = torch.rand(2)
+        torch.manual_seed(3)
+        vel = preprocess_ref._min_image_(coords[:, 1:] - coords[:, :-1], 1.0) / 0.01
+        a_ref = preprocess_ref._random_walk_noise(vel, std, 0.01)
+        b_ref = preprocess_ref._random_walk_noise((energy[:, 1:] - energy[:, :-1]) / 0.01, std * torch.tensor(0.7), 0.01)
+        assert torch.equal(a, a_ref) and torch.equal(b, b_ref)
+        assert torch.equal(after, torch.rand(2))          # draws happen even for std == 0
+        assert a.shape == coords.shape and float(a[:, 0].abs().max()) == 0.0
+
+
+def test_preprocess_without_gpu_raises():
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    g = load_golden("pre_uniform")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        data_utils.preprocess(torch.from_numpy(g["coords"])[:5], torch.from_numpy(g["energy"])[:5],
+                              {"temp_rate_std": 1.0}, dt=0.01, box_size=1.0)
