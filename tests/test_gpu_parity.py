@@ -230,13 +230,21 @@ def _compare_with_oracle(message, cfg, precision, tol, ckpt=0, seed=0):
     ya, yt = torch.randn(n, 3, generator=gen), torch.randn(n, 1, generator=gen)
     params = model_ref.init_params(L, H, nh, M, 3, seed=seed)
 
-    # oracle in fp64: the truth both fp32 implementations are measured against
-    p64 = {k_: v.double().requires_grad_(True) for k_, v in params.items()}
-    x64 = x.double().requires_grad_(True)
-    ea64 = ea.double().requires_grad_(True)
-    o = model_ref.forward(p64, x64, ei, ea64, nh, M, message=message)
-    lo = model_ref.loss(o["acceleration"], o["temp_rate"], ya.double(), yt.double(), 0.01, w_mom=0.1)
-    lo["loss"].backward()
+    # oracle in fp64 = the truth; the same oracle in fp32 = how far the reference's own CPU arithmetic
+    # sits from that truth.  A ReLU pre-activation within fp32 rounding of zero flips its gate in *any*
+    # fp32 implementation and moves gradients by O(1e-4) on these small graphs (DESIGN.md "ReLU gates"),
+    # so the gradient bar is: within tol of the truth, or no further from it than 2x the CPU fp32 path.
+    def run_oracle(dtype):
+        pp = {k_: v.to(dtype).requires_grad_(True) for k_, v in params.items()}
+        xx = x.to(dtype).requires_grad_(True)
+        ee = ea.to(dtype).requires_grad_(True)
+        oo = model_ref.forward(pp, xx, ei, ee, nh, M, message=message)
+        ll = model_ref.loss(oo["acceleration"], oo["temp_rate"], ya.to(dtype), yt.to(dtype), 0.01, w_mom=0.1)
+        ll["loss"].backward()
+        return pp, xx, ee, oo, ll
+
+    p64, x64, ea64, o, lo = run_oracle(torch.float64)
+    p32, x32, ea32, _, _ = run_oracle(torch.float32)
 
     dev = _dev()
     model = EncodeProcessDecode(L, H, nh, M, 3, message=message, precision=precision, edge_ckpt_every=ckpt)
@@ -253,16 +261,22 @@ def _compare_with_oracle(message, cfg, precision, tol, ckpt=0, seed=0):
     assert rel_l2(pred["temp_rate"].detach().cpu(), o["temp_rate"].detach()) < tol
     assert abs(ls["loss"].item() - lo["loss"].item()) < 10 * tol * abs(lo["loss"].item())
     gtol = tol * 5
+
+    def grad_ok(got, ref64, ref32, what):
+        err = rel_l2(got.cpu(), ref64)
+        floor = 2.0 * rel_l2(ref32, ref64)
+        assert err < max(gtol, floor), (what, err, floor)
+
     for name, prm in model.named_parameters():
         ref = p64[name].grad
         if ref is None or float(ref.abs().max()) == 0.0:
             assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
         else:
             assert prm.grad is not None, name
-            assert rel_l2(prm.grad.cpu(), ref) < gtol, (name, rel_l2(prm.grad.cpu(), ref))
-    assert rel_l2(xg.grad.cpu(), x64.grad) < gtol
+            grad_ok(prm.grad, ref, p32[name].grad, name)
+    grad_ok(xg.grad, x64.grad, x32.grad, "x")
     if message == "edge":
-        assert rel_l2(eag.grad.cpu(), ea64.grad) < gtol
+        grad_ok(eag.grad, ea64.grad, ea32.grad, "edge_attr")
     return model, graph
 
 
