@@ -31,13 +31,14 @@ int num_sms() {
 }
 
 // tensor-core implementations (mp_tc.cu); return CGNN_ERR_UNSUPPORTED for shapes they do not cover
-int tc_mlp_fwd(MlpTask& a, int precision, cudaStream_t s);
+int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s);
+int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision);
 int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s);
 int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp);
 
-static int run_fwd(MlpTask& a, int precision, cudaStream_t s) {
+static int run_fwd(MlpTask& a, int precision, cudaStream_t s, void* ws = nullptr, int64_t wsb = 0) {
     if (precision == CGNN_PREC_FP32) return simt_mlp_fwd(a, s);
-    if (precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16) return tc_mlp_fwd(a, precision, s);
+    if (precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16) return tc_mlp_fwd(a, precision, ws, wsb, s);
     set_error("unknown precision %d", precision);
     return CGNN_ERR_INVALID;
 }
@@ -92,9 +93,15 @@ static int check_latent(const cgnn_mlp* mlp, int mult, const char* who) {
     return CGNN_OK;
 }
 
+extern "C" int64_t cgnn_mp_edge_fwd_workspace_bytes(const cgnn_mlp* mlp, int64_t n, int32_t precision) {
+    if (mlp_validate(mlp, "cgnn_mp_edge_fwd_workspace_bytes")) return -1;
+    if (precision == CGNN_PREC_FP32) return 0;
+    return tc_edge_fwd_workspace(mlp, n, precision);
+}
+
 extern "C" int cgnn_mp_edge_fwd(const cgnn_mlp* mlp, const float* h, const float* e_in, const int32_t* senders,
-                                int64_t n, int32_t k, float* e_out, float* agg_edge, int32_t precision,
-                                cgnn_stream stream) {
+                                int64_t n, int32_t k, float* e_out, float* agg_edge, void* workspace,
+                                int64_t workspace_bytes, int32_t precision, cgnn_stream stream) {
     int rc = mlp_validate(mlp, "cgnn_mp_edge_fwd");
     if (rc) return rc;
     if ((rc = check_latent(mlp, 3, "cgnn_mp_edge_fwd"))) return rc;
@@ -103,7 +110,7 @@ extern "C" int cgnn_mp_edge_fwd(const cgnn_mlp* mlp, const float* h, const float
     MlpTask a{};
     a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.k = k; a.L = mlp->out_dim;
     a.h = h; a.e_in = e_in; a.senders = senders; a.out = e_out; a.agg_out = agg_edge;
-    return run_fwd(a, precision, (cudaStream_t)stream);
+    return run_fwd(a, precision, (cudaStream_t)stream, workspace, workspace_bytes);
 }
 
 extern "C" int cgnn_aggregate_senders(const float* h, const int32_t* senders, int64_t n, int32_t k, int32_t latent,

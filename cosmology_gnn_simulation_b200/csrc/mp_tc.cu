@@ -5,8 +5,8 @@
 
 namespace cgnn {
 
-int tc_mlp_fwd(MlpTask& a, int precision, cudaStream_t s) {
-    (void)a; (void)precision; (void)s;
+int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s) {
+    (void)a; (void)precision; (void)ws; (void)wsb; (void)s;
     set_error("tensor-core precision modes are not built yet");
     return CGNN_ERR_UNSUPPORTED;
 }
@@ -16,5 +16,6 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
     return CGNN_ERR_UNSUPPORTED;
 }
 int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp) { (void)mlp; return 0; }
+int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) { (void)mlp; (void)n; (void)precision; return 0; }
 
 }  // namespace cgnn

@@ -188,8 +188,13 @@ def mp_edge_fwd(p: MlpParams, h, e_in, senders, k: int, e_out, agg_edge, precisi
         if EDGE_FWD_EVENTS is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream(h.device))
+        nbytes = lib().cgnn_mp_edge_fwd_workspace_bytes(byref(m), h.shape[0], PREC[precision])
+        if nbytes < 0:
+            check(-1, "cgnn_mp_edge_fwd_workspace_bytes")
+        ws = workspace.get(h.device, "edge_fwd", nbytes) if nbytes > 0 else None
         check(lib().cgnn_mp_edge_fwd(byref(m), ptr(h), ptr(e_in), ptr(senders), h.shape[0], k, ptr(e_out),
-                                     ptr(agg_edge), PREC[precision], stream_ptr(h.device)), "cgnn_mp_edge_fwd")
+                                     ptr(agg_edge), ptr(ws), 0 if ws is None else ws.numel(), PREC[precision],
+                                     stream_ptr(h.device)), "cgnn_mp_edge_fwd")
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(h.device))
             EDGE_FWD_EVENTS.append(ev)

@@ -121,9 +121,12 @@ int cgnn_mlp_rows_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const floa
  *  sender aggregation (reference-actual message): agg[i] = sum_r h[senders[i*k+r]]
  *  node phase:  u_n = LN(MLP_n([h | agg]));  h_out = h + u_n
  */
+/* workspace of cgnn_mp_edge_fwd (0 for CGNN_PREC_FP32; the tensor-core modes stage split-bf16 weight
+ * images and the per-node layer-1 partial products there) */
+int64_t cgnn_mp_edge_fwd_workspace_bytes(const cgnn_mlp* edge_mlp, int64_t n, int32_t precision);
 int cgnn_mp_edge_fwd(const cgnn_mlp* edge_mlp, const float* h, const float* e_in,
                      const int32_t* senders, int64_t n, int32_t k, float* e_out, float* agg_edge,
-                     int32_t precision, cgnn_stream stream);
+                     void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
 int cgnn_aggregate_senders(const float* h, const int32_t* senders, int64_t n, int32_t k,
                            int32_t latent, float* agg, cgnn_stream stream);
 int cgnn_mp_node_fwd(const cgnn_mlp* node_mlp, const float* h, const float* agg, int64_t n,
