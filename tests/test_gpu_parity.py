@@ -235,9 +235,9 @@ def _compare_with_oracle(message, cfg, precision, tol, ckpt=0, seed=0):
     # fp32 implementation and moves gradients by O(1e-4) on these small graphs (DESIGN.md "ReLU gates"),
     # so the gradient bar is: within tol of the truth, or no further from it than 2x the CPU fp32 path.
     def run_oracle(dtype):
-        pp = {k_: v.to(dtype).requires_grad_(True) for k_, v in params.items()}
-        xx = x.to(dtype).requires_grad_(True)
-        ee = ea.to(dtype).requires_grad_(True)
+        pp = {k_: v.detach().to(dtype).clone().requires_grad_(True) for k_, v in params.items()}
+        xx = x.detach().to(dtype).clone().requires_grad_(True)
+        ee = ea.detach().to(dtype).clone().requires_grad_(True)
         oo = model_ref.forward(pp, xx, ei, ee, nh, M, message=message)
         ll = model_ref.loss(oo["acceleration"], oo["temp_rate"], ya.to(dtype), yt.to(dtype), 0.01, w_mom=0.1)
         ll["loss"].backward()
