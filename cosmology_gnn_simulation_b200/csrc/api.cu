@@ -33,18 +33,27 @@ int num_sms() {
 // tensor-core implementations (mp_tc.cu); return CGNN_ERR_UNSUPPORTED for shapes they do not cover
 int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s);
 int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision);
+int64_t tc_node_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision);
 int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s);
 int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp);
 
+static bool is_tc(int precision) { return precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16; }
+
 static int run_fwd(MlpTask& a, int precision, cudaStream_t s, void* ws = nullptr, int64_t wsb = 0) {
-    if (precision == CGNN_PREC_FP32) return simt_mlp_fwd(a, s);
+    // encoder / decoder rows always run the FP32 kernels (see cgnn.h: the tensor-core modes cover the processor)
+    if (precision == CGNN_PREC_FP32 || (is_tc(precision) && a.mode == MODE_ROWS)) return simt_mlp_fwd(a, s);
     if (precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16) return tc_mlp_fwd(a, precision, ws, wsb, s);
     set_error("unknown precision %d", precision);
     return CGNN_ERR_INVALID;
 }
 static int run_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s) {
-    if (precision == CGNN_PREC_FP32) return simt_mlp_bwd(a, g, ws, wsb, s);
-    if (precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16) return tc_mlp_bwd(a, g, ws, wsb, precision, s);
+    if (precision == CGNN_PREC_FP32 || (is_tc(precision) && a.mode == MODE_ROWS)) return simt_mlp_bwd(a, g, ws, wsb, s);
+    if (is_tc(precision)) {
+        // the tensor-core backward covers what tc_mlp_bwd implements; everything else recomputes and
+        // differentiates with the FP32 kernels (same math, higher precision)
+        int rc = tc_mlp_bwd(a, g, ws, wsb, precision, s);
+        return rc == CGNN_ERR_UNSUPPORTED ? simt_mlp_bwd(a, g, ws, wsb, s) : rc;
+    }
     set_error("unknown precision %d", precision);
     return CGNN_ERR_INVALID;
 }
@@ -106,7 +115,7 @@ extern "C" int cgnn_mp_edge_fwd(const cgnn_mlp* mlp, const float* h, const float
     if (rc) return rc;
     if ((rc = check_latent(mlp, 3, "cgnn_mp_edge_fwd"))) return rc;
     CGNN_CHECK_ARG(h && e_in && senders && e_out && n >= 1, "cgnn_mp_edge_fwd: bad arguments");
-    CGNN_CHECK_ARG(k >= 1 && k <= 32, "cgnn_mp_edge_fwd: need 1 <= k <= 32");
+    CGNN_CHECK_ARG(k >= 1 && k <= 64, "cgnn_mp_edge_fwd: need 1 <= k <= 64");
     MlpTask a{};
     a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.k = k; a.L = mlp->out_dim;
     a.h = h; a.e_in = e_in; a.senders = senders; a.out = e_out; a.agg_out = agg_edge;
@@ -120,8 +129,14 @@ extern "C" int cgnn_aggregate_senders(const float* h, const int32_t* senders, in
     return simt_aggregate_senders(h, senders, n, k, latent, agg, (cudaStream_t)stream);
 }
 
+extern "C" int64_t cgnn_mp_node_fwd_workspace_bytes(const cgnn_mlp* mlp, int64_t n, int32_t precision) {
+    if (mlp_validate(mlp, "cgnn_mp_node_fwd_workspace_bytes")) return -1;
+    if (precision == CGNN_PREC_FP32) return 0;
+    return tc_node_fwd_workspace(mlp, n, precision);
+}
+
 extern "C" int cgnn_mp_node_fwd(const cgnn_mlp* mlp, const float* h, const float* agg, int64_t n, float* h_out,
-                                int32_t precision, cgnn_stream stream) {
+                                void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream) {
     int rc = mlp_validate(mlp, "cgnn_mp_node_fwd");
     if (rc) return rc;
     if ((rc = check_latent(mlp, 2, "cgnn_mp_node_fwd"))) return rc;
@@ -129,7 +144,7 @@ extern "C" int cgnn_mp_node_fwd(const cgnn_mlp* mlp, const float* h, const float
     MlpTask a{};
     a.mlp = mlp_to_dev(mlp); a.mode = MODE_NODE; a.n = n; a.L = mlp->out_dim;
     a.h = h; a.agg = agg; a.out = h_out;
-    return run_fwd(a, precision, (cudaStream_t)stream);
+    return run_fwd(a, precision, (cudaStream_t)stream, workspace, workspace_bytes);
 }
 
 extern "C" int cgnn_mp_node_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const float* h, const float* agg,

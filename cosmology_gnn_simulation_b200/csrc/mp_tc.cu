@@ -1,21 +1,648 @@
-// Tensor-core (tcgen05) implementations of the MLP tiles.  Placeholder dispatch until the
-// kernels land: reports CGNN_ERR_UNSUPPORTED so callers fail loudly instead of falling back.
+// Tensor-core (tcgen05) implementation of the fused processor MLP tiles, forward.
+//
+// One kernel, `tc_chain_fwd<NS>`, runs a chain of Linear layers over 256-row tiles on a CTA PAIR
+// (cta_group::2, UMMA 256x128x16, BF16 operands, FP32 accumulators in TMEM):
+//
+//   * weights live in shared memory for the whole (persistent) kernel as BF16 images in the UMMA
+//     K-major layout -- split by output row between the two CTAs of the pair, so one CTA holds
+//     64 x 128 x {hi, lo} per weight block;
+//   * activations never touch shared memory: the A operand of every layer is written to TMEM by the
+//     epilogue warps (tcgen05.st, two BF16 per 32-bit column) and read from there by the MMA (the "TS"
+//     form); the accumulator is read back with tcgen05.ld, one row per thread;
+//   * NS = 3 ("bf16x3"): every FP32 value x is split into hi = bf16(x), lo = bf16(x - hi) and a product
+//     is hi*hi + lo*hi + hi*lo (three MMAs, ~2^-17 relative error, FP32-like results);
+//     NS = 1 ("bf16"): single pass;
+//   * two tiles are in flight per CTA (TMEM columns [0,256) and [256,512)): while the tensor core works
+//     on one, the four epilogue warps of the other do bias/ReLU/split or the LayerNorm epilogue;
+//   * the edge phase uses W1 = [W1s | W1r | W1e] (graph_network.py:89 concat order): P_s = h W1s^T and
+//     P_r = h W1r^T + b1 are computed once per NODE by this same kernel (a 1-layer chain) and the
+//     per-edge layer 1 is e W1e^T + P_s[sender] + P_r[receiver]  (5 L^2 -> 3 L^2 MACs per edge);
+//   * inputs stream in through TMA (2-D tensor maps, 16-column boxes, 64-byte swizzle), the sender rows
+//     of P_s through per-row bulk copies, outputs leave through TMA stores.
+//
+// Reference semantics: InteractionNetwork.forward + residuals, graph_network.py:83-101,177-183.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "mlp_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cgnn {
+namespace {
+
+using namespace ptx;
+
+constexpr int TC_H = 128;                 // latent = hidden = out width handled by this kernel
+constexpr int TC_THREADS = 320;           // 8 epilogue warps (2 groups of 4) + producer warp + MMA warp
+constexpr int CH = 16;                    // columns per streamed chunk (64-byte rows, SWIZZLE_64B)
+constexpr int NCH = TC_H / CH;            // 8 chunks per 128-column tile
+constexpr int CH_BYTES = 128 * CH * 4;    // 8192
+constexpr int NRING = 3;                  // input ring depth
+constexpr int WIMG = 64 * TC_H * 2;       // bytes of one weight image half (64 output rows x 128 k, bf16)
+constexpr int PS_STRIDE = TC_H * 4 + 16;  // padded row stride of the gathered P_s rows (conflict-free row reads)
+constexpr int MAX_BLOCKS = 4;             // weight blocks (MMA phases) per tile
+constexpr float LN_EPS = 1e-5f;
+
+struct TcParams {
+    int64_t n_rows;             // rows of the stream (edges or nodes)
+    int64_t n_pair_tiles;       // ceil(n_rows / 256)
+    int n_in;                   // input phases (1: in0; 2: in0 then in1)
+    int n_layers;               // Linear layers (1 or 3)
+    int k;                      // > 0: edge mode, rows per receiver
+    int has_ln;
+    const float* residual;      // [n_rows][128] added to the result (nullable)
+    float* agg_out;             // edge mode: [n_rows / k][128] per-receiver sum of the result before the residual (nullable)
+    const int32_t* senders;     // edge mode
+    const float* Ps;            // edge mode: [N][128]
+    const float* Pr;            // edge mode: [N][128] (includes the layer-1 bias)
+    const uint8_t* w_images;    // [n_blocks][NSI][2 halves][WIMG]
+    const float* vec;           // [5][128]: bias of layer 1, 2, 3, gamma, beta
+};
+
+// shared-memory layout (dynamic, 1024-byte aligned base)
+struct Smem {
+    static constexpr int ring = 0;                                 // NRING * CH_BYTES
+    static constexpr int sbuf = ring + NRING * CH_BYTES;           // 2 groups * 2 * CH_BYTES
+    static constexpr int vec = sbuf + 4 * CH_BYTES;                // 5 * 128 floats
+    static constexpr int bars = vec + 5 * TC_H * 4;                // barriers (256 bytes)
+    static constexpr int weights = bars + 256;                     // n_blocks * NSI * WIMG
+};
+static_assert(Smem::weights % 128 == 0 && Smem::sbuf % 1024 == 0, "chunk buffers need 1024-byte, weight images 128-byte alignment");
+
+struct Bars {
+    uint64_t w_full;
+    // "full" barriers are per consumer group: a group only ever waits on barriers whose uses are all its own,
+    // so the phase parity it tracks can never alias a phase that belongs to the other group's tiles
+    uint64_t in_full[2][NRING], in_empty[NRING];
+    uint64_t ps_full[2], ps_empty;
+    uint64_t a_ready[2];        // used in the leader CTA: 8 arrivals (4 warps x 2 CTAs)
+    uint64_t mma_done[2];       // per CTA, one tcgen05.commit arrival
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(x0, x1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
+    lo = pack_bf16x2(x0 - h0, x1 - h1);
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// byte offset of the 16-byte piece j (0..3) of row r inside a 64-byte-swizzled chunk buffer
+__device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+template <int NS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
+             const __grid_constant__ CUtensorMap tm_out, const TcParams p) {
+    constexpr int NSI = NS == 3 ? 2 : 1;                    // weight / activation images per value (hi [, lo])
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Bars* bars = reinterpret_cast<Bars*>(smem + Smem::bars);
+    float* sVec = reinterpret_cast<float*>(smem + Smem::vec);
+    const int n_blocks = p.n_in + p.n_layers - 1;           // MMA phases per tile
+    uint8_t* sW = smem + Smem::weights;
+    uint8_t* sPs = sW + n_blocks * NSI * WIMG;              // edge mode only: 128 * PS_STRIDE
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int64_t n_it = p.n_pair_tiles > cluster_id ? (p.n_pair_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+    const bool edge = p.k > 0;
+
+    // ---- one-time setup ---------------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&bars->w_full, 1);
+        for (int i = 0; i < NRING; ++i) {
+            mbar_init(&bars->in_full[0][i], 1);
+            mbar_init(&bars->in_full[1][i], 1);
+            mbar_init(&bars->in_empty[i], 4);
+        }
+        mbar_init(&bars->ps_full[0], 1);
+        mbar_init(&bars->ps_full[1], 1);
+        mbar_init(&bars->ps_empty, 4);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->a_ready[s], 8); mbar_init(&bars->mma_done[s], 1); }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 5 * TC_H; i += TC_THREADS) sVec[i] = p.vec[i];
+    if (warp == 9) tmem_alloc<2>(&bars->tmem_base, 512);
+    if (warp == 8 && lane == 0) {
+        prefetch_tmap(&tm_in0);
+        prefetch_tmap(&tm_in1);
+        prefetch_tmap(&tm_out);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 8) {
+        // ============================ producer: weights, input chunks, sender gathers ============================
+        if (lane == 0) {
+            mbar_expect_tx(&bars->w_full, (uint32_t)(n_blocks * NSI * WIMG));
+            for (int b = 0; b < n_blocks; ++b)
+                for (int sp = 0; sp < NSI; ++sp)
+                    bulk_g2s(sW + (b * NSI + sp) * WIMG, p.w_images + ((size_t)(b * NSI + sp) * 2 + rank) * WIMG, WIMG, &bars->w_full);
+        }
+        uint32_t seq = 0;
+        for (int64_t it = 0; it < n_it; ++it) {
+            const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
+            if (lane == 0) {
+                for (int ip = 0; ip < p.n_in; ++ip)
+                    for (int q = 0; q < NCH; ++q, ++seq) {
+                        const uint32_t buf = seq % NRING, use = seq / NRING;
+                        mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 100 + buf);
+                        uint64_t* full = &bars->in_full[it & 1][buf];
+                        mbar_expect_tx(full, CH_BYTES);
+                        tma_load_2d(smem + Smem::ring + buf * CH_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CH, (int)row0, full);
+                    }
+            }
+            if (edge) {
+                int64_t valid = p.n_rows - row0;
+                valid = valid < 0 ? 0 : (valid > 128 ? 128 : valid);
+                if (lane == 0) {
+                    mbar_wait_or_trap(&bars->ps_empty, (uint32_t)((it & 1) ^ 1), 110);
+                    mbar_expect_tx(&bars->ps_full[it & 1], (uint32_t)(valid * TC_H * 4));
+                }
+                __syncwarp();
+                for (int r = lane; r < (int)valid; r += 32) {
+                    const int32_t s = p.senders[row0 + r];
+                    bulk_g2s(sPs + r * PS_STRIDE, p.Ps + (size_t)s * TC_H, TC_H * 4, &bars->ps_full[it & 1]);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ============================ MMA issuer (leader CTA, one thread) =======================================
+        if (rank == 0 && lane == 0) {
+            mbar_wait_or_trap(&bars->w_full, 0, 120);
+            const uint32_t idesc = umma_idesc_bf16(256, TC_H);
+            const uint32_t w_base = smem_u32(sW);
+            int64_t it_s[2] = {0, 1};
+            int ph_s[2] = {0, 0};
+            uint32_t par[2] = {0, 0};
+            int active = (n_it > 0) + (n_it > 1);
+            uint32_t spins = 0;
+            while (active > 0) {
+                for (int s = 0; s < 2; ++s) {
+                    if (it_s[s] >= n_it) continue;
+                    if (!mbar_try_wait(&bars->a_ready[s], par[s])) {
+                        if (++spins > (1u << 27)) { printf("cgnn: MMA issuer timeout slot %d it %lld ph %d\n", s, (long long)it_s[s], ph_s[s]); __trap(); }
+                        continue;
+                    }
+                    spins = 0;
+                    tc_fence_after_sync();
+                    const int ph = ph_s[s];
+                    const uint32_t d = tmem + s * 256;
+                    const uint32_t a_hi = d + 128, a_lo = d + 192;
+                    const uint32_t w_hi = w_base + (ph * NSI) * WIMG, w_lo = w_hi + WIMG;
+                    uint32_t acc = (ph > 0 && ph < p.n_in) ? 1u : 0u;       // later input phases accumulate into layer 1
+#pragma unroll
+                    for (int ks = 0; ks < TC_H / 16; ++ks) {
+                        umma_bf16_ts<2>(d, a_hi + ks * 8, umma_desc(w_hi + ks * 256, 128, TC_H * 16), idesc, acc);
+                        acc = 1u;
+                    }
+                    if (NS == 3) {
+#pragma unroll
+                        for (int ks = 0; ks < TC_H / 16; ++ks)
+                            umma_bf16_ts<2>(d, a_lo + ks * 8, umma_desc(w_hi + ks * 256, 128, TC_H * 16), idesc, 1u);
+#pragma unroll
+                        for (int ks = 0; ks < TC_H / 16; ++ks)
+                            umma_bf16_ts<2>(d, a_hi + ks * 8, umma_desc(w_lo + ks * 256, 128, TC_H * 16), idesc, 1u);
+                    }
+                    umma_commit<2>(&bars->mma_done[s]);
+                    par[s] ^= 1u;
+                    if (++ph_s[s] == n_blocks) {
+                        ph_s[s] = 0;
+                        it_s[s] += 2;
+                        if (it_s[s] >= n_it) --active;
+                    }
+                }
+            }
+        }
+    } else {
+        // ============================ epilogue groups: thread = row ==============================================
+        const int g = warp >> 2;                        // group = TMEM slot
+        const int wq = warp & 3;                        // lane quarter this warp may touch
+        const int r = wq * 32 + lane;                   // row inside the CTA's 128-row tile
+        const int gt = tid - g * 128;                   // thread index inside the group
+        const uint32_t tslot = tmem + ((uint32_t)(wq * 32) << 16) + g * 256;
+        const uint32_t tD = tslot, tAhi = tslot + 128, tAlo = tslot + 192;
+        uint8_t* sS = smem + Smem::sbuf + g * 2 * CH_BYTES;
+        uint32_t pm = 0;                                // parity of mma_done[g]
+        uint32_t in_par = 0;                            // bit b: parity of this group's next use of in_full[g][b]
+        const int bar_id = 1 + g;
+        mbar_wait_or_trap(&bars->w_full, 0, 130);       // a_ready from this CTA also tells the leader its weights landed
+
+        for (int64_t it = g; it < n_it; it += 2) {
+            const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
+            uint32_t seq = (uint32_t)it * (uint32_t)(NCH * p.n_in);
+            // ---- input phases: stream chunks, split, write the A operand -------------------------------------
+            for (int ip = 0; ip < p.n_in; ++ip) {
+                if (ip > 0) {                            // A is still being read by the previous phase's MMA
+                    mbar_wait_or_trap(&bars->mma_done[g], pm, 140);
+                    pm ^= 1u;
+                    tc_fence_after_sync();
+                }
+                for (int q = 0; q < NCH; ++q, ++seq) {
+                    const uint32_t buf = seq % NRING;
+                    mbar_wait_or_trap(&bars->in_full[g][buf], (in_par >> buf) & 1u, 150 + buf);
+                    in_par ^= 1u << buf;
+                    const uint8_t* src = smem + Smem::ring + buf * CH_BYTES;
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 v = *reinterpret_cast<const float4*>(src + swz64(r, j));
+                        split2(v.x, v.y, hi[2 * j], lo[2 * j]);
+                        split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
+                    tmem_st_32x32b_x8(tAhi + q * 8, hi);
+                    if (NS == 3) tmem_st_32x32b_x8(tAlo + q * 8, lo);
+                }
+                tmem_st_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&bars->a_ready[g], 0);
+            }
+            // ---- hidden layers ------------------------------------------------------------------------------------
+            for (int l = 0; l + 1 < p.n_layers; ++l) {
+                mbar_wait_or_trap(&bars->mma_done[g], pm, 160 + l);
+                pm ^= 1u;
+                tc_fence_after_sync();
+                const bool gather = edge && l == 0;
+                if (gather) mbar_wait_or_trap(&bars->ps_full[g], (uint32_t)((it >> 1) & 1), 170);
+                const float* bias = sVec + l * TC_H;
+                int64_t grow = row0 + r;
+                const float* pr_row = nullptr;
+                if (gather) {
+                    if (grow >= p.n_rows) grow = p.n_rows - 1;       // clamp (results of padded rows are never stored)
+                    pr_row = p.Pr + (size_t)(grow / p.k) * TC_H;
+                }
+#pragma unroll 1
+                for (int c0 = 0; c0 < TC_H; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32b_x32(tD + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                    if (gather) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 a = *reinterpret_cast<const float4*>(sPs + r * PS_STRIDE + (c0 + j) * 4);
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(pr_row + c0 + j));
+                            v[j] += a.x + b.x; v[j + 1] += a.y + b.y; v[j + 2] += a.z + b.z; v[j + 3] += a.w + b.w;
+                        }
+                    }
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) split2(fmaxf(v[2 * j], 0.0f), fmaxf(v[2 * j + 1], 0.0f), hi[j], lo[j]);
+                    tmem_st_32x32b_x16(tAhi + c0 / 2, hi);
+                    if (NS == 3) tmem_st_32x32b_x16(tAlo + c0 / 2, lo);
+                }
+                tmem_st_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    if (gather) mbar_arrive_local(&bars->ps_empty);
+                    mbar_arrive_cluster(&bars->a_ready[g], 0);
+                }
+            }
+            // ---- final layer: bias, LayerNorm, segmented sum, residual, store -----------------------------------
+            mbar_wait_or_trap(&bars->mma_done[g], pm, 180);
+            pm ^= 1u;
+            tc_fence_after_sync();
+            const float* bias = sVec + (p.n_layers - 1) * TC_H;
+            float mean = 0.0f, rstd = 1.0f;
+            if (p.has_ln) {
+                float s = 0.0f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TC_H; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32b_x32(tD + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s += v[j] + bias[c0 + j];
+                }
+                mean = s * (1.0f / TC_H);
+                float q2 = 0.0f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TC_H; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32b_x32(tD + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const float d = v[j] + bias[c0 + j] - mean; q2 = fmaf(d, d, q2); }
+                }
+                rstd = 1.0f / sqrtf(q2 * (1.0f / TC_H) + LN_EPS);
+            }
+            const float* gamma = sVec + 3 * TC_H;
+            const float* beta = sVec + 4 * TC_H;
+#pragma unroll 1
+            for (int q = 0; q < NCH; ++q) {
+                float v[16];
+                tmem_ld_32x32b_x16(tD + q * CH, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float u = v[j] + bias[q * CH + j];
+                    if (p.has_ln) u = (u - mean) * rstd * gamma[q * CH + j] + beta[q * CH + j];
+                    v[j] = u;
+                }
+                uint8_t* S = sS + (q & 1) * CH_BYTES;
+                if (gt == 0) bulk_wait_read<1>();            // the store that last read this buffer (chunk q-2) is done
+                named_bar_sync(bar_id, 128);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(S + swz64(r, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                named_bar_sync(bar_id, 128);
+                if (p.agg_out != nullptr) {
+                    // per-receiver sum of the k rows, rank order (deterministic): thread <-> (receiver, column)
+                    const int c = gt & 15;
+                    const int nrecv = 128 / p.k;
+                    for (int rv = gt >> 4; rv < nrecv; rv += 8) {
+                        const int64_t recv = row0 / p.k + rv;
+                        if (recv * p.k < p.n_rows) {
+                            float s = 0.0f;
+                            for (int j = 0; j < p.k; ++j) {
+                                const int rr = rv * p.k + j;
+                                s += *reinterpret_cast<const float*>(S + swz64(rr, c >> 2) + (c & 3) * 4);
+                            }
+                            p.agg_out[recv * TC_H + q * CH + c] = s;
+                        }
+                    }
+                }
+                if (p.agg_out != nullptr && p.residual != nullptr) named_bar_sync(bar_id, 128);   // agg reads u before the residual lands
+                if (p.residual != nullptr) {
+                    // coalesced: 4 threads per row (16 bytes each), 32 rows per pass
+                    const int j = gt & 3;
+#pragma unroll
+                    for (int pass = 0; pass < 4; ++pass) {
+                        const int rr = (gt >> 2) + pass * 32;
+                        const int64_t grow = row0 + rr;
+                        if (grow < p.n_rows) {
+                            const float4 e = __ldg(reinterpret_cast<const float4*>(p.residual + grow * TC_H + q * CH + j * 4));
+                            float4* dst = reinterpret_cast<float4*>(S + swz64(rr, j));
+                            float4 u = *dst;
+                            u.x += e.x; u.y += e.y; u.z += e.z; u.w += e.w;
+                            *dst = u;
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(bar_id, 128);
+                if (gt == 0) {
+                    tma_store_2d(&tm_out, S, q * CH, (int)row0);
+                    bulk_commit();
+                }
+            }
+            // D and A of this slot are free again: the next tile of this group starts with its input phase
+        }
+        if (gt == 0) bulk_wait_all<0>();
+    }
+
+    // ---- teardown -----------------------------------------------------------------------------------------
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 9) tmem_dealloc<2>(tmem, 512);
+}
+
+// Builds the shared-memory weight images: for block b, the K-major BF16 image(s) of W[:, col0 : col0+128]
+// ([128 out][ld] row-major FP32), split by output row into two halves of 64 rows.
+struct PrepBlock { const float* W; int ld; int col0; };
+struct PrepArgs {
+    PrepBlock blk[MAX_BLOCKS];
+    int n_blocks;
+    const float* vec_src[5];      // bias1, bias2, bias3, gamma, beta (nullable -> zeros / ones for gamma)
+};
+
+template <int NS>
+__global__ void tc_prep_kernel(PrepArgs a, uint8_t* __restrict__ images, float* __restrict__ vec) {
+    constexpr int NSI = NS == 3 ? 2 : 1;
+    const int b = blockIdx.y;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte piece: (n, k8)
+    if (b < a.n_blocks && idx < TC_H * (TC_H / 8)) {
+        const int n = idx / (TC_H / 8), k8 = idx % (TC_H / 8);
+        const float* src = a.blk[b].W + (size_t)n * a.blk[b].ld + a.blk[b].col0 + k8 * 8;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split2(src[2 * j], src[2 * j + 1], hi[j], lo[j]);
+        const int half = n >> 6, nl = n & 63;
+        const size_t off = (size_t)(nl >> 3) * (TC_H * 16) + (size_t)k8 * 128 + (nl & 7) * 16;
+        *reinterpret_cast<uint4*>(images + ((size_t)(b * NSI + 0) * 2 + half) * WIMG + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (NS == 3)
+            *reinterpret_cast<uint4*>(images + ((size_t)(b * NSI + 1) * 2 + half) * WIMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (b == 0 && idx < 5 * TC_H) {
+        const int v = idx / TC_H, c = idx % TC_H;
+        vec[idx] = a.vec_src[v] ? a.vec_src[v][c] : (v == 3 ? 1.0f : 0.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_row_map(CUtensorMap* m, const float* base, int64_t rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CGNN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+        CGNN_CHECK_ARG(f != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)TC_H, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)TC_H * 4};
+    cuuint32_t box[2] = {(cuuint32_t)CH, 128};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (base %p, rows %lld)", (int)r, (const void*)base, (long long)rows);
+        return CGNN_ERR_CUDA;
+    }
+    return CGNN_OK;
+}
+
+size_t chain_smem_bytes(int n_blocks, int nsi, bool edge) {
+    return (size_t)Smem::weights + (size_t)n_blocks * nsi * WIMG + (edge ? 128 * PS_STRIDE : 0);
+}
+
+struct ChainLaunch {
+    int ns;                       // 1 or 3
+    PrepArgs prep;
+    TcParams p;
+    const float* in0;
+    const float* in1;
+    float* out;
+    uint8_t* images;              // workspace: n_blocks * NSI * 2 * WIMG
+    float* vec;                   // workspace: 5 * 128 floats
+};
+
+template <int NS>
+int launch_chain_t(ChainLaunch& c, cudaStream_t stream) {
+    constexpr int NSI = NS == 3 ? 2 : 1;
+    const int n_blocks = c.prep.n_blocks;
+    dim3 pg((TC_H * (TC_H / 8) + 255) / 256, n_blocks);
+    tc_prep_kernel<NS><<<pg, 256, 0, stream>>>(c.prep, c.images, c.vec);
+    CGNN_LAUNCH_CHECK();
+    c.p.w_images = c.images;
+    c.p.vec = c.vec;
+    c.p.n_pair_tiles = (c.p.n_rows + 255) / 256;
+    CUtensorMap m0, m1, mo;
+    int rc;
+    if ((rc = make_row_map(&m0, c.in0, c.p.n_rows))) return rc;
+    if ((rc = make_row_map(&m1, c.in1 ? c.in1 : c.in0, c.p.n_rows))) return rc;
+    if ((rc = make_row_map(&mo, c.out, c.p.n_rows))) return rc;
+    const bool edge = c.p.k > 0;
+    const size_t smem = chain_smem_bytes(n_blocks, NSI, edge);
+    CGNN_CHECK_ARG(smem <= 227 * 1024, "tensor-core chain: shared memory need %zu exceeds 227 KB", smem);
+    auto kern = tc_chain_fwd<NS>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int64_t pairs = num_sms() / 2;
+    if (c.p.n_pair_tiles < pairs) pairs = c.p.n_pair_tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(pairs * 2));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CGNN_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mo, c.p));
+    count_launch();
+    return CGNN_OK;
+}
+
+int launch_chain(ChainLaunch& c, cudaStream_t stream) {
+    return c.ns == 3 ? launch_chain_t<3>(c, stream) : launch_chain_t<1>(c, stream);
+}
+
+constexpr int64_t IMG_BYTES_MAX = (int64_t)MAX_BLOCKS * 2 * 2 * WIMG;     // one chain's weight images
+constexpr int64_t VEC_BYTES = 5 * TC_H * 4;
+
+bool tc_shape_ok(const MlpDev& m, int in_mult) {
+    return m.n_layers == 3 && m.hidden == TC_H && m.out_dim == TC_H && m.in_dim == in_mult * TC_H && m.gamma != nullptr;
+}
+
+}  // namespace
+
+// workspace: [3 chains x (images + vec)] [P_s: n x 128] [P_r: n x 128]
+int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) {
+    (void)mlp; (void)precision;
+    return 3 * (IMG_BYTES_MAX + align_up(VEC_BYTES, 256)) + 2 * align_up(n * TC_H * 4, 256);
+}
+int64_t tc_node_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) {
+    (void)mlp; (void)n; (void)precision;
+    return IMG_BYTES_MAX + align_up(VEC_BYTES, 256);
+}
 
 int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s) {
-    (void)a; (void)precision; (void)ws; (void)wsb; (void)s;
-    set_error("tensor-core precision modes are not built yet");
+    const int ns = precision == CGNN_PREC_BF16X3 ? 3 : 1;
+    const MlpDev& m = a.mlp;
+    if (a.mode == MODE_EDGE) {
+        if (!tc_shape_ok(m, 3) || a.k < 1 || 128 % a.k != 0) {
+            set_error("tensor-core edge phase supports latent = hidden = 128, 2 hidden layers and k dividing 128 (got in %d hidden %d out %d layers %d k %d)",
+                      m.in_dim, m.hidden, m.out_dim, m.n_layers, a.k);
+            return CGNN_ERR_UNSUPPORTED;
+        }
+        const int64_t need = tc_edge_fwd_workspace(nullptr, a.n, precision);
+        if (ws == nullptr || wsb < need) {
+            set_error("cgnn_mp_edge_fwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
+            return CGNN_ERR_WORKSPACE;
+        }
+        Carver cv(ws);
+        uint8_t* img[3]; float* vec[3];
+        for (int i = 0; i < 3; ++i) { img[i] = cv.take<uint8_t>(IMG_BYTES_MAX); vec[i] = cv.take<float>(5 * TC_H); }
+        float* Ps = cv.take<float>(a.n * TC_H);
+        float* Pr = cv.take<float>(a.n * TC_H);
+        int rc;
+        // P_s = h W1[:, 0:L]^T ;  P_r = h W1[:, L:2L]^T + b1      (one-layer chains over the N node rows)
+        for (int which = 0; which < 2; ++which) {
+            ChainLaunch c{};
+            c.ns = ns;
+            c.prep.n_blocks = 1;
+            c.prep.blk[0] = {m.W[0], 3 * TC_H, which * TC_H};
+            c.prep.vec_src[0] = which == 1 ? m.b[0] : nullptr;
+            c.p.n_rows = a.n; c.p.n_in = 1; c.p.n_layers = 1; c.p.k = 0; c.p.has_ln = 0;
+            c.in0 = a.h; c.out = which == 0 ? Ps : Pr;
+            c.images = img[which]; c.vec = vec[which];
+            if ((rc = launch_chain(c, s))) return rc;
+        }
+        ChainLaunch c{};
+        c.ns = ns;
+        c.prep.n_blocks = 3;
+        c.prep.blk[0] = {m.W[0], 3 * TC_H, 2 * TC_H};
+        c.prep.blk[1] = {m.W[1], TC_H, 0};
+        c.prep.blk[2] = {m.W[2], TC_H, 0};
+        c.prep.vec_src[0] = nullptr;                  // b1 is folded into P_r
+        c.prep.vec_src[1] = m.b[1]; c.prep.vec_src[2] = m.b[2]; c.prep.vec_src[3] = m.gamma; c.prep.vec_src[4] = m.beta;
+        c.p.n_rows = a.n * a.k; c.p.n_in = 1; c.p.n_layers = 3; c.p.k = a.k; c.p.has_ln = 1;
+        c.p.residual = a.e_in; c.p.agg_out = a.agg_out; c.p.senders = a.senders; c.p.Ps = Ps; c.p.Pr = Pr;
+        c.in0 = a.e_in; c.out = a.out;
+        c.images = img[2]; c.vec = vec[2];
+        return launch_chain(c, s);
+    }
+    if (a.mode == MODE_NODE) {
+        if (!tc_shape_ok(m, 2)) {
+            set_error("tensor-core node phase supports latent = hidden = 128 and 2 hidden layers (got in %d hidden %d out %d layers %d)",
+                      m.in_dim, m.hidden, m.out_dim, m.n_layers);
+            return CGNN_ERR_UNSUPPORTED;
+        }
+        const int64_t need = tc_node_fwd_workspace(nullptr, a.n, precision);
+        if (ws == nullptr || wsb < need) {
+            set_error("cgnn_mp_node_fwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
+            return CGNN_ERR_WORKSPACE;
+        }
+        Carver cv(ws);
+        ChainLaunch c{};
+        c.ns = ns;
+        c.images = cv.take<uint8_t>(IMG_BYTES_MAX); c.vec = cv.take<float>(5 * TC_H);
+        c.prep.n_blocks = 4;
+        c.prep.blk[0] = {m.W[0], 2 * TC_H, 0};
+        c.prep.blk[1] = {m.W[0], 2 * TC_H, TC_H};
+        c.prep.blk[2] = {m.W[1], TC_H, 0};
+        c.prep.blk[3] = {m.W[2], TC_H, 0};
+        c.prep.vec_src[0] = m.b[0]; c.prep.vec_src[1] = m.b[1]; c.prep.vec_src[2] = m.b[2];
+        c.prep.vec_src[3] = m.gamma; c.prep.vec_src[4] = m.beta;
+        c.p.n_rows = a.n; c.p.n_in = 2; c.p.n_layers = 3; c.p.k = 0; c.p.has_ln = 1;
+        c.p.residual = a.h;
+        c.in0 = a.h; c.in1 = a.agg; c.out = a.out;
+        return launch_chain(c, s);
+    }
+    set_error("tensor-core precision modes cover the processor (edge / node) phases; encoder and decoder rows run in FP32");
     return CGNN_ERR_UNSUPPORTED;
 }
+
 int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s) {
     (void)a; (void)g; (void)ws; (void)wsb; (void)precision; (void)s;
-    set_error("tensor-core precision modes are not built yet");
+    set_error("tensor-core backward is not built yet");
     return CGNN_ERR_UNSUPPORTED;
 }
 int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp) { (void)mlp; return 0; }
-int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) { (void)mlp; (void)n; (void)precision; return 0; }
 
 }  // namespace cgnn

@@ -209,8 +209,13 @@ def aggregate_senders(h, senders, k: int, agg):
 def mp_node_fwd(p: MlpParams, h, agg, h_out, precision: str = "fp32"):
     m = p.c_struct()
     with torch.cuda.device(h.device):
-        check(lib().cgnn_mp_node_fwd(byref(m), ptr(h), ptr(agg), h.shape[0], ptr(h_out), PREC[precision],
-                                     stream_ptr(h.device)), "cgnn_mp_node_fwd")
+        nbytes = lib().cgnn_mp_node_fwd_workspace_bytes(byref(m), h.shape[0], PREC[precision])
+        if nbytes < 0:
+            check(-1, "cgnn_mp_node_fwd_workspace_bytes")
+        ws = workspace.get(h.device, "node_fwd", nbytes) if nbytes > 0 else None
+        check(lib().cgnn_mp_node_fwd(byref(m), ptr(h), ptr(agg), h.shape[0], ptr(h_out), ptr(ws),
+                                     0 if ws is None else ws.numel(), PREC[precision], stream_ptr(h.device)),
+              "cgnn_mp_node_fwd")
 
 
 def mp_node_bwd(p: MlpParams, h, agg, dh_next, dh, dagg, precision: str = "fp32"):

@@ -59,6 +59,10 @@ typedef enum {
     CGNN_PREC_FP32 = 0,        /* FP32 SIMT FMA everywhere (<= 1e-5 parity mode) */
     CGNN_PREC_BF16X3 = 1,      /* tcgen05 tensor cores, bf16 hi/lo split operands (3 MMAs), FP32 accum/storage */
     CGNN_PREC_BF16 = 2         /* tcgen05, single bf16 pass (fastest; ~1e-2, outside the parity bar) */
+    /* The tensor-core modes cover the processor phases (cgnn_mp_edge_* / cgnn_mp_node_*) for
+     * latent = hidden = 128 with 2 hidden layers and k dividing 128; other shapes return
+     * CGNN_ERR_UNSUPPORTED.  The row-wise encoder / decoder entry points accept the tensor-core modes
+     * and run their FP32 kernels. */
 } cgnn_precision;
 
 const char* cgnn_last_error(void);
@@ -129,8 +133,10 @@ int cgnn_mp_edge_fwd(const cgnn_mlp* edge_mlp, const float* h, const float* e_in
                      void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
 int cgnn_aggregate_senders(const float* h, const int32_t* senders, int64_t n, int32_t k,
                            int32_t latent, float* agg, cgnn_stream stream);
+int64_t cgnn_mp_node_fwd_workspace_bytes(const cgnn_mlp* node_mlp, int64_t n, int32_t precision);
 int cgnn_mp_node_fwd(const cgnn_mlp* node_mlp, const float* h, const float* agg, int64_t n,
-                     float* h_out, int32_t precision, cgnn_stream stream);
+                     float* h_out, void* workspace, int64_t workspace_bytes, int32_t precision,
+                     cgnn_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5  one message-passing step, backward (activations recomputed inside the tile).
