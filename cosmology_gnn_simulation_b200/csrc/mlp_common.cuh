@@ -34,6 +34,8 @@ struct MlpTask {
     const float* e_in;          // EDGE  [E][L]
     const float* agg;           // NODE  [N][L]
     const int32_t* senders;     // EDGE  [E]
+    const int32_t* t_rowptr;    // EDGE backward: sender-sorted transpose (rowptr [N+1], perm [E])
+    const int32_t* t_perm;
     // forward outputs
     float* out;                 // ROWS [rows][out]; EDGE e_out [E][L]; NODE h_out [N][L]
     float* agg_out;             // EDGE optional [N][L]

@@ -21,22 +21,14 @@
 //     of P_s through per-row bulk copies, outputs leave through TMA stores.
 //
 // Reference semantics: InteractionNetwork.forward + residuals, graph_network.py:83-101,177-183.
-#include <cuda.h>
-
-#include "common.cuh"
-#include "mlp_common.cuh"
-#include "tc_ptx.cuh"
+#include "tc_common.cuh"
 
 namespace cgnn {
 namespace {
 
 using namespace ptx;
 
-constexpr int TC_H = 128;                 // latent = hidden = out width handled by this kernel
 constexpr int TC_THREADS = 320;           // 8 epilogue warps (2 groups of 4) + producer warp + MMA warp
-constexpr int CH = 16;                    // columns per streamed chunk (64-byte rows, SWIZZLE_64B)
-constexpr int NCH = TC_H / CH;            // 8 chunks per 128-column tile
-constexpr int CH_BYTES = 128 * CH * 4;    // 8192
 constexpr int NRING = 3;                  // input ring depth
 constexpr int WIMG = 64 * TC_H * 2;       // bytes of one weight image half (64 output rows x 128 k, bf16)
 constexpr int PS_STRIDE = TC_H * 4 + 16;  // padded row stride of the gathered P_s rows (conflict-free row reads)
@@ -48,8 +40,11 @@ struct TcParams {
     int64_t n_pair_tiles;       // ceil(n_rows / 256)
     int n_in;                   // input phases (1: in0; 2: in0 then in1)
     int n_layers;               // Linear layers (1 or 3)
-    int k;                      // > 0: edge mode, rows per receiver
+    int k;                      // > 0: rows per receiver (gather / segmented sum)
     int has_ln;
+    int gather;                 // layer-1 pre-activation += Ps[sender] + Pr[receiver]
+    int relu_out;               // ReLU on the result (before mask / residual)
+    const float* mask_src;      // [n_rows][128]: result = mask_src > 0 ? result : 0 (nullable)
     const float* residual;      // [n_rows][128] added to the result (nullable)
     float* agg_out;             // edge mode: [n_rows / k][128] per-receiver sum of the result before the residual (nullable)
     const int32_t* senders;     // edge mode
@@ -80,26 +75,6 @@ struct Bars {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    hi = pack_bf16x2(x0, x1);
-    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
-    lo = pack_bf16x2(x0 - h0, x1 - h1);
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-
-// byte offset of the 16-byte piece j (0..3) of row r inside a 64-byte-swizzled chunk buffer
-__device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
-
 template <int NS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
@@ -110,13 +85,13 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     float* sVec = reinterpret_cast<float*>(smem + Smem::vec);
     const int n_blocks = p.n_in + p.n_layers - 1;           // MMA phases per tile
     uint8_t* sW = smem + Smem::weights;
-    uint8_t* sPs = sW + n_blocks * NSI * WIMG;              // edge mode only: 128 * PS_STRIDE
+    uint8_t* sPs = sW + n_blocks * NSI * WIMG;              // gather only: 128 * PS_STRIDE
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int64_t n_it = p.n_pair_tiles > cluster_id ? (p.n_pair_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
-    const bool edge = p.k > 0;
+    const bool gather_on = p.gather != 0;
 
     // ---- one-time setup ---------------------------------------------------------------------------
     if (tid == 0) {
@@ -166,7 +141,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         tma_load_2d(smem + Smem::ring + buf * CH_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CH, (int)row0, full);
                     }
             }
-            if (edge) {
+            if (gather_on) {
                 int64_t valid = p.n_rows - row0;
                 valid = valid < 0 ? 0 : (valid > 128 ? 128 : valid);
                 if (lane == 0) {
@@ -279,7 +254,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 mbar_wait_or_trap(&bars->mma_done[g], pm, 160 + l);
                 pm ^= 1u;
                 tc_fence_after_sync();
-                const bool gather = edge && l == 0;
+                const bool gather = gather_on && l == 0;
                 if (gather) mbar_wait_or_trap(&bars->ps_full[g], (uint32_t)((it >> 1) & 1), 170);
                 const float* bias = sVec + l * TC_H;
                 int64_t grow = row0 + r;
@@ -320,11 +295,19 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     mbar_arrive_cluster(&bars->a_ready[g], 0);
                 }
             }
-            // ---- final layer: bias, LayerNorm, segmented sum, residual, store -----------------------------------
+            // ---- final layer: bias, [gather], [LayerNorm], [ReLU], [mask], segmented sum, residual, store -------
             mbar_wait_or_trap(&bars->mma_done[g], pm, 180);
             pm ^= 1u;
             tc_fence_after_sync();
             const float* bias = sVec + (p.n_layers - 1) * TC_H;
+            const bool fgather = gather_on && p.n_layers == 1;      // one-layer chain: the gather lands here
+            const float* pr_row = nullptr;
+            if (fgather) {
+                mbar_wait_or_trap(&bars->ps_full[g], (uint32_t)((it >> 1) & 1), 171);
+                int64_t grow = row0 + r;
+                if (grow >= p.n_rows) grow = p.n_rows - 1;
+                pr_row = p.Pr + (size_t)(grow / p.k) * TC_H;
+            }
             float mean = 0.0f, rstd = 1.0f;
             if (p.has_ln) {
                 float s = 0.0f;
@@ -334,7 +317,10 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     tmem_ld_32x32b_x32(tD + c0, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) s += v[j] + bias[c0 + j];
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
+                        s += (v[j] + b.x) + (v[j + 1] + b.y) + (v[j + 2] + b.z) + (v[j + 3] + b.w);
+                    }
                 }
                 mean = s * (1.0f / TC_H);
                 float q2 = 0.0f;
@@ -344,7 +330,11 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     tmem_ld_32x32b_x32(tD + c0, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { const float d = v[j] + bias[c0 + j] - mean; q2 = fmaf(d, d, q2); }
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
+                        const float d0 = v[j] + b.x - mean, d1 = v[j + 1] + b.y - mean, d2 = v[j + 2] + b.z - mean, d3 = v[j + 3] + b.w - mean;
+                        q2 = fmaf(d0, d0, q2); q2 = fmaf(d1, d1, q2); q2 = fmaf(d2, d2, q2); q2 = fmaf(d3, d3, q2);
+                    }
                 }
                 rstd = 1.0f / sqrtf(q2 * (1.0f / TC_H) + LN_EPS);
             }
@@ -356,10 +346,32 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 tmem_ld_32x32b_x16(tD + q * CH, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float u = v[j] + bias[q * CH + j];
-                    if (p.has_ln) u = (u - mean) * rstd * gamma[q * CH + j] + beta[q * CH + j];
-                    v[j] = u;
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + q * CH + j);
+                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
+                if (fgather) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 a = *reinterpret_cast<const float4*>(sPs + r * PS_STRIDE + (q * CH + j) * 4);
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(pr_row + q * CH + j));
+                        v[j] += a.x + b.x; v[j + 1] += a.y + b.y; v[j + 2] += a.z + b.z; v[j + 3] += a.w + b.w;
+                    }
+                }
+                if (p.has_ln) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 gm = *reinterpret_cast<const float4*>(gamma + q * CH + j);
+                        const float4 bt = *reinterpret_cast<const float4*>(beta + q * CH + j);
+                        v[j] = (v[j] - mean) * rstd * gm.x + bt.x;
+                        v[j + 1] = (v[j + 1] - mean) * rstd * gm.y + bt.y;
+                        v[j + 2] = (v[j + 2] - mean) * rstd * gm.z + bt.z;
+                        v[j + 3] = (v[j + 3] - mean) * rstd * gm.w + bt.w;
+                    }
+                }
+                if (p.relu_out) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
                 }
                 uint8_t* S = sS + (q & 1) * CH_BYTES;
                 if (gt == 0) bulk_wait_read<1>();            // the store that last read this buffer (chunk q-2) is done
@@ -368,6 +380,23 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<float4*>(S + swz64(r, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 named_bar_sync(bar_id, 128);
+                const int pj = gt & 3;                       // coalesced passes: 4 threads per row (16 bytes each), 32 rows per pass
+                if (p.mask_src != nullptr) {
+#pragma unroll
+                    for (int pass = 0; pass < 4; ++pass) {
+                        const int rr = (gt >> 2) + pass * 32;
+                        const int64_t grow = row0 + rr;
+                        if (grow < p.n_rows) {
+                            const float4 m = __ldg(reinterpret_cast<const float4*>(p.mask_src + grow * TC_H + q * CH + pj * 4));
+                            float4* dst = reinterpret_cast<float4*>(S + swz64(rr, pj));
+                            float4 u = *dst;
+                            u.x = m.x > 0.0f ? u.x : 0.0f; u.y = m.y > 0.0f ? u.y : 0.0f;
+                            u.z = m.z > 0.0f ? u.z : 0.0f; u.w = m.w > 0.0f ? u.w : 0.0f;
+                            *dst = u;
+                        }
+                    }
+                    if (p.agg_out != nullptr) named_bar_sync(bar_id, 128);
+                }
                 if (p.agg_out != nullptr) {
                     // per-receiver sum of the k rows, rank order (deterministic): thread <-> (receiver, column)
                     const int c = gt & 15;
@@ -383,18 +412,16 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             p.agg_out[recv * TC_H + q * CH + c] = s;
                         }
                     }
+                    if (p.residual != nullptr) named_bar_sync(bar_id, 128);   // agg reads the value before the residual lands
                 }
-                if (p.agg_out != nullptr && p.residual != nullptr) named_bar_sync(bar_id, 128);   // agg reads u before the residual lands
                 if (p.residual != nullptr) {
-                    // coalesced: 4 threads per row (16 bytes each), 32 rows per pass
-                    const int j = gt & 3;
 #pragma unroll
                     for (int pass = 0; pass < 4; ++pass) {
                         const int rr = (gt >> 2) + pass * 32;
                         const int64_t grow = row0 + rr;
                         if (grow < p.n_rows) {
-                            const float4 e = __ldg(reinterpret_cast<const float4*>(p.residual + grow * TC_H + q * CH + j * 4));
-                            float4* dst = reinterpret_cast<float4*>(S + swz64(rr, j));
+                            const float4 e = __ldg(reinterpret_cast<const float4*>(p.residual + grow * TC_H + q * CH + pj * 4));
+                            float4* dst = reinterpret_cast<float4*>(S + swz64(rr, pj));
                             float4 u = *dst;
                             u.x += e.x; u.y += e.y; u.z += e.z; u.w += e.w;
                             *dst = u;
@@ -408,6 +435,10 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     bulk_commit();
                 }
             }
+            if (fgather) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(&bars->ps_empty);
+            }
             // D and A of this slot are free again: the next tile of this group starts with its input phase
         }
         if (gt == 0) bulk_wait_all<0>();
@@ -420,11 +451,11 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     if (warp == 9) tmem_dealloc<2>(tmem, 512);
 }
 
-// Builds the shared-memory weight images: for block b, the K-major BF16 image(s) of W[:, col0 : col0+128]
-// ([128 out][ld] row-major FP32), split by output row into two halves of 64 rows.
-struct PrepBlock { const float* W; int ld; int col0; };
+// Builds the shared-memory weight images of a chain: for block b the K-major BF16 image(s) of the 128 x 128
+// matrix B[n][k] = W[(row0 + n) * ld + col0 + k]  (or, transposed, W[(row0 + k) * ld + col0 + n]),
+// split by output row n into two halves of 64 rows (one per CTA of the pair).
 struct PrepArgs {
-    PrepBlock blk[MAX_BLOCKS];
+    ChainBlock blk[MAX_BLOCKS];
     int n_blocks;
     const float* vec_src[5];      // bias1, bias2, bias3, gamma, beta (nullable -> zeros / ones for gamma)
 };
@@ -436,10 +467,16 @@ __global__ void tc_prep_kernel(PrepArgs a, uint8_t* __restrict__ images, float* 
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte piece: (n, k8)
     if (b < a.n_blocks && idx < TC_H * (TC_H / 8)) {
         const int n = idx / (TC_H / 8), k8 = idx % (TC_H / 8);
-        const float* src = a.blk[b].W + (size_t)n * a.blk[b].ld + a.blk[b].col0 + k8 * 8;
+        const ChainBlock& B = a.blk[b];
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k8 * 8 + j;
+            x[j] = B.transpose ? B.W[(size_t)(B.row0 + k) * B.ld + B.col0 + n] : B.W[(size_t)(B.row0 + n) * B.ld + B.col0 + k];
+        }
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split2(src[2 * j], src[2 * j + 1], hi[j], lo[j]);
+        for (int j = 0; j < 4; ++j) split2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
         const int half = n >> 6, nl = n & 63;
         const size_t off = (size_t)(nl >> 3) * (TC_H * 16) + (size_t)k8 * 128 + (nl & 7) * 16;
         *reinterpret_cast<uint4*>(images + ((size_t)(b * NSI + 0) * 2 + half) * WIMG + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -452,9 +489,69 @@ __global__ void tc_prep_kernel(PrepArgs a, uint8_t* __restrict__ images, float* 
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------------
+size_t chain_smem_bytes(int n_blocks, int nsi, bool gather) {
+    return (size_t)Smem::weights + (size_t)n_blocks * nsi * WIMG + (gather ? 128 * PS_STRIDE : 0);
+}
+
+template <int NS>
+int run_chain_t(const ChainOp& op, cudaStream_t stream) {
+    constexpr int NSI = NS == 3 ? 2 : 1;
+    const int n_in = op.in1 ? 2 : 1;
+    const int n_blocks = n_in + op.n_layers - 1;
+    CGNN_CHECK_ARG(op.n_layers == 1 || op.n_layers == 3, "tensor-core chain: 1 or 3 layers");
+    CGNN_CHECK_ARG(n_blocks <= MAX_BLOCKS && op.rows >= 1 && op.in0 && op.out && op.images && op.vec, "tensor-core chain: bad arguments");
+    const bool gather = op.Ps != nullptr;
+    if (gather || op.agg_out) CGNN_CHECK_ARG(op.k >= 1 && 128 % op.k == 0, "tensor-core chain: k must divide 128 (got %d)", op.k);
+    PrepArgs pa{};
+    pa.n_blocks = n_blocks;
+    for (int b = 0; b < n_blocks; ++b) pa.blk[b] = op.blk[b];
+    if (op.n_layers == 1) {
+        pa.vec_src[0] = op.bias[0];
+    } else {
+        pa.vec_src[0] = op.bias[0]; pa.vec_src[1] = op.bias[1]; pa.vec_src[2] = op.bias[2];
+    }
+    pa.vec_src[3] = op.gamma; pa.vec_src[4] = op.beta;
+    dim3 pg((TC_H * (TC_H / 8) + 255) / 256, n_blocks);
+    tc_prep_kernel<NS><<<pg, 256, 0, stream>>>(pa, op.images, op.vec);
+    CGNN_LAUNCH_CHECK();
+    TcParams p{};
+    p.n_rows = op.rows; p.n_pair_tiles = (op.rows + 255) / 256;
+    p.n_in = n_in; p.n_layers = op.n_layers; p.k = op.k; p.has_ln = op.gamma != nullptr;
+    p.gather = gather; p.relu_out = op.relu_out; p.mask_src = op.mask_src; p.residual = op.residual;
+    p.agg_out = op.agg_out; p.senders = op.senders; p.Ps = op.Ps; p.Pr = op.Pr;
+    p.w_images = op.images; p.vec = op.vec;
+    CUtensorMap m0, m1, mo;
+    int rc;
+    if ((rc = make_row_map(&m0, op.in0, op.rows))) return rc;
+    if ((rc = make_row_map(&m1, op.in1 ? op.in1 : op.in0, op.rows))) return rc;
+    if ((rc = make_row_map(&mo, op.out, op.rows))) return rc;
+    const size_t smem = chain_smem_bytes(n_blocks, NSI, gather);
+    CGNN_CHECK_ARG(smem <= 227 * 1024, "tensor-core chain: shared memory need %zu exceeds 227 KB", smem);
+    auto kern = tc_chain_fwd<NS>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int64_t pairs = num_sms() / 2;
+    if (p.n_pair_tiles < pairs) pairs = p.n_pair_tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(pairs * 2));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CGNN_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mo, p));
+    count_launch();
+    return CGNN_OK;
+}
+
+}  // namespace
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -482,167 +579,10 @@ int make_row_map(CUtensorMap* m, const float* base, int64_t rows) {
     return CGNN_OK;
 }
 
-size_t chain_smem_bytes(int n_blocks, int nsi, bool edge) {
-    return (size_t)Smem::weights + (size_t)n_blocks * nsi * WIMG + (edge ? 128 * PS_STRIDE : 0);
+int64_t chain_image_bytes() { return (int64_t)MAX_BLOCKS * 2 * 2 * WIMG; }
+int64_t chain_vec_bytes() { return align_up(5 * TC_H * 4, 256); }
+int run_chain(const ChainOp& op, cudaStream_t stream) {
+    return op.ns == 3 ? run_chain_t<3>(op, stream) : run_chain_t<1>(op, stream);
 }
-
-struct ChainLaunch {
-    int ns;                       // 1 or 3
-    PrepArgs prep;
-    TcParams p;
-    const float* in0;
-    const float* in1;
-    float* out;
-    uint8_t* images;              // workspace: n_blocks * NSI * 2 * WIMG
-    float* vec;                   // workspace: 5 * 128 floats
-};
-
-template <int NS>
-int launch_chain_t(ChainLaunch& c, cudaStream_t stream) {
-    constexpr int NSI = NS == 3 ? 2 : 1;
-    const int n_blocks = c.prep.n_blocks;
-    dim3 pg((TC_H * (TC_H / 8) + 255) / 256, n_blocks);
-    tc_prep_kernel<NS><<<pg, 256, 0, stream>>>(c.prep, c.images, c.vec);
-    CGNN_LAUNCH_CHECK();
-    c.p.w_images = c.images;
-    c.p.vec = c.vec;
-    c.p.n_pair_tiles = (c.p.n_rows + 255) / 256;
-    CUtensorMap m0, m1, mo;
-    int rc;
-    if ((rc = make_row_map(&m0, c.in0, c.p.n_rows))) return rc;
-    if ((rc = make_row_map(&m1, c.in1 ? c.in1 : c.in0, c.p.n_rows))) return rc;
-    if ((rc = make_row_map(&mo, c.out, c.p.n_rows))) return rc;
-    const bool edge = c.p.k > 0;
-    const size_t smem = chain_smem_bytes(n_blocks, NSI, edge);
-    CGNN_CHECK_ARG(smem <= 227 * 1024, "tensor-core chain: shared memory need %zu exceeds 227 KB", smem);
-    auto kern = tc_chain_fwd<NS>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        CGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    int64_t pairs = num_sms() / 2;
-    if (c.p.n_pair_tiles < pairs) pairs = c.p.n_pair_tiles;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(pairs * 2));
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    CGNN_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mo, c.p));
-    count_launch();
-    return CGNN_OK;
-}
-
-int launch_chain(ChainLaunch& c, cudaStream_t stream) {
-    return c.ns == 3 ? launch_chain_t<3>(c, stream) : launch_chain_t<1>(c, stream);
-}
-
-constexpr int64_t IMG_BYTES_MAX = (int64_t)MAX_BLOCKS * 2 * 2 * WIMG;     // one chain's weight images
-constexpr int64_t VEC_BYTES = 5 * TC_H * 4;
-
-bool tc_shape_ok(const MlpDev& m, int in_mult) {
-    return m.n_layers == 3 && m.hidden == TC_H && m.out_dim == TC_H && m.in_dim == in_mult * TC_H && m.gamma != nullptr;
-}
-
-}  // namespace
-
-// workspace: [3 chains x (images + vec)] [P_s: n x 128] [P_r: n x 128]
-int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) {
-    (void)mlp; (void)precision;
-    return 3 * (IMG_BYTES_MAX + align_up(VEC_BYTES, 256)) + 2 * align_up(n * TC_H * 4, 256);
-}
-int64_t tc_node_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) {
-    (void)mlp; (void)n; (void)precision;
-    return IMG_BYTES_MAX + align_up(VEC_BYTES, 256);
-}
-
-int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s) {
-    const int ns = precision == CGNN_PREC_BF16X3 ? 3 : 1;
-    const MlpDev& m = a.mlp;
-    if (a.mode == MODE_EDGE) {
-        if (!tc_shape_ok(m, 3) || a.k < 1 || 128 % a.k != 0) {
-            set_error("tensor-core edge phase supports latent = hidden = 128, 2 hidden layers and k dividing 128 (got in %d hidden %d out %d layers %d k %d)",
-                      m.in_dim, m.hidden, m.out_dim, m.n_layers, a.k);
-            return CGNN_ERR_UNSUPPORTED;
-        }
-        const int64_t need = tc_edge_fwd_workspace(nullptr, a.n, precision);
-        if (ws == nullptr || wsb < need) {
-            set_error("cgnn_mp_edge_fwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
-            return CGNN_ERR_WORKSPACE;
-        }
-        Carver cv(ws);
-        uint8_t* img[3]; float* vec[3];
-        for (int i = 0; i < 3; ++i) { img[i] = cv.take<uint8_t>(IMG_BYTES_MAX); vec[i] = cv.take<float>(5 * TC_H); }
-        float* Ps = cv.take<float>(a.n * TC_H);
-        float* Pr = cv.take<float>(a.n * TC_H);
-        int rc;
-        // P_s = h W1[:, 0:L]^T ;  P_r = h W1[:, L:2L]^T + b1      (one-layer chains over the N node rows)
-        for (int which = 0; which < 2; ++which) {
-            ChainLaunch c{};
-            c.ns = ns;
-            c.prep.n_blocks = 1;
-            c.prep.blk[0] = {m.W[0], 3 * TC_H, which * TC_H};
-            c.prep.vec_src[0] = which == 1 ? m.b[0] : nullptr;
-            c.p.n_rows = a.n; c.p.n_in = 1; c.p.n_layers = 1; c.p.k = 0; c.p.has_ln = 0;
-            c.in0 = a.h; c.out = which == 0 ? Ps : Pr;
-            c.images = img[which]; c.vec = vec[which];
-            if ((rc = launch_chain(c, s))) return rc;
-        }
-        ChainLaunch c{};
-        c.ns = ns;
-        c.prep.n_blocks = 3;
-        c.prep.blk[0] = {m.W[0], 3 * TC_H, 2 * TC_H};
-        c.prep.blk[1] = {m.W[1], TC_H, 0};
-        c.prep.blk[2] = {m.W[2], TC_H, 0};
-        c.prep.vec_src[0] = nullptr;                  // b1 is folded into P_r
-        c.prep.vec_src[1] = m.b[1]; c.prep.vec_src[2] = m.b[2]; c.prep.vec_src[3] = m.gamma; c.prep.vec_src[4] = m.beta;
-        c.p.n_rows = a.n * a.k; c.p.n_in = 1; c.p.n_layers = 3; c.p.k = a.k; c.p.has_ln = 1;
-        c.p.residual = a.e_in; c.p.agg_out = a.agg_out; c.p.senders = a.senders; c.p.Ps = Ps; c.p.Pr = Pr;
-        c.in0 = a.e_in; c.out = a.out;
-        c.images = img[2]; c.vec = vec[2];
-        return launch_chain(c, s);
-    }
-    if (a.mode == MODE_NODE) {
-        if (!tc_shape_ok(m, 2)) {
-            set_error("tensor-core node phase supports latent = hidden = 128 and 2 hidden layers (got in %d hidden %d out %d layers %d)",
-                      m.in_dim, m.hidden, m.out_dim, m.n_layers);
-            return CGNN_ERR_UNSUPPORTED;
-        }
-        const int64_t need = tc_node_fwd_workspace(nullptr, a.n, precision);
-        if (ws == nullptr || wsb < need) {
-            set_error("cgnn_mp_node_fwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
-            return CGNN_ERR_WORKSPACE;
-        }
-        Carver cv(ws);
-        ChainLaunch c{};
-        c.ns = ns;
-        c.images = cv.take<uint8_t>(IMG_BYTES_MAX); c.vec = cv.take<float>(5 * TC_H);
-        c.prep.n_blocks = 4;
-        c.prep.blk[0] = {m.W[0], 2 * TC_H, 0};
-        c.prep.blk[1] = {m.W[0], 2 * TC_H, TC_H};
-        c.prep.blk[2] = {m.W[1], TC_H, 0};
-        c.prep.blk[3] = {m.W[2], TC_H, 0};
-        c.prep.vec_src[0] = m.b[0]; c.prep.vec_src[1] = m.b[1]; c.prep.vec_src[2] = m.b[2];
-        c.prep.vec_src[3] = m.gamma; c.prep.vec_src[4] = m.beta;
-        c.p.n_rows = a.n; c.p.n_in = 2; c.p.n_layers = 3; c.p.k = 0; c.p.has_ln = 1;
-        c.p.residual = a.h;
-        c.in0 = a.h; c.in1 = a.agg; c.out = a.out;
-        return launch_chain(c, s);
-    }
-    set_error("tensor-core precision modes cover the processor (edge / node) phases; encoder and decoder rows run in FP32");
-    return CGNN_ERR_UNSUPPORTED;
-}
-
-int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s) {
-    (void)a; (void)g; (void)ws; (void)wsb; (void)precision; (void)s;
-    set_error("tensor-core backward is not built yet");
-    return CGNN_ERR_UNSUPPORTED;
-}
-int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp) { (void)mlp; return 0; }
 
 }  // namespace cgnn

@@ -1,0 +1,74 @@
+// Shared pieces of the tcgen05 kernels (mp_tc.cu: chained MLP tiles; wgrad_tc.cu: weight gradients).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "mlp_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace cgnn {
+
+constexpr int TC_H = 128;                 // latent = hidden = out width handled by the tensor-core kernels
+constexpr int CH = 16;                    // columns per streamed chunk (64-byte rows, SWIZZLE_64B)
+constexpr int NCH = TC_H / CH;            // 8 chunks per 128-column tile
+constexpr int CH_BYTES = 128 * CH * 4;    // 8192
+
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = ptx::pack_bf16x2(x0, x1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
+    lo = ptx::pack_bf16x2(x0 - h0, x1 - h1);
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// byte offset of the 16-byte piece j (0..3) of row r inside a 64-byte-swizzled chunk buffer
+__device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+// 2-D tensor map over a row-major FP32 [rows][128] array: boxes of 128 rows x 16 columns, 64-byte swizzle
+int make_row_map(CUtensorMap* m, const float* base, int64_t rows);
+
+// ---- building blocks used by the backward orchestration (defined in mp_tc.cu / wgrad_tc.cu) -----------
+struct ChainBlock { const float* W; int ld; int row0; int col0; int transpose; };
+struct ChainOp {
+    int ns;                       // 1 (bf16) or 3 (bf16x3)
+    int64_t rows;
+    const float* in0;             // [rows][128]
+    const float* in1;             // second input phase (nullable)
+    int n_layers;                 // 1 or 3
+    ChainBlock blk[4];            // n_in + n_layers - 1 weight blocks
+    const float* bias[3];         // per layer (nullable)
+    const float* gamma; const float* beta;      // LayerNorm after the last layer (nullable)
+    int relu_out;                 // ReLU on the result (before mask / residual)
+    int k;                        // > 0: rows per receiver (gather and/or segmented sum)
+    const int32_t* senders; const float* Ps; const float* Pr;   // gather: layer-1 pre-activation += Ps[sender] + Pr[row / k]
+    const float* mask_src;        // result = mask_src > 0 ? result : 0   (nullable)
+    const float* residual;        // result += residual                   (nullable)
+    float* agg_out;               // [rows / k][128] = per-receiver sum of the result before the residual (nullable)
+    float* out;                   // [rows][128]
+    uint8_t* images; float* vec;  // workspace (chain_image_bytes(), chain_vec_bytes())
+};
+int64_t chain_image_bytes();
+int64_t chain_vec_bytes();
+int run_chain(const ChainOp& op, cudaStream_t stream);
+
+// dW[n][col0 + c] (=|+=) sum_rows X[row][n] * A[row][c];  db[n] (=|+=) sum_rows X[row][n]   (deterministic)
+int64_t wgrad_workspace_bytes();
+int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, int ld, int col0, float* db,
+              int accumulate, void* ws, cudaStream_t stream);
+
+
+// dY = LayerNorm backward of (Y, dU), dU = (dU_rows ? dU_rows[row] : 0) + (dU_recv ? dU_recv[row / k] : 0); dY may alias Y
+int64_t ln_bwd_workspace_bytes();
+int run_ln_bwd(const float* Y, const float* dU_rows, const float* dU_recv, int k, const float* gamma, int64_t rows,
+               float* dY, float* dgamma, float* dbeta, int accumulate, void* ws, cudaStream_t stream);
+
+}  // namespace cgnn

@@ -1,0 +1,282 @@
+// Host-side composition of the tensor-core kernels into the processor phases (forward and backward).
+//
+// Forward (one launch per phase, fully fused):        mp_tc.cu   tc_chain_fwd, 3-layer chains
+// Backward (round 1: tensor-core but not yet fused):  every GEMM of the recompute / dgrad / wgrad chain is
+//   a tensor-core launch over FP32 row streams held in a bounded workspace (edge rows are processed in
+//   chunks, so the transient activations never exceed CHUNK_ROWS x 5 buffers):
+//     recompute   A1 = relu(L1(in)), A2 = relu(L2(A1)), Y = L3(A2)          1-layer chains
+//     LayerNorm   dY = LNbwd(Y, dU)  (+ d gamma, d beta)                    ln_bwd_kernel
+//     dgrad       G2 = (dY W3) * [A2>0],  G1 = (G2 W2) * [A1>0],  dIn = G1 W1   1-layer chains, transposed blocks
+//     wgrad       dW3 = dY^T A2, dW2 = G2^T A1, dW1 = G1^T in  (+ bias columns)  tc_wgrad_kernel
+//   With W1 = [W1s | W1r | W1e] the per-edge layer 1 only sees e; the sender / receiver parts act on the
+//   per-node sums of G1 (sender-sorted transpose / k consecutive rows).
+//
+// Reference semantics: graph_network.py:83-101,177-183 and its autograd (train.py:264).
+#include "tc_common.cuh"
+
+namespace cgnn {
+namespace {
+
+constexpr int64_t CHUNK_ROWS = 1 << 21;      // edge rows per backward chunk (1 GiB per FP32 buffer)
+
+bool tc_shape_ok(const MlpDev& m, int in_mult) {
+    return m.n_layers == 3 && m.hidden == TC_H && m.out_dim == TC_H && m.in_dim == in_mult * TC_H && m.gamma != nullptr;
+}
+
+int64_t rows_bytes(int64_t rows) { return align_up(rows * TC_H * 4, 256); }
+
+struct Scratch {
+    uint8_t* images; float* vec; void* wg; void* lnb;
+    void carve(Carver& cv) {
+        images = cv.take<uint8_t>(chain_image_bytes());
+        vec = cv.take<float>(chain_vec_bytes() / 4);
+        wg = cv.take<uint8_t>(wgrad_workspace_bytes());
+        lnb = cv.take<uint8_t>(ln_bwd_workspace_bytes());
+    }
+    static int64_t bytes() { return chain_image_bytes() + chain_vec_bytes() + wgrad_workspace_bytes() + ln_bwd_workspace_bytes(); }
+};
+
+ChainOp base_op(int ns, const Scratch& sc, int64_t rows) {
+    ChainOp op{};
+    op.ns = ns; op.rows = rows; op.n_layers = 1; op.images = sc.images; op.vec = sc.vec;
+    return op;
+}
+
+// P_s = h W1[:, 0:L]^T,  P_r = h W1[:, L:2L]^T + b1   (graph_network.py:89: concat order sender, receiver, edge)
+int project_nodes(int ns, const Scratch& sc, const MlpDev& m, const float* h, int64_t n, float* Ps, float* Pr, cudaStream_t s) {
+    for (int which = 0; which < 2; ++which) {
+        ChainOp op = base_op(ns, sc, n);
+        op.in0 = h;
+        op.blk[0] = {m.W[0], 3 * TC_H, 0, which * TC_H, 0};
+        op.bias[0] = which == 1 ? m.b[0] : nullptr;
+        op.out = which == 0 ? Ps : Pr;
+        int rc = run_chain(op, s);
+        if (rc) return rc;
+    }
+    return CGNN_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// workspace sizes
+// ------------------------------------------------------------------------------------------------
+int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) {
+    (void)mlp; (void)precision;
+    return Scratch::bytes() + 2 * rows_bytes(n);
+}
+int64_t tc_node_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) {
+    (void)mlp; (void)n; (void)precision;
+    return Scratch::bytes();
+}
+// k == 0: node phase
+int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int k, int precision) {
+    (void)mlp; (void)precision;
+    if (k == 0) return Scratch::bytes() + 5 * rows_bytes(n);
+    int64_t chunk = n * k < CHUNK_ROWS ? n * k : CHUNK_ROWS;
+    return Scratch::bytes() + 5 * rows_bytes(chunk) + 4 * rows_bytes(n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s) {
+    const int ns = precision == CGNN_PREC_BF16X3 ? 3 : 1;
+    const MlpDev& m = a.mlp;
+    if (a.mode == MODE_EDGE) {
+        if (!tc_shape_ok(m, 3) || a.k < 1 || 128 % a.k != 0) {
+            set_error("tensor-core edge phase supports latent = hidden = 128, 2 hidden layers and k dividing 128 (got in %d hidden %d out %d layers %d k %d)",
+                      m.in_dim, m.hidden, m.out_dim, m.n_layers, a.k);
+            return CGNN_ERR_UNSUPPORTED;
+        }
+        const int64_t need = tc_edge_fwd_workspace(nullptr, a.n, precision);
+        if (ws == nullptr || wsb < need) {
+            set_error("cgnn_mp_edge_fwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
+            return CGNN_ERR_WORKSPACE;
+        }
+        Carver cv(ws);
+        Scratch sc; sc.carve(cv);
+        float* Ps = cv.take<float>(a.n * TC_H);
+        float* Pr = cv.take<float>(a.n * TC_H);
+        int rc = project_nodes(ns, sc, m, a.h, a.n, Ps, Pr, s);
+        if (rc) return rc;
+        ChainOp op = base_op(ns, sc, a.n * a.k);
+        op.n_layers = 3;
+        op.in0 = a.e_in;
+        op.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 0};
+        op.blk[1] = {m.W[1], TC_H, 0, 0, 0};
+        op.blk[2] = {m.W[2], TC_H, 0, 0, 0};
+        op.bias[0] = nullptr;                         // b1 is folded into P_r
+        op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta;
+        op.k = a.k; op.senders = a.senders; op.Ps = Ps; op.Pr = Pr;
+        op.residual = a.e_in; op.agg_out = a.agg_out; op.out = a.out;
+        return run_chain(op, s);
+    }
+    if (a.mode == MODE_NODE) {
+        if (!tc_shape_ok(m, 2)) {
+            set_error("tensor-core node phase supports latent = hidden = 128 and 2 hidden layers (got in %d hidden %d out %d layers %d)",
+                      m.in_dim, m.hidden, m.out_dim, m.n_layers);
+            return CGNN_ERR_UNSUPPORTED;
+        }
+        const int64_t need = tc_node_fwd_workspace(nullptr, a.n, precision);
+        if (ws == nullptr || wsb < need) {
+            set_error("cgnn_mp_node_fwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
+            return CGNN_ERR_WORKSPACE;
+        }
+        Carver cv(ws);
+        Scratch sc; sc.carve(cv);
+        ChainOp op = base_op(ns, sc, a.n);
+        op.n_layers = 3;
+        op.in0 = a.h; op.in1 = a.agg;
+        op.blk[0] = {m.W[0], 2 * TC_H, 0, 0, 0};
+        op.blk[1] = {m.W[0], 2 * TC_H, 0, TC_H, 0};
+        op.blk[2] = {m.W[1], TC_H, 0, 0, 0};
+        op.blk[3] = {m.W[2], TC_H, 0, 0, 0};
+        op.bias[0] = m.b[0]; op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta;
+        op.residual = a.h; op.out = a.out;
+        return run_chain(op, s);
+    }
+    set_error("tensor-core precision modes cover the processor (edge / node) phases; encoder and decoder rows run in FP32");
+    return CGNN_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+// Shared tail of both phases for one row range: given the layer-1 pre-activation inputs already applied
+// (A1 = relu(pre1) in bufA1) it recomputes A2, Y, runs LayerNorm backward and the dgrad chain down to
+// G1 = dL/dpre1 (written to g1_out, optionally with its per-receiver sum), and accumulates dW2, dW3, db2,
+// db3, d gamma, d beta.   Buffers: A1, A2, T (Y then dY), G2.
+static int backward_tail(int ns, const Scratch& sc, const MlpDev& m, const cgnn_mlp_grad* g, int64_t rows,
+                         float* A1, float* A2, float* T, float* G2, const float* dU_rows, const float* dU_recv, int k,
+                         float* g1_out, float* g1_agg, int accumulate, cudaStream_t s) {
+    int rc;
+    {   // A2 = relu(A1 W2^T + b2)
+        ChainOp op = base_op(ns, sc, rows);
+        op.in0 = A1; op.blk[0] = {m.W[1], TC_H, 0, 0, 0}; op.bias[0] = m.b[1]; op.relu_out = 1; op.out = A2;
+        if ((rc = run_chain(op, s))) return rc;
+    }
+    {   // Y = A2 W3^T + b3
+        ChainOp op = base_op(ns, sc, rows);
+        op.in0 = A2; op.blk[0] = {m.W[2], TC_H, 0, 0, 0}; op.bias[0] = m.b[2]; op.out = T;
+        if ((rc = run_chain(op, s))) return rc;
+    }
+    // dY = LNbwd(Y, dU)  (in place), d gamma, d beta
+    if ((rc = run_ln_bwd(T, dU_rows, dU_recv, k, m.gamma, rows, T, g->ln_gamma, g->ln_beta, accumulate, sc.lnb, s))) return rc;
+    // dW3 = dY^T A2, db3
+    if ((rc = run_wgrad(ns, T, A2, rows, g->W[2], TC_H, 0, g->b[2], accumulate, sc.wg, s))) return rc;
+    {   // G2 = (dY W3) * [A2 > 0]
+        ChainOp op = base_op(ns, sc, rows);
+        op.in0 = T; op.blk[0] = {m.W[2], TC_H, 0, 0, 1}; op.mask_src = A2; op.out = G2;
+        if ((rc = run_chain(op, s))) return rc;
+    }
+    // dW2 = G2^T A1, db2
+    if ((rc = run_wgrad(ns, G2, A1, rows, g->W[1], TC_H, 0, g->b[1], accumulate, sc.wg, s))) return rc;
+    {   // G1 = (G2 W2) * [A1 > 0]   (+ per-receiver sum)
+        ChainOp op = base_op(ns, sc, rows);
+        op.in0 = G2; op.blk[0] = {m.W[1], TC_H, 0, 0, 1}; op.mask_src = A1; op.out = g1_out;
+        op.k = k; op.agg_out = g1_agg;
+        if ((rc = run_chain(op, s))) return rc;
+    }
+    return CGNN_OK;
+}
+
+int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s) {
+    const int ns = precision == CGNN_PREC_BF16X3 ? 3 : 1;
+    const MlpDev& m = a.mlp;
+    int rc;
+    if (a.mode == MODE_NODE) {
+        if (!tc_shape_ok(m, 2)) return CGNN_ERR_UNSUPPORTED;
+        const int64_t need = tc_bwd_workspace(nullptr, a.n, 0, precision);
+        if (ws == nullptr || wsb < need) {
+            set_error("cgnn_mp_node_bwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
+            return CGNN_ERR_WORKSPACE;
+        }
+        Carver cv(ws);
+        Scratch sc; sc.carve(cv);
+        const int64_t n = a.n;
+        float* A1 = cv.take<float>(n * TC_H); float* A2 = cv.take<float>(n * TC_H); float* T = cv.take<float>(n * TC_H);
+        float* G2 = cv.take<float>(n * TC_H); float* G1 = cv.take<float>(n * TC_H);
+        {   // A1 = relu([h | agg] W1^T + b1)
+            ChainOp op = base_op(ns, sc, n);
+            op.in0 = a.h; op.in1 = a.agg;
+            op.blk[0] = {m.W[0], 2 * TC_H, 0, 0, 0}; op.blk[1] = {m.W[0], 2 * TC_H, 0, TC_H, 0};
+            op.bias[0] = m.b[0]; op.relu_out = 1; op.out = A1;
+            if ((rc = run_chain(op, s))) return rc;
+        }
+        if ((rc = backward_tail(ns, sc, m, g, n, A1, A2, T, G2, a.dout, nullptr, 1, G1, nullptr, 0, s))) return rc;
+        // dW1 = G1^T [h | agg], db1
+        if ((rc = run_wgrad(ns, G1, a.h, n, g->W[0], 2 * TC_H, 0, g->b[0], 0, sc.wg, s))) return rc;
+        if ((rc = run_wgrad(ns, G1, a.agg, n, g->W[0], 2 * TC_H, TC_H, nullptr, 0, sc.wg, s))) return rc;
+        {   // dh = dh_next + G1 W1[:, 0:L]
+            ChainOp op = base_op(ns, sc, n);
+            op.in0 = G1; op.blk[0] = {m.W[0], 2 * TC_H, 0, 0, 1}; op.residual = a.dout; op.out = a.dh;
+            if ((rc = run_chain(op, s))) return rc;
+        }
+        {   // dagg = G1 W1[:, L:2L]
+            ChainOp op = base_op(ns, sc, n);
+            op.in0 = G1; op.blk[0] = {m.W[0], 2 * TC_H, 0, TC_H, 1}; op.out = a.dagg_out;
+            if ((rc = run_chain(op, s))) return rc;
+        }
+        return CGNN_OK;
+    }
+    if (a.mode == MODE_EDGE) {
+        if (!tc_shape_ok(m, 3) || a.k < 1 || 128 % a.k != 0 || a.t_rowptr == nullptr || a.t_perm == nullptr) return CGNN_ERR_UNSUPPORTED;
+        const int64_t n = a.n, k = a.k, E = n * k;
+        const int64_t need = tc_bwd_workspace(nullptr, n, a.k, precision);
+        if (ws == nullptr || wsb < need) {
+            set_error("cgnn_mp_edge_bwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
+            return CGNN_ERR_WORKSPACE;
+        }
+        Carver cv(ws);
+        Scratch sc; sc.carve(cv);
+        const int64_t chunk = E < CHUNK_ROWS ? E : CHUNK_ROWS;
+        float* A1 = cv.take<float>(chunk * TC_H); float* A2 = cv.take<float>(chunk * TC_H); float* T = cv.take<float>(chunk * TC_H);
+        float* G2 = cv.take<float>(chunk * TC_H); float* spare = cv.take<float>(chunk * TC_H); (void)spare;
+        float* Ps = cv.take<float>(n * TC_H); float* Pr = cv.take<float>(n * TC_H);
+        float* dPs = cv.take<float>(n * TC_H); float* dPr = cv.take<float>(n * TC_H);
+        if ((rc = project_nodes(ns, sc, m, a.h, n, Ps, Pr, s))) return rc;
+        for (int64_t r0 = 0, c = 0; r0 < E; r0 += chunk, ++c) {
+            const int64_t rows = E - r0 < chunk ? E - r0 : chunk;       // chunk is a multiple of 256 and of k unless it is the whole graph
+            const float* e_in = a.e_in + r0 * TC_H;
+            const float* de_next = a.de_next ? a.de_next + r0 * TC_H : nullptr;
+            float* G1 = a.gs + r0 * TC_H;
+            const int acc = c > 0;
+            {   // A1 = relu(e W1e^T + Ps[sender] + Pr[receiver])
+                ChainOp op = base_op(ns, sc, rows);
+                op.in0 = e_in; op.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 0};
+                op.k = a.k; op.senders = a.senders + r0; op.Ps = Ps; op.Pr = Pr + (r0 / k) * TC_H;
+                op.relu_out = 1; op.out = A1;
+                if ((rc = run_chain(op, s))) return rc;
+            }
+            // dU = de_next + dagg[receiver]
+            if ((rc = backward_tail(ns, sc, m, g, rows, A1, A2, T, G2, de_next, a.dagg + (r0 / k) * TC_H, a.k, G1,
+                                    dPr + (r0 / k) * TC_H, acc, s))) return rc;
+            // dW1e = G1^T e, db1
+            if ((rc = run_wgrad(ns, G1, e_in, rows, g->W[0], 3 * TC_H, 2 * TC_H, g->b[0], acc, sc.wg, s))) return rc;
+            {   // de = de_next + G1 W1e
+                ChainOp op = base_op(ns, sc, rows);
+                op.in0 = G1; op.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}; op.residual = de_next; op.out = a.de + r0 * TC_H;
+                if ((rc = run_chain(op, s))) return rc;
+            }
+        }
+        // per-node sums of G1: by sender (transpose CSR, deterministic) and by receiver (dPr, from the chunks)
+        CGNN_CUDA(cudaMemsetAsync(dPs, 0, (size_t)n * TC_H * 4, s));
+        if ((rc = simt_scatter_to_senders(a.gs, 0, a.t_rowptr, a.t_perm, n, a.k, TC_H, dPs, s))) return rc;
+        if ((rc = run_wgrad(ns, dPs, a.h, n, g->W[0], 3 * TC_H, 0, nullptr, 0, sc.wg, s))) return rc;
+        if ((rc = run_wgrad(ns, dPr, a.h, n, g->W[0], 3 * TC_H, TC_H, nullptr, 0, sc.wg, s))) return rc;
+        {   // dh += dPs W1s + dPr W1r
+            ChainOp op = base_op(ns, sc, n);
+            op.in0 = dPs; op.in1 = dPr;
+            op.blk[0] = {m.W[0], 3 * TC_H, 0, 0, 1}; op.blk[1] = {m.W[0], 3 * TC_H, 0, TC_H, 1};
+            op.residual = a.dh; op.out = a.dh;
+            if ((rc = run_chain(op, s))) return rc;
+        }
+        return CGNN_OK;
+    }
+    return CGNN_ERR_UNSUPPORTED;
+}
+
+int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp) { (void)mlp; return 0; }
+
+}  // namespace cgnn

@@ -178,9 +178,8 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
             if edge_mode:
                 de_new = torch.empty_like(e_t)
                 gs = torch.empty_like(e_t)
-                put(p.proc_edge[t], ops.mp_edge_bwd(p.proc_edge[t], hs[t], e_t, senders, k, de, dagg, de_new,
-                                                    dh_new, gs, prec))
-                ops.scatter_to_senders(gs, False, rowptr, perm, k, dh_new)
+                put(p.proc_edge[t], ops.mp_edge_bwd(p.proc_edge[t], hs[t], e_t, senders, rowptr, perm, k, de, dagg,
+                                                    de_new, dh_new, gs, prec))
                 return dh_new, de_new
             ops.scatter_to_senders(dagg, True, rowptr, perm, k, dh_new)
             return dh_new, None

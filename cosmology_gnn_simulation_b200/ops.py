@@ -218,25 +218,35 @@ def mp_node_fwd(p: MlpParams, h, agg, h_out, precision: str = "fp32"):
               "cgnn_mp_node_fwd")
 
 
+def _mp_bwd_ws(mlp_c: CgnnMlp, n: int, k: int, precision: str, device):
+    nbytes = lib().cgnn_mp_bwd_workspace_bytes(byref(mlp_c), n, k, PREC[precision])
+    if nbytes < 0:
+        check(-1, "cgnn_mp_bwd_workspace_bytes")
+    return workspace.get(device, "mlp_bwd", nbytes)
+
+
 def mp_node_bwd(p: MlpParams, h, agg, dh_next, dh, dagg, precision: str = "fp32"):
     m = p.c_struct()
     g, grads = p.new_grads()
     with torch.cuda.device(h.device):
-        ws = _bwd_ws(m, h.device)
+        ws = _mp_bwd_ws(m, h.shape[0], 0, precision, h.device)
         check(lib().cgnn_mp_node_bwd(byref(m), byref(g), ptr(h), ptr(agg), ptr(dh_next), h.shape[0], ptr(dh),
                                      ptr(dagg), ptr(ws), ws.numel(), PREC[precision], stream_ptr(h.device)),
               "cgnn_mp_node_bwd")
     return grads
 
 
-def mp_edge_bwd(p: MlpParams, h, e_in, senders, k: int, de_next, dagg, de, dh, gs, precision: str = "fp32"):
+def mp_edge_bwd(p: MlpParams, h, e_in, senders, rowptr, perm, k: int, de_next, dagg, de, dh, gs,
+                precision: str = "fp32"):
+    """Edge-phase backward including the deterministic scatter of the sender gradients into `dh`
+    (`rowptr`, `perm`: sender-sorted transpose from `csr_transpose`); `gs` [E,L] is scratch."""
     m = p.c_struct()
     g, grads = p.new_grads()
     with torch.cuda.device(h.device):
-        ws = _bwd_ws(m, h.device)
-        check(lib().cgnn_mp_edge_bwd(byref(m), byref(g), ptr(h), ptr(e_in), ptr(senders), h.shape[0], k,
-                                     ptr(de_next), ptr(dagg), ptr(de), ptr(dh), ptr(gs), ptr(ws), ws.numel(),
-                                     PREC[precision], stream_ptr(h.device)), "cgnn_mp_edge_bwd")
+        ws = _mp_bwd_ws(m, h.shape[0], k, precision, h.device)
+        check(lib().cgnn_mp_edge_bwd(byref(m), byref(g), ptr(h), ptr(e_in), ptr(senders), ptr(rowptr), ptr(perm),
+                                     h.shape[0], k, ptr(de_next), ptr(dagg), ptr(de), ptr(dh), ptr(gs), ptr(ws),
+                                     ws.numel(), PREC[precision], stream_ptr(h.device)), "cgnn_mp_edge_bwd")
     return grads
 
 

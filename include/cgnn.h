@@ -143,15 +143,20 @@ int cgnn_mp_node_fwd(const cgnn_mlp* node_mlp, const float* h, const float* agg,
  *  node phase: given dh_next = dL/dh^{t+1}:  dh = dh_next + dIn[:, :L];  dagg = dIn[:, L:]
  *  edge phase (message = edge): given de_next = dL/de^{t+1} (NULL = zero) and dagg:
  *      dU = de_next + dagg[receiver];  de = de_next + dIn[:, 2L:];
- *      dh[receiver] += sum_rank dIn[:, L:2L];  gs[e] = dIn[:, :L]  (per-edge sender gradient)
- *  sender scatter: dh[j] += sum over edges e with sender j (perm order) of src[e]   (src = gs,
- *      stride L) or of dagg[e / k] (message = sender).
+ *      dh[receiver] += sum_rank dIn[:, L:2L];  dh[sender] += dIn[:, :L] summed over the sender-sorted
+ *      transpose (t_rowptr, t_perm from cgnn_csr_transpose; fixed order, no atomics).  gs[E][L] is
+ *      scratch for the per-edge sender gradient.
+ *  cgnn_scatter_to_senders: dh[j] += sum over edges e with sender j (perm order) of src[e] (stride L)
+ *      or of src[e / k] (src_is_per_receiver: message = sender, where src = dagg).
  */
+/* workspace of cgnn_mp_node_bwd (k = 0) / cgnn_mp_edge_bwd (k = in-degree) */
+int64_t cgnn_mp_bwd_workspace_bytes(const cgnn_mlp* mlp, int64_t n, int32_t k, int32_t precision);
 int cgnn_mp_node_bwd(const cgnn_mlp* node_mlp, const cgnn_mlp_grad* grad, const float* h,
                      const float* agg, const float* dh_next, int64_t n, float* dh, float* dagg,
                      void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
 int cgnn_mp_edge_bwd(const cgnn_mlp* edge_mlp, const cgnn_mlp_grad* grad, const float* h,
-                     const float* e_in, const int32_t* senders, int64_t n, int32_t k,
+                     const float* e_in, const int32_t* senders, const int32_t* t_rowptr,
+                     const int32_t* t_perm, int64_t n, int32_t k,
                      const float* de_next, const float* dagg, float* de, float* dh, float* gs,
                      void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
 int cgnn_scatter_to_senders(const float* src, int32_t src_is_per_receiver, const int32_t* rowptr,
