@@ -40,7 +40,8 @@ SIGNATURES = {
     "cgnn_csr_transpose_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "cgnn_csr_transpose": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "cgnn_edge_index_to_senders": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
-    "cgnn_mlp_rows_fwd": (c_int, [POINTER(CgnnMlp), c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
+    "cgnn_mlp_rows_workspace_bytes": (c_int64, [POINTER(CgnnMlp), c_int64, c_int32, c_int32]),
+    "cgnn_mlp_rows_fwd": (c_int, [POINTER(CgnnMlp), c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_mlp_bwd_workspace_bytes": (c_int64, [POINTER(CgnnMlp)]),
     "cgnn_mlp_rows_bwd": (c_int, [POINTER(CgnnMlp), POINTER(CgnnMlpGrad), c_void_p, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_int32, c_void_p]),

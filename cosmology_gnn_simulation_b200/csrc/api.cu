@@ -37,18 +37,22 @@ int64_t tc_node_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision);
 int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s);
 int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp);
 int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int k, int precision);
+int64_t tc_rows_workspace(const cgnn_mlp* mlp, int64_t rows, int precision, int backward);
 
 static bool is_tc(int precision) { return precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16; }
 
 static int run_fwd(MlpTask& a, int precision, cudaStream_t s, void* ws = nullptr, int64_t wsb = 0) {
-    // encoder / decoder rows always run the FP32 kernels (see cgnn.h: the tensor-core modes cover the processor)
-    if (precision == CGNN_PREC_FP32 || (is_tc(precision) && a.mode == MODE_ROWS)) return simt_mlp_fwd(a, s);
-    if (precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16) return tc_mlp_fwd(a, precision, ws, wsb, s);
+    if (precision == CGNN_PREC_FP32) return simt_mlp_fwd(a, s);
+    if (is_tc(precision)) {
+        int rc = tc_mlp_fwd(a, precision, ws, wsb, s);
+        // row-wise MLPs of shapes the tensor-core chain does not cover run the FP32 kernels (see cgnn.h)
+        return (rc == CGNN_ERR_UNSUPPORTED && a.mode == MODE_ROWS) ? simt_mlp_fwd(a, s) : rc;
+    }
     set_error("unknown precision %d", precision);
     return CGNN_ERR_INVALID;
 }
 static int run_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s) {
-    if (precision == CGNN_PREC_FP32 || (is_tc(precision) && a.mode == MODE_ROWS)) return simt_mlp_bwd(a, g, ws, wsb, s);
+    if (precision == CGNN_PREC_FP32) return simt_mlp_bwd(a, g, ws, wsb, s);
     if (is_tc(precision)) {
         // the tensor-core backward covers what tc_mlp_bwd implements; everything else recomputes and
         // differentiates with the FP32 kernels (same math, higher precision)
@@ -67,15 +71,23 @@ extern "C" const char* cgnn_last_error(void) { return g_error; }
 extern "C" const char* cgnn_version(void) { return "cgnn 0.1 (sm_100a)"; }
 extern "C" int64_t cgnn_launch_count(void) { return g_launches.load(); }
 
-extern "C" int cgnn_mlp_rows_fwd(const cgnn_mlp* mlp, const float* x, int64_t rows, float* out, int32_t precision,
-                                 cgnn_stream stream) {
+extern "C" int64_t cgnn_mlp_rows_workspace_bytes(const cgnn_mlp* mlp, int64_t rows, int32_t precision, int32_t backward) {
+    if (mlp_validate(mlp, "cgnn_mlp_rows_workspace_bytes")) return -1;
+    int64_t a = backward ? simt_mlp_bwd_workspace(mlp) : 0;
+    if (precision == CGNN_PREC_FP32) return a;
+    int64_t b = tc_rows_workspace(mlp, rows, precision, backward);
+    return a > b ? a : b;
+}
+
+extern "C" int cgnn_mlp_rows_fwd(const cgnn_mlp* mlp, const float* x, int64_t rows, float* out, void* workspace,
+                                 int64_t workspace_bytes, int32_t precision, cgnn_stream stream) {
     int rc = mlp_validate(mlp, "cgnn_mlp_rows_fwd");
     if (rc) return rc;
     CGNN_CHECK_ARG(x && out && rows >= 0, "cgnn_mlp_rows_fwd: bad arguments");
     if (rows == 0) return CGNN_OK;
     MlpTask a{};
     a.mlp = mlp_to_dev(mlp); a.mode = MODE_ROWS; a.n = rows; a.x = x; a.out = out;
-    return run_fwd(a, precision, (cudaStream_t)stream);
+    return run_fwd(a, precision, (cudaStream_t)stream, workspace, workspace_bytes);
 }
 
 extern "C" int64_t cgnn_mlp_bwd_workspace_bytes(const cgnn_mlp* mlp) {

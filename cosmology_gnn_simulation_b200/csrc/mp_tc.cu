@@ -29,7 +29,7 @@ namespace {
 using namespace ptx;
 
 constexpr int TC_THREADS = 320;           // 8 epilogue warps (2 groups of 4) + producer warp + MMA warp
-constexpr int NRING = 3;                  // input ring depth
+constexpr int MAXRING = 16;               // input ring depth is chosen per launch from the shared memory left (3 .. 16)
 constexpr int WIMG = 64 * TC_H * 2;       // bytes of one weight image half (64 output rows x 128 k, bf16)
 constexpr int PS_STRIDE = TC_H * 4 + 16;  // padded row stride of the gathered P_s rows (conflict-free row reads)
 constexpr int MAX_BLOCKS = 4;             // weight blocks (MMA phases) per tile
@@ -50,26 +50,31 @@ struct TcParams {
     const int32_t* senders;     // edge mode
     const float* Ps;            // edge mode: [N][128]
     const float* Pr;            // edge mode: [N][128] (includes the layer-1 bias)
+    int n_ring;                 // input ring depth (3 .. MAXRING)
+    int n_ps;                   // gather staging buffers: 2 (one per group) when shared memory allows, else 1
     const uint8_t* w_images;    // [n_blocks][NSI][2 halves][WIMG]
     const float* vec;           // [5][128]: bias of layer 1, 2, 3, gamma, beta
 };
 
 // shared-memory layout (dynamic, 1024-byte aligned base)
 struct Smem {
-    static constexpr int ring = 0;                                 // NRING * CH_BYTES
-    static constexpr int sbuf = ring + NRING * CH_BYTES;           // 2 groups * 2 * CH_BYTES
+    static constexpr int sbuf = 0;                                 // 2 groups * 2 * CH_BYTES (output staging)
     static constexpr int vec = sbuf + 4 * CH_BYTES;                // 5 * 128 floats
-    static constexpr int bars = vec + 5 * TC_H * 4;                // barriers (256 bytes)
-    static constexpr int weights = bars + 256;                     // n_blocks * NSI * WIMG
+    static constexpr int bars = vec + 5 * TC_H * 4;                // barriers (512 bytes)
+    static constexpr int weights = bars + 512;                     // n_blocks * NSI * WIMG
+    // then: n_ps * 128 * PS_STRIDE gather staging, then (1024-aligned) n_ring * CH_BYTES input ring
 };
 static_assert(Smem::weights % 128 == 0 && Smem::sbuf % 1024 == 0, "chunk buffers need 1024-byte, weight images 128-byte alignment");
+__host__ __device__ constexpr uint32_t ring_offset(int n_blocks, int nsi, int n_ps) {
+    return (uint32_t)((Smem::weights + n_blocks * nsi * WIMG + n_ps * 128 * PS_STRIDE + 1023) / 1024 * 1024);
+}
 
 struct Bars {
     uint64_t w_full;
     // "full" barriers are per consumer group: a group only ever waits on barriers whose uses are all its own,
     // so the phase parity it tracks can never alias a phase that belongs to the other group's tiles
-    uint64_t in_full[2][NRING], in_empty[NRING];
-    uint64_t ps_full[2], ps_empty;
+    uint64_t in_full[2][MAXRING], in_empty[MAXRING];
+    uint64_t ps_full[2], ps_empty[2];
     uint64_t a_ready[2];        // used in the leader CTA: 8 arrivals (4 warps x 2 CTAs)
     uint64_t mma_done[2];       // per CTA, one tcgen05.commit arrival
     uint32_t tmem_base;
@@ -85,7 +90,9 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     float* sVec = reinterpret_cast<float*>(smem + Smem::vec);
     const int n_blocks = p.n_in + p.n_layers - 1;           // MMA phases per tile
     uint8_t* sW = smem + Smem::weights;
-    uint8_t* sPs = sW + n_blocks * NSI * WIMG;              // gather only: 128 * PS_STRIDE
+    uint8_t* sPs0 = sW + n_blocks * NSI * WIMG;             // gather only: n_ps * 128 * PS_STRIDE
+    uint8_t* sRing = smem + ring_offset(n_blocks, NSI, p.gather ? p.n_ps : 0);
+    const int NRING = p.n_ring;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -96,14 +103,15 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     // ---- one-time setup ---------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(&bars->w_full, 1);
-        for (int i = 0; i < NRING; ++i) {
+        for (int i = 0; i < MAXRING; ++i) {
             mbar_init(&bars->in_full[0][i], 1);
             mbar_init(&bars->in_full[1][i], 1);
             mbar_init(&bars->in_empty[i], 4);
         }
         mbar_init(&bars->ps_full[0], 1);
         mbar_init(&bars->ps_full[1], 1);
-        mbar_init(&bars->ps_empty, 4);
+        mbar_init(&bars->ps_empty[0], 4);
+        mbar_init(&bars->ps_empty[1], 4);
         for (int s = 0; s < 2; ++s) { mbar_init(&bars->a_ready[s], 8); mbar_init(&bars->mma_done[s], 1); }
         fence_mbar_init();
     }
@@ -138,20 +146,27 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 100 + buf);
                         uint64_t* full = &bars->in_full[it & 1][buf];
                         mbar_expect_tx(full, CH_BYTES);
-                        tma_load_2d(smem + Smem::ring + buf * CH_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CH, (int)row0, full);
+                        tma_load_2d(sRing + buf * CH_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CH, (int)row0, full);
                     }
             }
             if (gather_on) {
                 int64_t valid = p.n_rows - row0;
                 valid = valid < 0 ? 0 : (valid > 128 ? 128 : valid);
+                int32_t snd[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) snd[j] = lane + 32 * j < (int)valid ? p.senders[row0 + lane + 32 * j] : 0;
+                const int pb = (int)(it & (p.n_ps - 1));                    // staging buffer
+                const int64_t use = p.n_ps == 2 ? (it >> 1) : it;           // how often it has been used before
                 if (lane == 0) {
-                    mbar_wait_or_trap(&bars->ps_empty, (uint32_t)((it & 1) ^ 1), 110);
+                    mbar_wait_or_trap(&bars->ps_empty[pb], (uint32_t)((use & 1) ^ 1), 110);
                     mbar_expect_tx(&bars->ps_full[it & 1], (uint32_t)(valid * TC_H * 4));
                 }
                 __syncwarp();
-                for (int r = lane; r < (int)valid; r += 32) {
-                    const int32_t s = p.senders[row0 + r];
-                    bulk_g2s(sPs + r * PS_STRIDE, p.Ps + (size_t)s * TC_H, TC_H * 4, &bars->ps_full[it & 1]);
+                uint8_t* dstPs = sPs0 + pb * (128 * PS_STRIDE);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = lane + 32 * j;
+                    if (r < (int)valid) bulk_g2s(dstPs + r * PS_STRIDE, p.Ps + (size_t)snd[j] * TC_H, TC_H * 4, &bars->ps_full[it & 1]);
                 }
             }
         }
@@ -220,6 +235,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
         for (int64_t it = g; it < n_it; it += 2) {
             const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
             uint32_t seq = (uint32_t)it * (uint32_t)(NCH * p.n_in);
+            const int pb = (int)(it & (p.n_ps - 1));
+            const uint8_t* sPs = sPs0 + pb * (128 * PS_STRIDE);
             // ---- input phases: stream chunks, split, write the A operand -------------------------------------
             for (int ip = 0; ip < p.n_in; ++ip) {
                 if (ip > 0) {                            // A is still being read by the previous phase's MMA
@@ -231,7 +248,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     const uint32_t buf = seq % NRING;
                     mbar_wait_or_trap(&bars->in_full[g][buf], (in_par >> buf) & 1u, 150 + buf);
                     in_par ^= 1u << buf;
-                    const uint8_t* src = smem + Smem::ring + buf * CH_BYTES;
+                    const uint8_t* src = sRing + buf * CH_BYTES;
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -266,6 +283,11 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 #pragma unroll 1
                 for (int c0 = 0; c0 < TC_H; c0 += 32) {
                     float v[32];
+                    float4 prv[8];
+                    if (gather) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) prv[j] = __ldg(reinterpret_cast<const float4*>(pr_row + c0 + 4 * j));
+                    }
                     tmem_ld_32x32b_x32(tD + c0, v);
                     tmem_ld_wait();
 #pragma unroll
@@ -277,7 +299,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 a = *reinterpret_cast<const float4*>(sPs + r * PS_STRIDE + (c0 + j) * 4);
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(pr_row + c0 + j));
+                            const float4 b = prv[j >> 2];
                             v[j] += a.x + b.x; v[j + 1] += a.y + b.y; v[j + 2] += a.z + b.z; v[j + 3] += a.w + b.w;
                         }
                     }
@@ -291,7 +313,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) {
-                    if (gather) mbar_arrive_local(&bars->ps_empty);
+                    if (gather) mbar_arrive_local(&bars->ps_empty[pb]);
                     mbar_arrive_cluster(&bars->a_ready[g], 0);
                 }
             }
@@ -340,27 +362,54 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             }
             const float* gamma = sVec + 3 * TC_H;
             const float* beta = sVec + 4 * TC_H;
+            const int pj = gt & 3;                           // coalesced passes: 4 threads per row (16 bytes each), 32 rows per pass
 #pragma unroll 1
-            for (int q = 0; q < NCH; ++q) {
-                float v[16];
-                tmem_ld_32x32b_x16(tD + q * CH, v);
+            for (int q = 0; q < NCH; q += 2) {                // two 16-column chunks (both staging buffers) per iteration
+                // operands of the coalesced passes and of the gather: issued first, consumed after the TMEM read
+                float4 mk[2][4], rs[2][4], prv[8];
+                if (p.mask_src != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int pass = 0; pass < 4; ++pass) {
+                            const int64_t grow = row0 + (gt >> 2) + pass * 32;
+                            mk[c][pass] = grow < p.n_rows ? __ldg(reinterpret_cast<const float4*>(p.mask_src + grow * TC_H + (q + c) * CH + pj * 4))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                }
+                if (p.residual != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int pass = 0; pass < 4; ++pass) {
+                            const int64_t grow = row0 + (gt >> 2) + pass * 32;
+                            rs[c][pass] = grow < p.n_rows ? __ldg(reinterpret_cast<const float4*>(p.residual + grow * TC_H + (q + c) * CH + pj * 4))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                }
+                if (fgather) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) prv[j] = __ldg(reinterpret_cast<const float4*>(pr_row + q * CH + 4 * j));
+                }
+                float v[32];
+                tmem_ld_32x32b_x32(tD + q * CH, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
+                for (int j = 0; j < 32; j += 4) {
                     const float4 b = *reinterpret_cast<const float4*>(bias + q * CH + j);
                     v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                 }
                 if (fgather) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
+                    for (int j = 0; j < 32; j += 4) {
                         const float4 a = *reinterpret_cast<const float4*>(sPs + r * PS_STRIDE + (q * CH + j) * 4);
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(pr_row + q * CH + j));
+                        const float4 b = prv[j >> 2];
                         v[j] += a.x + b.x; v[j + 1] += a.y + b.y; v[j + 2] += a.z + b.z; v[j + 3] += a.w + b.w;
                     }
                 }
                 if (p.has_ln) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
+                    for (int j = 0; j < 32; j += 4) {
                         const float4 gm = *reinterpret_cast<const float4*>(gamma + q * CH + j);
                         const float4 bt = *reinterpret_cast<const float4*>(beta + q * CH + j);
                         v[j] = (v[j] - mean) * rstd * gm.x + bt.x;
@@ -371,73 +420,75 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 }
                 if (p.relu_out) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
                 }
-                uint8_t* S = sS + (q & 1) * CH_BYTES;
-                if (gt == 0) bulk_wait_read<1>();            // the store that last read this buffer (chunk q-2) is done
+                if (gt == 0) bulk_wait_read<0>();            // the stores of the previous pair have read both buffers
                 named_bar_sync(bar_id, 128);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4*>(S + swz64(r, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(sS + c * CH_BYTES + swz64(r, j)) =
+                            make_float4(v[16 * c + 4 * j], v[16 * c + 4 * j + 1], v[16 * c + 4 * j + 2], v[16 * c + 4 * j + 3]);
                 named_bar_sync(bar_id, 128);
-                const int pj = gt & 3;                       // coalesced passes: 4 threads per row (16 bytes each), 32 rows per pass
                 if (p.mask_src != nullptr) {
 #pragma unroll
-                    for (int pass = 0; pass < 4; ++pass) {
-                        const int rr = (gt >> 2) + pass * 32;
-                        const int64_t grow = row0 + rr;
-                        if (grow < p.n_rows) {
-                            const float4 m = __ldg(reinterpret_cast<const float4*>(p.mask_src + grow * TC_H + q * CH + pj * 4));
-                            float4* dst = reinterpret_cast<float4*>(S + swz64(rr, pj));
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int pass = 0; pass < 4; ++pass) {
+                            const int rr = (gt >> 2) + pass * 32;
+                            float4* dst = reinterpret_cast<float4*>(sS + c * CH_BYTES + swz64(rr, pj));
                             float4 u = *dst;
+                            const float4 m = mk[c][pass];
                             u.x = m.x > 0.0f ? u.x : 0.0f; u.y = m.y > 0.0f ? u.y : 0.0f;
                             u.z = m.z > 0.0f ? u.z : 0.0f; u.w = m.w > 0.0f ? u.w : 0.0f;
                             *dst = u;
                         }
-                    }
                     if (p.agg_out != nullptr) named_bar_sync(bar_id, 128);
                 }
                 if (p.agg_out != nullptr) {
-                    // per-receiver sum of the k rows, rank order (deterministic): thread <-> (receiver, column)
-                    const int c = gt & 15;
+                    // per-receiver sum of the k rows, rank order (deterministic): thread <-> (receiver, column of the pair)
+                    const int c32 = gt & 31;
+                    const uint8_t* Sc = sS + (c32 >> 4) * CH_BYTES;
+                    const int c = c32 & 15;
                     const int nrecv = 128 / p.k;
-                    for (int rv = gt >> 4; rv < nrecv; rv += 8) {
+                    for (int rv = gt >> 5; rv < nrecv; rv += 4) {
                         const int64_t recv = row0 / p.k + rv;
                         if (recv * p.k < p.n_rows) {
-                            float s = 0.0f;
+                            float sum = 0.0f;
                             for (int j = 0; j < p.k; ++j) {
                                 const int rr = rv * p.k + j;
-                                s += *reinterpret_cast<const float*>(S + swz64(rr, c >> 2) + (c & 3) * 4);
+                                sum += *reinterpret_cast<const float*>(Sc + swz64(rr, c >> 2) + (c & 3) * 4);
                             }
-                            p.agg_out[recv * TC_H + q * CH + c] = s;
+                            p.agg_out[recv * TC_H + q * CH + c32] = sum;
                         }
                     }
                     if (p.residual != nullptr) named_bar_sync(bar_id, 128);   // agg reads the value before the residual lands
                 }
                 if (p.residual != nullptr) {
 #pragma unroll
-                    for (int pass = 0; pass < 4; ++pass) {
-                        const int rr = (gt >> 2) + pass * 32;
-                        const int64_t grow = row0 + rr;
-                        if (grow < p.n_rows) {
-                            const float4 e = __ldg(reinterpret_cast<const float4*>(p.residual + grow * TC_H + q * CH + pj * 4));
-                            float4* dst = reinterpret_cast<float4*>(S + swz64(rr, pj));
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int pass = 0; pass < 4; ++pass) {
+                            const int rr = (gt >> 2) + pass * 32;
+                            float4* dst = reinterpret_cast<float4*>(sS + c * CH_BYTES + swz64(rr, pj));
                             float4 u = *dst;
+                            const float4 e = rs[c][pass];
                             u.x += e.x; u.y += e.y; u.z += e.z; u.w += e.w;
                             *dst = u;
                         }
-                    }
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
                 if (gt == 0) {
-                    tma_store_2d(&tm_out, S, q * CH, (int)row0);
+                    tma_store_2d(&tm_out, sS, q * CH, (int)row0);
+                    tma_store_2d(&tm_out, sS + CH_BYTES, (q + 1) * CH, (int)row0);
                     bulk_commit();
                 }
             }
             if (fgather) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive_local(&bars->ps_empty);
+                if (lane == 0) mbar_arrive_local(&bars->ps_empty[pb]);
             }
             // D and A of this slot are free again: the next tile of this group starts with its input phase
         }
@@ -458,6 +509,7 @@ struct PrepArgs {
     ChainBlock blk[MAX_BLOCKS];
     int n_blocks;
     const float* vec_src[5];      // bias1, bias2, bias3, gamma, beta (nullable -> zeros / ones for gamma)
+    int vec_len[5];               // valid entries (zero padded to 128)
 };
 
 template <int NS>
@@ -472,7 +524,8 @@ __global__ void tc_prep_kernel(PrepArgs a, uint8_t* __restrict__ images, float* 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = k8 * 8 + j;
-            x[j] = B.transpose ? B.W[(size_t)(B.row0 + k) * B.ld + B.col0 + n] : B.W[(size_t)(B.row0 + n) * B.ld + B.col0 + k];
+            const bool valid = n < (B.nmax ? B.nmax : TC_H) && k < (B.kmax ? B.kmax : TC_H);
+            x[j] = !valid ? 0.0f : B.transpose ? B.W[(size_t)(B.row0 + k) * B.ld + B.col0 + n] : B.W[(size_t)(B.row0 + n) * B.ld + B.col0 + k];
         }
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -485,13 +538,11 @@ __global__ void tc_prep_kernel(PrepArgs a, uint8_t* __restrict__ images, float* 
     }
     if (b == 0 && idx < 5 * TC_H) {
         const int v = idx / TC_H, c = idx % TC_H;
-        vec[idx] = a.vec_src[v] ? a.vec_src[v][c] : (v == 3 ? 1.0f : 0.0f);
+        vec[idx] = (a.vec_src[v] && c < a.vec_len[v]) ? a.vec_src[v][c] : (v == 3 ? 1.0f : 0.0f);
     }
 }
 
-size_t chain_smem_bytes(int n_blocks, int nsi, bool gather) {
-    return (size_t)Smem::weights + (size_t)n_blocks * nsi * WIMG + (gather ? 128 * PS_STRIDE : 0);
-}
+constexpr size_t SMEM_MAX = 227 * 1024;
 
 template <int NS>
 int run_chain_t(const ChainOp& op, cudaStream_t stream) {
@@ -511,6 +562,8 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
         pa.vec_src[0] = op.bias[0]; pa.vec_src[1] = op.bias[1]; pa.vec_src[2] = op.bias[2];
     }
     pa.vec_src[3] = op.gamma; pa.vec_src[4] = op.beta;
+    for (int v = 0; v < 5; ++v) pa.vec_len[v] = TC_H;
+    if (op.out_valid > 0) pa.vec_len[op.n_layers - 1] = op.out_valid;       // bias of a narrow last layer
     dim3 pg((TC_H * (TC_H / 8) + 255) / 256, n_blocks);
     tc_prep_kernel<NS><<<pg, 256, 0, stream>>>(pa, op.images, op.vec);
     CGNN_LAUNCH_CHECK();
@@ -525,8 +578,14 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     if ((rc = make_row_map(&m0, op.in0, op.rows))) return rc;
     if ((rc = make_row_map(&m1, op.in1 ? op.in1 : op.in0, op.rows))) return rc;
     if ((rc = make_row_map(&mo, op.out, op.rows))) return rc;
-    const size_t smem = chain_smem_bytes(n_blocks, NSI, gather);
-    CGNN_CHECK_ARG(smem <= 227 * 1024, "tensor-core chain: shared memory need %zu exceeds 227 KB", smem);
+    // spend the shared memory the weights leave on a second gather buffer, then on input-ring depth
+    p.n_ps = 1;
+    if (gather && ring_offset(n_blocks, NSI, 2) + 3 * CH_BYTES <= SMEM_MAX) p.n_ps = 2;
+    const size_t ring_off = ring_offset(n_blocks, NSI, gather ? p.n_ps : 0);
+    CGNN_CHECK_ARG(ring_off + 3 * CH_BYTES <= SMEM_MAX, "tensor-core chain: shared memory need %zu exceeds 227 KB", ring_off + 3 * CH_BYTES);
+    p.n_ring = (int)((SMEM_MAX - ring_off) / CH_BYTES);
+    if (p.n_ring > MAXRING) p.n_ring = MAXRING;
+    const size_t smem = ring_off + (size_t)p.n_ring * CH_BYTES;
     auto kern = tc_chain_fwd<NS>;
     static size_t configured = 0;
     if (smem > configured) {

@@ -37,7 +37,8 @@ __device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 
 int make_row_map(CUtensorMap* m, const float* base, int64_t rows);
 
 // ---- building blocks used by the backward orchestration (defined in mp_tc.cu / wgrad_tc.cu) -----------
-struct ChainBlock { const float* W; int ld; int row0; int col0; int transpose; };
+// B[n][k] = W[(row0 + n) * ld + col0 + k] (transpose: W[(row0 + k) * ld + col0 + n]); zero where n >= nmax or k >= kmax (0 = 128)
+struct ChainBlock { const float* W; int ld; int row0; int col0; int transpose; int nmax; int kmax; };
 struct ChainOp {
     int ns;                       // 1 (bf16) or 3 (bf16x3)
     int64_t rows;
@@ -48,6 +49,7 @@ struct ChainOp {
     const float* bias[3];         // per layer (nullable)
     const float* gamma; const float* beta;      // LayerNorm after the last layer (nullable)
     int relu_out;                 // ReLU on the result (before mask / residual)
+    int out_valid;                // > 0: the last layer has only this many outputs (bias zero-padded to 128)
     int k;                        // > 0: rows per receiver (gather and/or segmented sum)
     const int32_t* senders; const float* Ps; const float* Pr;   // gather: layer-1 pre-activation += Ps[sender] + Pr[row / k]
     const float* mask_src;        // result = mask_src > 0 ? result : 0   (nullable)
@@ -62,8 +64,9 @@ int run_chain(const ChainOp& op, cudaStream_t stream);
 
 // dW[n][col0 + c] (=|+=) sum_rows X[row][n] * A[row][c];  db[n] (=|+=) sum_rows X[row][n]   (deterministic)
 int64_t wgrad_workspace_bytes();
+// only the first nrows rows / ncols columns of the 128 x 128 product are written (0 = all 128)
 int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, int ld, int col0, float* db,
-              int accumulate, void* ws, cudaStream_t stream);
+              int accumulate, void* ws, cudaStream_t stream, int nrows = 0, int ncols = 0);
 
 
 // dY = LayerNorm backward of (Y, dU), dU = (dU_rows ? dU_rows[row] : 0) + (dU_recv ? dU_recv[row / k] : 0); dY may alias Y

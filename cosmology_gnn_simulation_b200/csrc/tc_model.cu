@@ -56,6 +56,38 @@ int project_nodes(int ns, const Scratch& sc, const MlpDev& m, const float* h, in
     return CGNN_OK;
 }
 
+// [rows][w] -> [rows][128], zero padded  /  [rows][128] -> [rows][w]
+__global__ void pad_rows_kernel(const float* __restrict__ src, int w, int64_t rows, float* __restrict__ dst) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= rows * TC_H) return;
+    const int64_t r = idx / TC_H;
+    const int c = (int)(idx - r * TC_H);
+    dst[idx] = c < w ? src[r * w + c] : 0.0f;
+}
+__global__ void slice_rows_kernel(const float* __restrict__ src, int w, int64_t rows, float* __restrict__ dst) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= rows * w) return;
+    const int64_t r = idx / w;
+    const int c = (int)(idx - r * w);
+    dst[idx] = src[r * TC_H + c];
+}
+int pad_rows(const float* src, int w, int64_t rows, float* dst, cudaStream_t s) {
+    pad_rows_kernel<<<(unsigned)((rows * TC_H + 255) / 256), 256, 0, s>>>(src, w, rows, dst);
+    CGNN_LAUNCH_CHECK();
+    return CGNN_OK;
+}
+int slice_rows(const float* src, int w, int64_t rows, float* dst, cudaStream_t s) {
+    slice_rows_kernel<<<(unsigned)((rows * w + 255) / 256), 256, 0, s>>>(src, w, rows, dst);
+    CGNN_LAUNCH_CHECK();
+    return CGNN_OK;
+}
+
+// encoder / decoder MLPs: 3 layers, hidden 128, in <= 128, out <= 128 (LayerNorm only with out == 128)
+bool tc_rows_ok(const MlpDev& m) {
+    return m.n_layers == 3 && m.hidden == TC_H && m.in_dim >= 1 && m.in_dim <= TC_H && m.out_dim >= 1 && m.out_dim <= TC_H &&
+           (m.gamma == nullptr || m.out_dim == TC_H);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -68,6 +100,11 @@ int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) {
 int64_t tc_node_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) {
     (void)mlp; (void)n; (void)precision;
     return Scratch::bytes();
+}
+int64_t tc_rows_workspace(const cgnn_mlp* mlp, int64_t rows, int precision, int backward) {
+    (void)mlp; (void)precision;
+    const int64_t chunk = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
+    return Scratch::bytes() + (backward ? 6 : 2) * rows_bytes(chunk);
 }
 // k == 0: node phase
 int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int k, int precision) {
@@ -136,7 +173,40 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
         op.residual = a.h; op.out = a.out;
         return run_chain(op, s);
     }
-    set_error("tensor-core precision modes cover the processor (edge / node) phases; encoder and decoder rows run in FP32");
+    if (a.mode == MODE_ROWS) {
+        if (!tc_rows_ok(m)) return CGNN_ERR_UNSUPPORTED;          // the caller runs the FP32 kernels
+        const int64_t need = tc_rows_workspace(nullptr, a.n, precision, 0);
+        if (ws == nullptr || wsb < need) {
+            set_error("cgnn_mlp_rows_fwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
+            return CGNN_ERR_WORKSPACE;
+        }
+        Carver cv(ws);
+        Scratch sc; sc.carve(cv);
+        const int64_t chunk = a.n < CHUNK_ROWS ? a.n : CHUNK_ROWS;
+        float* Xp = cv.take<float>(chunk * TC_H);
+        float* O = cv.take<float>(chunk * TC_H);
+        int rc;
+        for (int64_t r0 = 0; r0 < a.n; r0 += chunk) {
+            const int64_t rows = a.n - r0 < chunk ? a.n - r0 : chunk;
+            const float* in = a.x + r0 * m.in_dim;
+            if (m.in_dim < TC_H) {
+                if ((rc = pad_rows(in, m.in_dim, rows, Xp, s))) return rc;
+                in = Xp;
+            }
+            ChainOp op = base_op(ns, sc, rows);
+            op.n_layers = 3;
+            op.in0 = in;
+            op.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim};
+            op.blk[1] = {m.W[1], TC_H, 0, 0, 0};
+            op.blk[2] = {m.W[2], TC_H, 0, 0, 0, m.out_dim, 0};
+            op.bias[0] = m.b[0]; op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta;
+            op.out_valid = m.out_dim < TC_H ? m.out_dim : 0;
+            op.out = m.out_dim == TC_H ? a.out + r0 * TC_H : O;
+            if ((rc = run_chain(op, s))) return rc;
+            if (m.out_dim < TC_H && (rc = slice_rows(O, m.out_dim, rows, a.out + r0 * m.out_dim, s))) return rc;
+        }
+        return CGNN_OK;
+    }
     return CGNN_ERR_UNSUPPORTED;
 }
 
@@ -156,18 +226,20 @@ static int backward_tail(int ns, const Scratch& sc, const MlpDev& m, const cgnn_
         op.in0 = A1; op.blk[0] = {m.W[1], TC_H, 0, 0, 0}; op.bias[0] = m.b[1]; op.relu_out = 1; op.out = A2;
         if ((rc = run_chain(op, s))) return rc;
     }
-    {   // Y = A2 W3^T + b3
-        ChainOp op = base_op(ns, sc, rows);
-        op.in0 = A2; op.blk[0] = {m.W[2], TC_H, 0, 0, 0}; op.bias[0] = m.b[2]; op.out = T;
-        if ((rc = run_chain(op, s))) return rc;
-    }
-    // dY = LNbwd(Y, dU)  (in place), d gamma, d beta
-    if ((rc = run_ln_bwd(T, dU_rows, dU_recv, k, m.gamma, rows, T, g->ln_gamma, g->ln_beta, accumulate, sc.lnb, s))) return rc;
+    if (m.gamma != nullptr) {
+        {   // Y = A2 W3^T + b3
+            ChainOp op = base_op(ns, sc, rows);
+            op.in0 = A2; op.blk[0] = {m.W[2], TC_H, 0, 0, 0}; op.bias[0] = m.b[2]; op.out = T;
+            if ((rc = run_chain(op, s))) return rc;
+        }
+        // dY = LNbwd(Y, dU)  (in place), d gamma, d beta
+        if ((rc = run_ln_bwd(T, dU_rows, dU_recv, k, m.gamma, rows, T, g->ln_gamma, g->ln_beta, accumulate, sc.lnb, s))) return rc;
+    }   // else: no LayerNorm (decoders) -- the caller put dY, zero-padded to 128 columns, into T
     // dW3 = dY^T A2, db3
-    if ((rc = run_wgrad(ns, T, A2, rows, g->W[2], TC_H, 0, g->b[2], accumulate, sc.wg, s))) return rc;
+    if ((rc = run_wgrad(ns, T, A2, rows, g->W[2], TC_H, 0, g->b[2], accumulate, sc.wg, s, m.out_dim, 0))) return rc;
     {   // G2 = (dY W3) * [A2 > 0]
         ChainOp op = base_op(ns, sc, rows);
-        op.in0 = T; op.blk[0] = {m.W[2], TC_H, 0, 0, 1}; op.mask_src = A2; op.out = G2;
+        op.in0 = T; op.blk[0] = {m.W[2], TC_H, 0, 0, 1, 0, m.out_dim}; op.mask_src = A2; op.out = G2;
         if ((rc = run_chain(op, s))) return rc;
     }
     // dW2 = G2^T A1, db2
@@ -185,6 +257,47 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
     const int ns = precision == CGNN_PREC_BF16X3 ? 3 : 1;
     const MlpDev& m = a.mlp;
     int rc;
+    if (a.mode == MODE_ROWS) {
+        // input gradients come out 128 wide: only produced directly when the input is 128 wide (decoders)
+        if (!tc_rows_ok(m) || (a.dx != nullptr && m.in_dim != TC_H)) return CGNN_ERR_UNSUPPORTED;
+        const int64_t need = tc_rows_workspace(nullptr, a.n, precision, 1);
+        if (ws == nullptr || wsb < need) {
+            set_error("cgnn_mlp_rows_bwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
+            return CGNN_ERR_WORKSPACE;
+        }
+        Carver cv(ws);
+        Scratch sc; sc.carve(cv);
+        const int64_t chunk = a.n < CHUNK_ROWS ? a.n : CHUNK_ROWS;
+        float* Xp = cv.take<float>(chunk * TC_H); float* A1 = cv.take<float>(chunk * TC_H); float* A2 = cv.take<float>(chunk * TC_H);
+        float* T = cv.take<float>(chunk * TC_H); float* G2 = cv.take<float>(chunk * TC_H); float* G1 = cv.take<float>(chunk * TC_H);
+        for (int64_t r0 = 0, c = 0; r0 < a.n; r0 += chunk, ++c) {
+            const int64_t rows = a.n - r0 < chunk ? a.n - r0 : chunk;
+            const int acc = c > 0;
+            const float* in = a.x + r0 * m.in_dim;
+            if (m.in_dim < TC_H) {
+                if ((rc = pad_rows(in, m.in_dim, rows, Xp, s))) return rc;
+                in = Xp;
+            }
+            {   // A1 = relu(x W1^T + b1)
+                ChainOp op = base_op(ns, sc, rows);
+                op.in0 = in; op.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim}; op.bias[0] = m.b[0]; op.relu_out = 1; op.out = A1;
+                if ((rc = run_chain(op, s))) return rc;
+            }
+            const float* dU = a.dout + r0 * m.out_dim;
+            if (m.gamma == nullptr) {                       // no LayerNorm: dY = dout, zero padded
+                if (m.out_dim < TC_H) { if ((rc = pad_rows(dU, m.out_dim, rows, T, s))) return rc; }
+                else CGNN_CUDA(cudaMemcpyAsync(T, dU, (size_t)rows * TC_H * 4, cudaMemcpyDeviceToDevice, s));
+            }
+            if ((rc = backward_tail(ns, sc, m, g, rows, A1, A2, T, G2, dU, nullptr, 1, G1, nullptr, acc, s))) return rc;
+            if ((rc = run_wgrad(ns, G1, in, rows, g->W[0], m.in_dim, 0, g->b[0], acc, sc.wg, s, 0, m.in_dim))) return rc;
+            if (a.dx != nullptr) {                         // dx = G1 W1   (in_dim == 128)
+                ChainOp op = base_op(ns, sc, rows);
+                op.in0 = G1; op.blk[0] = {m.W[0], TC_H, 0, 0, 1}; op.out = a.dx + r0 * TC_H;
+                if ((rc = run_chain(op, s))) return rc;
+            }
+        }
+        return CGNN_OK;
+    }
     if (a.mode == MODE_NODE) {
         if (!tc_shape_ok(m, 2)) return CGNN_ERR_UNSUPPORTED;
         const int64_t need = tc_bwd_workspace(nullptr, a.n, 0, precision);

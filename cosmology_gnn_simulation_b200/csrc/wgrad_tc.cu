@@ -19,7 +19,7 @@ namespace {
 using namespace ptx;
 
 constexpr int WG_THREADS = 192;           // 4 converter warps + producer warp + MMA warp
-constexpr int WG_RING = 4;
+constexpr int WG_RING = 8;
 constexpr int OP_BYTES = 128 * 128 * 2;   // one BF16 operand image (128 mn x 128 k)
 constexpr int ONES_BYTES = 16 * 128 * 2;
 constexpr int PW = 132;                   // floats per partial row: 128 dW columns + db + pad
@@ -181,10 +181,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int n_cta, float* __restrict__ dW, int ld, int col0,
-                                    float* __restrict__ db, int accumulate) {
+                                    float* __restrict__ db, int accumulate, int nrows, int ncols) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 128 * 129) return;
     const int n = idx / 129, c = idx % 129;
+    if (n >= nrows || (c < 128 && c >= ncols)) return;
     float s = 0.0f;
     for (int g = 0; g < n_cta; ++g) s += partials[((size_t)g * 128 + n) * PW + c];
     if (c < 128) {
@@ -264,7 +265,7 @@ constexpr int LNB_BLOCKS = 592;       // 4 per SM
 int64_t wgrad_workspace_bytes() { return align_up((int64_t)148 * 128 * PW * 4, 256); }
 
 int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, int ld, int col0, float* db,
-              int accumulate, void* ws, cudaStream_t stream) {
+              int accumulate, void* ws, cudaStream_t stream, int nrows, int ncols) {
     CGNN_CHECK_ARG(X && A && dW && ws && rows >= 1, "tensor-core wgrad: bad arguments");
     const int nsi = ns == 3 ? 2 : 1;
     const int64_t n_tiles = (rows + 127) / 128;
@@ -286,7 +287,8 @@ int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, i
         tc_wgrad_kernel<1><<<grid, WG_THREADS, smem, stream>>>(mx, ma, n_tiles, partials);
     }
     CGNN_LAUNCH_CHECK();
-    wgrad_reduce_kernel<<<(128 * 129 + 255) / 256, 256, 0, stream>>>(partials, grid, dW, ld, col0, db, accumulate);
+    wgrad_reduce_kernel<<<(128 * 129 + 255) / 256, 256, 0, stream>>>(partials, grid, dW, ld, col0, db, accumulate,
+                                                                     nrows > 0 ? nrows : 128, ncols > 0 ? ncols : 128);
     CGNN_LAUNCH_CHECK();
     return CGNN_OK;
 }

@@ -144,6 +144,13 @@ class MlpParams:
         return g, outs
 
 
+def _rows_ws(mlp_c: CgnnMlp, rows: int, precision: str, backward: int, device):
+    nbytes = lib().cgnn_mlp_rows_workspace_bytes(byref(mlp_c), rows, PREC[precision], backward)
+    if nbytes < 0:
+        check(-1, "cgnn_mlp_rows_workspace_bytes")
+    return workspace.get(device, "mlp_bwd" if backward else "rows_fwd", nbytes)
+
+
 def _bwd_ws(mlp_c: CgnnMlp, device):
     nbytes = lib().cgnn_mlp_bwd_workspace_bytes(byref(mlp_c))
     if nbytes < 0:
@@ -159,8 +166,9 @@ def mlp_rows_fwd(p: MlpParams, x: torch.Tensor, precision: str = "fp32") -> torc
     out = torch.empty((x.shape[0], p.out_dim), dtype=torch.float32, device=x.device)
     m = p.c_struct()
     with torch.cuda.device(x.device):
-        check(lib().cgnn_mlp_rows_fwd(byref(m), ptr(x), x.shape[0], ptr(out), PREC[precision], stream_ptr(x.device)),
-              "cgnn_mlp_rows_fwd")
+        ws = _rows_ws(m, x.shape[0], precision, 0, x.device)
+        check(lib().cgnn_mlp_rows_fwd(byref(m), ptr(x), x.shape[0], ptr(out), ptr(ws), ws.numel(), PREC[precision],
+                                      stream_ptr(x.device)), "cgnn_mlp_rows_fwd")
     return out
 
 
@@ -170,7 +178,7 @@ def mlp_rows_bwd(p: MlpParams, x: torch.Tensor, dout: torch.Tensor, need_dx: boo
     g, grads = p.new_grads()
     dx = torch.empty_like(x) if need_dx else None
     with torch.cuda.device(x.device):
-        ws = _bwd_ws(m, x.device)
+        ws = _rows_ws(m, x.shape[0], precision, 1, x.device)
         check(lib().cgnn_mlp_rows_bwd(byref(m), byref(g), ptr(x), x.shape[0], ptr(dout), ptr(dx), ptr(ws),
                                       ws.numel(), PREC[precision], stream_ptr(x.device)), "cgnn_mlp_rows_bwd")
     return grads, dx

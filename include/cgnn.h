@@ -61,8 +61,9 @@ typedef enum {
     CGNN_PREC_BF16 = 2         /* tcgen05, single bf16 pass (fastest; ~1e-2, outside the parity bar) */
     /* The tensor-core modes cover the processor phases (cgnn_mp_edge_* / cgnn_mp_node_*) for
      * latent = hidden = 128 with 2 hidden layers and k dividing 128; other shapes return
-     * CGNN_ERR_UNSUPPORTED.  The row-wise encoder / decoder entry points accept the tensor-core modes
-     * and run their FP32 kernels. */
+     * CGNN_ERR_UNSUPPORTED.  The row-wise encoder / decoder entry points use the tensor cores for 3-layer
+     * MLPs with hidden = 128 and in, out <= 128 (zero padded), and run their FP32 kernels for any other
+     * shape or when an input gradient narrower than 128 columns is requested. */
 } cgnn_precision;
 
 const char* cgnn_last_error(void);
@@ -109,10 +110,12 @@ int cgnn_edge_index_to_senders(const int64_t* edge_index, int64_t n, int32_t k, 
  * K3/K6  row-wise MLP (+LayerNorm) -- GraphIndependent.forward (graph_network.py:52-64) and the
  * decoders (graph_network.py:151-152,158-159).   out[r] = [LN](MLP(x[r])).
  */
-int cgnn_mlp_rows_fwd(const cgnn_mlp* mlp, const float* x, int64_t rows, float* out,
-                      int32_t precision, cgnn_stream stream);
+/* workspace of cgnn_mlp_rows_fwd (backward = 0) / cgnn_mlp_rows_bwd (backward = 1) */
+int64_t cgnn_mlp_rows_workspace_bytes(const cgnn_mlp* mlp, int64_t rows, int32_t precision, int32_t backward);
+int cgnn_mlp_rows_fwd(const cgnn_mlp* mlp, const float* x, int64_t rows, float* out, void* workspace,
+                      int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
 /* dx may be NULL.  Parameter gradients are written to `grad`. */
-int64_t cgnn_mlp_bwd_workspace_bytes(const cgnn_mlp* mlp);
+int64_t cgnn_mlp_bwd_workspace_bytes(const cgnn_mlp* mlp);   /* FP32 kernels only; prefer the *_workspace_bytes above */
 int cgnn_mlp_rows_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const float* x, int64_t rows,
                       const float* dout, float* dx, void* workspace, int64_t workspace_bytes,
                       int32_t precision, cgnn_stream stream);

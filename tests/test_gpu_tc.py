@@ -244,3 +244,69 @@ def test_model_tensor_core_mode_matches_oracle(message):
     (measured ~1e-5); gradients within the ReLU-gate noise of a 1e-5 forward perturbation (1e-2 bar)."""
     from test_gpu_parity import _compare_with_oracle, TOL_TC
     _compare_with_oracle(message, dict(n=1500, k=16, L=128, H=128, nh=2, M=4), "bf16x3", TOL_TC, gtol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------
+# row-wise MLPs (encoders: narrow input + LayerNorm; decoders: narrow output, no LayerNorm)
+# ------------------------------------------------------------------------------------------------
+def _rows_params(in_dim, out_dim, ln, gen):
+    from cosmology_gnn_simulation_b200.ops import MlpParams
+    dims = [(L, in_dim), (L, L), (out_dim, L)]
+    ws = [((torch.rand(o, i, generator=gen) * 2 - 1) / i ** 0.5) for o, i in dims]
+    bs = [((torch.rand(o, generator=gen) * 2 - 1) * 0.1) for o, _ in dims]
+    gamma = 1.0 + 0.1 * torch.randn(out_dim, generator=gen) if ln else None
+    beta = 0.1 * torch.randn(out_dim, generator=gen) if ln else None
+    d = _dev()
+    p = MlpParams([w.to(d) for w in ws], [b.to(d) for b in bs], None if gamma is None else gamma.to(d),
+                  None if beta is None else beta.to(d))
+    return p, ws, bs, gamma, beta
+
+
+def _mlp64(z, ws, bs, gamma, beta):
+    z = z.double()
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        z = z @ w.double().T + b.double()
+        if i < len(ws) - 1:
+            z = torch.relu(z)
+    if gamma is not None:
+        mu = z.mean(-1, keepdim=True)
+        var = ((z - mu) ** 2).mean(-1, keepdim=True)
+        z = (z - mu) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()
+    return z
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("in_dim,out_dim,ln,rows", [(4, 128, True, 70000), (17, 128, True, 3000), (128, 3, False, 3000),
+                                                     (128, 1, False, 500), (4, 128, True, 100)])
+def test_tc_rows_forward_backward(precision, in_dim, out_dim, ln, rows):
+    """graph_network.py:52-64 (encoders) and :151-152,158-159 (decoders) on the tensor cores."""
+    from cosmology_gnn_simulation_b200 import ops
+    gen = torch.Generator().manual_seed(rows + in_dim)
+    p, ws, bs, gamma, beta = _rows_params(in_dim, out_dim, ln, gen)
+    x = torch.randn(rows, in_dim, generator=gen)
+    dout = torch.randn(rows, out_dim, generator=gen)
+    dout[_fragile_rows(x, ws, bs, FRAGILE[precision])] = 0.0
+    w64 = [w.double().requires_grad_(True) for w in ws]
+    b64 = [b.double().requires_grad_(True) for b in bs]
+    g64 = None if gamma is None else gamma.double().requires_grad_(True)
+    be64 = None if beta is None else beta.double().requires_grad_(True)
+    x64 = x.double().requires_grad_(True)
+    ref = _mlp64(x64, w64, b64, g64, be64)
+    (ref * dout.double()).sum().backward()
+    d = _dev()
+    out = ops.mlp_rows_fwd(p, x.to(d), precision)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), ref.detach()) < TOL[precision]
+    need_dx = in_dim == L                      # decoders: the latent gradient; encoders: the reference never asks
+    grads, dx = ops.mlp_rows_bwd(p, x.to(d), dout.to(d), need_dx, precision)
+    torch.cuda.synchronize()
+    tol = GTOL[precision]
+    refs = []
+    for w, b in zip(w64, b64):
+        refs += [w.grad, b.grad]
+    if ln:
+        refs += [g64.grad, be64.grad]
+    for i, (got, want) in enumerate(zip(grads, refs)):
+        assert rel_l2(got.cpu(), want) < tol, (i, rel_l2(got.cpu(), want))
+    if need_dx:
+        assert rel_l2(dx.cpu(), x64.grad) < tol
