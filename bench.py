@@ -120,9 +120,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference leg (oracle port of the reference algorithm; the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_training_step_rate(k, L, M, steps, warmup, sample_n=8192, seed=0):
-    """Times the reference algorithm (reference-actual message='sender' semantics: gathers, cat,
-    Linear, ReLU, LayerNorm, index_add_, autograd backward) on the host cores with all threads.
+def cpu_training_step_rate(k, L, M, steps, warmup, sample_n=8192, seed=0, message="edge"):
+    """Times the reference algorithm (gathers, cat, Linear, ReLU, LayerNorm, index_add_, autograd backward;
+    `message` as the GPU arm) on the host cores with all threads.
     The particle count is a bounded sample of the workload (cost is linear in N at fixed k, L, M)."""
     from cosmology_gnn_simulation_b200 import synthetic
     from oracle import knn_ref, model_ref
@@ -145,7 +145,7 @@ def cpu_training_step_rate(k, L, M, steps, warmup, sample_n=8192, seed=0):
         for v in params.values():
             v.grad = None
         t0 = time.perf_counter()
-        o = model_ref.forward(params, x, ei, ea, 2, M, message="sender")
+        o = model_ref.forward(params, x, ei, ea, 2, M, message=message)
         ls = model_ref.loss(o["acceleration"], o["temp_rate"], ya, yt, 0.01, w_acc=W_ACC, w_temp=W_TEMP, w_mom=W_MOM)
         ls["loss"].backward()
         if it >= warmup:
@@ -161,7 +161,7 @@ def run_reference(args):
         return                                              # rank 0 alone runs the CPU arm
     n, k, L, M, kind = WORKLOADS[args.workload]
     sample_n = min(n, 8192)
-    r = cpu_training_step_rate(k, L, M, args.steps, max(args.warmup, 1), sample_n=sample_n)
+    r = cpu_training_step_rate(k, L, M, args.steps, max(args.warmup, 1), sample_n=sample_n, message=args.message)
     sample = (f"{sample_n} of {n} particles per step at the workload's k={k}, L={L}, M={M} "
               f"(cost linear in N); graph build (KD-tree on 27N ghosts, 1 thread) timed apart: "
               f"{r['knn_rate']:.3g} particles/s")
@@ -169,7 +169,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, "sender", "fp32", args.gpus),
+        "config": workload_config(args.workload, args.message, "fp32 (CPU)", args.gpus),
         "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -297,6 +297,13 @@ def run_gpu(args):
         return
     peaks = measured_peaks()
     fl = flops_edge_fwd(n, k, L)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "edge_fwd_traffic.json")     # dram bytes of the same launch from `ncu --set full`
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            t = json.load(f)
+        if t.get("workload") == args.workload and t.get("precision") == precision:
+            traffic = t.get("dram_bytes_per_launch")
     achieved = fl / (edge_ms * 1e-3) / 1e12 if edge_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -310,7 +317,9 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "cgnn_mp_edge_fwd (processor edge phase, forward)",
                      "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+                     "executed_flop_per_launch": (2.0 * n * k * 3 * L * L + 2.0 * n * 2 * L * L) * (3 if precision == "bf16x3" else 1)
+                     if precision != "fp32" else fl,
                      "flop_per_launch": fl, "ms_per_launch": edge_ms, "launches_timed": len(events),
                      "peak_source": peaks["source"] + " (bf16 dense, sustained)",
                      "share_of_step": edge_ms * M / (total_ms / args.steps)},
@@ -320,10 +329,10 @@ def run_gpu(args):
         "loss_check": [float(v) for v in last],
     }
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_training_step_rate(k, L, M, steps=2, warmup=1, sample_n=min(n, 8192))
+        r = cpu_training_step_rate(k, L, M, steps=2, warmup=1, sample_n=min(n, 8192), message=message)
         line["cpu_baseline"] = {
             "value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-            "sample": f"oracle port (reference-actual semantics), {r['sample_n']} of {n} particles per step, "
+            "sample": f"oracle port (message='{message}'), {r['sample_n']} of {n} particles per step, "
                       f"k={k}, L={L}, M={M}, fwd+loss+bwd, 1 warm-up + 2 timed steps; k-NN oracle "
                       f"(KD-tree on 27N ghosts, 1 thread) {r['knn_rate']:.3g} particles/s"}
     print(json.dumps(line), flush=True)
@@ -338,8 +347,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cgnn", choices=["cgnn", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
-    ap.add_argument("--message", default="sender", choices=["sender", "edge"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--message", default="edge", choices=["sender", "edge"],
+                    help="edge: the Interaction Network of the north star (default); sender: what PyG's default message() computes")
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cgnn" else args.warmup
