@@ -35,6 +35,10 @@ SIGNATURES = {
     "cgnn_launch_count": (c_int64, []),
     "cgnn_knn_workspace_bytes": (c_int64, [c_int64]),
     "cgnn_knn_periodic": (c_int, [c_void_p, c_int64, c_float, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "cgnn_knn_periodic_range": (c_int, [c_void_p, c_int64, c_float, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                        c_void_p]),
+    "cgnn_edge_features_range": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_int32, c_int64, c_int64, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
     "cgnn_edge_features": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "cgnn_csr_transpose_workspace_bytes": (c_int64, [c_int64, c_int64]),
@@ -46,7 +50,7 @@ SIGNATURES = {
     "cgnn_mlp_rows_bwd": (c_int, [POINTER(CgnnMlp), POINTER(CgnnMlpGrad), c_void_p, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_mp_edge_fwd_workspace_bytes": (c_int64, [POINTER(CgnnMlp), c_int64, c_int32]),
-    "cgnn_mp_edge_fwd": (c_int, [POINTER(CgnnMlp), c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+    "cgnn_mp_edge_fwd": (c_int, [POINTER(CgnnMlp), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p,
                                  c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_aggregate_senders": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "cgnn_mp_node_fwd_workspace_bytes": (c_int64, [POINTER(CgnnMlp), c_int64, c_int32]),
@@ -54,9 +58,9 @@ SIGNATURES = {
                                  c_void_p]),
     "cgnn_mp_node_bwd": (c_int, [POINTER(CgnnMlp), POINTER(CgnnMlpGrad), c_void_p, c_void_p, c_void_p, c_int64,
                                  c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
-    "cgnn_mp_bwd_workspace_bytes": (c_int64, [POINTER(CgnnMlp), c_int64, c_int32, c_int32]),
+    "cgnn_mp_bwd_workspace_bytes": (c_int64, [POINTER(CgnnMlp), c_int64, c_int64, c_int32, c_int32]),
     "cgnn_mp_edge_bwd": (c_int, [POINTER(CgnnMlp), POINTER(CgnnMlpGrad), c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_scatter_to_senders": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                         c_void_p, c_void_p]),

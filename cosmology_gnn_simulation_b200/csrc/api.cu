@@ -36,7 +36,7 @@ int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision);
 int64_t tc_node_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision);
 int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s);
 int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp);
-int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int k, int precision);
+int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int64_t n_nodes, int k, int precision);
 int64_t tc_rows_workspace(const cgnn_mlp* mlp, int64_t rows, int precision, int backward);
 
 static bool is_tc(int precision) { return precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16; }
@@ -115,22 +115,22 @@ static int check_latent(const cgnn_mlp* mlp, int mult, const char* who) {
     return CGNN_OK;
 }
 
-extern "C" int64_t cgnn_mp_edge_fwd_workspace_bytes(const cgnn_mlp* mlp, int64_t n, int32_t precision) {
+extern "C" int64_t cgnn_mp_edge_fwd_workspace_bytes(const cgnn_mlp* mlp, int64_t n_nodes, int32_t precision) {
     if (mlp_validate(mlp, "cgnn_mp_edge_fwd_workspace_bytes")) return -1;
     if (precision == CGNN_PREC_FP32) return 0;
-    return tc_edge_fwd_workspace(mlp, n, precision);
+    return tc_edge_fwd_workspace(mlp, n_nodes, precision);
 }
 
 extern "C" int cgnn_mp_edge_fwd(const cgnn_mlp* mlp, const float* h, const float* e_in, const int32_t* senders,
-                                int64_t n, int32_t k, float* e_out, float* agg_edge, void* workspace,
+                                int64_t n, int64_t n_nodes, int32_t k, float* e_out, float* agg_edge, void* workspace,
                                 int64_t workspace_bytes, int32_t precision, cgnn_stream stream) {
     int rc = mlp_validate(mlp, "cgnn_mp_edge_fwd");
     if (rc) return rc;
     if ((rc = check_latent(mlp, 3, "cgnn_mp_edge_fwd"))) return rc;
-    CGNN_CHECK_ARG(h && e_in && senders && e_out && n >= 1, "cgnn_mp_edge_fwd: bad arguments");
+    CGNN_CHECK_ARG(h && e_in && senders && e_out && n >= 1 && n_nodes >= n, "cgnn_mp_edge_fwd: bad arguments");
     CGNN_CHECK_ARG(k >= 1 && k <= 64, "cgnn_mp_edge_fwd: need 1 <= k <= 64");
     MlpTask a{};
-    a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.k = k; a.L = mlp->out_dim;
+    a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.n_nodes = n_nodes; a.k = k; a.L = mlp->out_dim;
     a.h = h; a.e_in = e_in; a.senders = senders; a.out = e_out; a.agg_out = agg_edge;
     return run_fwd(a, precision, (cudaStream_t)stream, workspace, workspace_bytes);
 }
@@ -160,11 +160,11 @@ extern "C" int cgnn_mp_node_fwd(const cgnn_mlp* mlp, const float* h, const float
     return run_fwd(a, precision, (cudaStream_t)stream, workspace, workspace_bytes);
 }
 
-extern "C" int64_t cgnn_mp_bwd_workspace_bytes(const cgnn_mlp* mlp, int64_t n, int32_t k, int32_t precision) {
+extern "C" int64_t cgnn_mp_bwd_workspace_bytes(const cgnn_mlp* mlp, int64_t n, int64_t n_nodes, int32_t k, int32_t precision) {
     if (mlp_validate(mlp, "cgnn_mp_bwd_workspace_bytes")) return -1;
     int64_t a = simt_mlp_bwd_workspace(mlp);
     if (precision == CGNN_PREC_FP32) return a;
-    int64_t b = tc_bwd_workspace(mlp, n, k, precision);
+    int64_t b = tc_bwd_workspace(mlp, n, n_nodes, k, precision);
     return a > b ? a : b;
 }
 
@@ -182,16 +182,18 @@ extern "C" int cgnn_mp_node_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, 
 }
 
 extern "C" int cgnn_mp_edge_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const float* h, const float* e_in,
-                                const int32_t* senders, const int32_t* t_rowptr, const int32_t* t_perm, int64_t n, int32_t k,
+                                const int32_t* senders, const int32_t* t_rowptr, const int32_t* t_perm, int64_t n,
+                                int64_t n_nodes, int32_t k,
                                 const float* de_next, const float* dagg, float* de, float* dh, float* gs,
                                 void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream) {
     int rc = mlp_validate(mlp, "cgnn_mp_edge_bwd");
     if (rc) return rc;
     if ((rc = check_latent(mlp, 3, "cgnn_mp_edge_bwd"))) return rc;
-    CGNN_CHECK_ARG(grad && h && e_in && senders && t_rowptr && t_perm && dagg && de && dh && gs && n >= 1, "cgnn_mp_edge_bwd: bad arguments");
+    CGNN_CHECK_ARG(grad && h && e_in && senders && t_rowptr && t_perm && dagg && de && dh && gs && n >= 1 && n_nodes >= n,
+                   "cgnn_mp_edge_bwd: bad arguments");
     CGNN_CHECK_ARG(k >= 1 && k <= 64, "cgnn_mp_edge_bwd: need 1 <= k <= 64");
     MlpTask a{};
-    a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.k = k; a.L = mlp->out_dim;
+    a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.n_nodes = n_nodes; a.k = k; a.L = mlp->out_dim;
     a.h = h; a.e_in = e_in; a.senders = senders; a.de_next = de_next; a.dagg = dagg;
     a.de = de; a.dh = dh; a.gs = gs; a.need_input_grad = 1;
     a.t_rowptr = t_rowptr; a.t_perm = t_perm;
@@ -201,7 +203,7 @@ extern "C" int cgnn_mp_edge_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, 
     }
     // FP32 kernels: gs[e] = dIn[:, :L] per edge, then the deterministic scatter over the transpose
     if ((rc = simt_mlp_bwd(a, grad, workspace, workspace_bytes, (cudaStream_t)stream))) return rc;
-    return simt_scatter_to_senders(gs, 0, t_rowptr, t_perm, n, k, mlp->out_dim, dh, (cudaStream_t)stream);
+    return simt_scatter_to_senders(gs, 0, t_rowptr, t_perm, n_nodes, k, mlp->out_dim, dh, (cudaStream_t)stream);
 }
 
 extern "C" int cgnn_scatter_to_senders(const float* src, int32_t src_is_per_receiver, const int32_t* rowptr,

@@ -7,16 +7,16 @@ namespace cgnn {
 namespace {
 
 __global__ void edge_features_kernel(const float* __restrict__ pos, const int32_t* __restrict__ nbr_ext,
-                                     int64_t n, int k, float box, int disp_mode,
+                                     int64_t n, int k, float box, int disp_mode, int64_t q0, int64_t nq,
                                      int32_t* __restrict__ senders, int64_t* __restrict__ edge_index,
                                      float4* __restrict__ edge_attr) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int64_t n_edges = n * k;
+    int64_t n_edges = nq * k;
     if (e >= n_edges) return;
     unsigned c = (unsigned)nbr_ext[e];
     int sid = (int)(c / (unsigned)n);
     int s = (int)(c - (unsigned)sid * (unsigned)n);
-    int64_t r = e / k;
+    int64_t r = q0 + e / k;                 // global receiver id
     if (senders) senders[e] = s;
     if (edge_index) { edge_index[e] = s; edge_index[n_edges + e] = r; }
     if (edge_attr) {
@@ -76,14 +76,22 @@ using namespace cgnn;
 extern "C" int cgnn_edge_features(const float* pos, const int32_t* nbr_ext, int64_t n, int32_t k, float box,
                                   int32_t disp_mode, int32_t* senders, int64_t* edge_index, float* edge_attr,
                                   cgnn_stream stream_) {
+    return cgnn_edge_features_range(pos, nbr_ext, n, k, box, disp_mode, 0, n, senders, edge_index, edge_attr, stream_);
+}
+
+extern "C" int cgnn_edge_features_range(const float* pos, const int32_t* nbr_ext, int64_t n, int32_t k, float box,
+                                        int32_t disp_mode, int64_t q0, int64_t nq, int32_t* senders, int64_t* edge_index,
+                                        float* edge_attr, cgnn_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    CGNN_CHECK_ARG(q0 >= 0 && nq >= 0 && q0 + nq <= n, "cgnn_edge_features_range: receiver range outside [0, n)");
+    if (nq == 0) return CGNN_OK;
     CGNN_CHECK_ARG(pos && nbr_ext, "cgnn_edge_features: null pointer");
     CGNN_CHECK_ARG(n >= 1 && k >= 1, "cgnn_edge_features: bad sizes");
     CGNN_CHECK_ARG(disp_mode == CGNN_DISP_RAW || disp_mode == CGNN_DISP_MIN_IMAGE, "cgnn_edge_features: bad disp_mode");
     CGNN_CHECK_ARG(((uintptr_t)edge_attr & 15) == 0, "cgnn_edge_features: edge_attr must be 16-byte aligned");
-    int64_t n_edges = n * k;
+    int64_t n_edges = nq * k;
     int blocks = (int)((n_edges + 255) / 256);
-    edge_features_kernel<<<blocks, 256, 0, stream>>>(pos, nbr_ext, n, k, box, disp_mode, senders, edge_index,
+    edge_features_kernel<<<blocks, 256, 0, stream>>>(pos, nbr_ext, n, k, box, disp_mode, q0, nq, senders, edge_index,
                                                      reinterpret_cast<float4*>(edge_attr));
     CGNN_LAUNCH_CHECK();
     return CGNN_OK;

@@ -161,7 +161,7 @@ __device__ __forceinline__ void visit_cells(const float4* __restrict__ sorted, c
 
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_query(const float4* __restrict__ sorted, const int* __restrict__ cell_start, int nc, int64_t n,
-          float box, float inv_w, int k, int32_t* __restrict__ nbr_ext) {
+          float box, float inv_w, int k, int64_t q0, int64_t nq, int32_t* __restrict__ nbr_ext) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (gridDim.x * (int64_t)blockDim.x) >> 5;
@@ -171,6 +171,7 @@ knn_query(const float4* __restrict__ sorted, const int* __restrict__ cell_start,
         float4 me = sorted[q];
         float qx = me.x, qy = me.y, qz = me.z;
         int qi = __float_as_int(me.w);
+        if (qi < q0 || qi >= q0 + nq) continue;          // only the queries of this rank's slab (warp-uniform)
         int cx = cell_coord(qx, inv_w, nc), cy = cell_coord(qy, inv_w, nc), cz = cell_coord(qz, inv_w, nc);
         unsigned long long best = KEY_INF;
         for (int R = 1;; ++R) {
@@ -193,7 +194,7 @@ knn_query(const float4* __restrict__ sorted, const int* __restrict__ cell_start,
                 if (fds > 0.0f && kd2 <= fds * fds * 0.99999f) break;
             }
         }
-        if (lane < k) nbr_ext[(int64_t)qi * k + lane] = (int32_t)(unsigned)(best & 0xFFFFFFFFull);
+        if (lane < k) nbr_ext[((int64_t)qi - q0) * k + lane] = (int32_t)(unsigned)(best & 0xFFFFFFFFull);
     }
 }
 
@@ -230,8 +231,15 @@ extern "C" int64_t cgnn_knn_workspace_bytes(int64_t n) {
 
 extern "C" int cgnn_knn_periodic(const float* pos, int64_t n, float box, int32_t k, int32_t* nbr_ext,
                                  void* workspace, int64_t workspace_bytes, cgnn_stream stream_) {
+    return cgnn_knn_periodic_range(pos, n, box, k, 0, n, nbr_ext, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int cgnn_knn_periodic_range(const float* pos, int64_t n, float box, int32_t k, int64_t q0, int64_t nq,
+                                       int32_t* nbr_ext, void* workspace, int64_t workspace_bytes, cgnn_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CGNN_CHECK_ARG(pos && nbr_ext && workspace, "cgnn_knn_periodic: null pointer");
+    CGNN_CHECK_ARG(q0 >= 0 && nq >= 0 && q0 + nq <= n, "cgnn_knn_periodic_range: query range [%lld, +%lld) outside [0, %lld)", (long long)q0, (long long)nq, (long long)n);
+    if (nq == 0) return CGNN_OK;
     CGNN_CHECK_ARG(n >= 1 && k >= 1 && k <= 32, "cgnn_knn_periodic: need n >= 1 and 1 <= k <= 32 (got n=%lld k=%d)", (long long)n, k);
     CGNN_CHECK_ARG(27 * n >= k, "cgnn_knn_periodic: 27*N = %lld < k = %d", (long long)(27 * n), k);
     CGNN_CHECK_ARG(27 * n < (1ll << 32), "cgnn_knn_periodic: 27*N must fit 32 bits");
@@ -264,7 +272,7 @@ extern "C" int cgnn_knn_periodic(const float* pos, int64_t n, float box, int32_t
     int64_t want_blocks = (n * 32 + KNN_THREADS - 1) / KNN_THREADS;
     int64_t max_blocks = (int64_t)num_sms() * 8;
     int q_blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
-    knn_query<<<q_blocks, KNN_THREADS, 0, stream>>>(sorted, start, p.nc, n, box, inv_w, k, nbr_ext);
+    knn_query<<<q_blocks, KNN_THREADS, 0, stream>>>(sorted, start, p.nc, n, box, inv_w, k, q0, nq, nbr_ext);
     CGNN_LAUNCH_CHECK();
     return CGNN_OK;
 }

@@ -26,6 +26,7 @@ struct MlpTask {
     MlpDev mlp;
     int mode;
     int64_t n;                  // ROWS: rows; EDGE/NODE: number of nodes (receivers)
+    int64_t n_nodes;            // EDGE: rows of h / dh (receivers first, then halo senders); == n on one GPU
     int k, L;                   // EDGE: in-degree; EDGE/NODE: latent width
     int act_stride;             // shared-memory row stride of the activation buffers
     // forward inputs

@@ -43,9 +43,11 @@ ChainOp base_op(int ns, const Scratch& sc, int64_t rows) {
 }
 
 // P_s = h W1[:, 0:L]^T,  P_r = h W1[:, L:2L]^T + b1   (graph_network.py:89: concat order sender, receiver, edge)
-int project_nodes(int ns, const Scratch& sc, const MlpDev& m, const float* h, int64_t n, float* Ps, float* Pr, cudaStream_t s) {
+// P_s covers all n_nodes rows of h (receivers + halo senders), P_r the n receivers (the first n rows)
+int project_nodes(int ns, const Scratch& sc, const MlpDev& m, const float* h, int64_t n, int64_t n_nodes, float* Ps, float* Pr,
+                  cudaStream_t s) {
     for (int which = 0; which < 2; ++which) {
-        ChainOp op = base_op(ns, sc, n);
+        ChainOp op = base_op(ns, sc, which == 0 ? n_nodes : n);
         op.in0 = h;
         op.blk[0] = {m.W[0], 3 * TC_H, 0, which * TC_H, 0};
         op.bias[0] = which == 1 ? m.b[0] : nullptr;
@@ -107,11 +109,11 @@ int64_t tc_rows_workspace(const cgnn_mlp* mlp, int64_t rows, int precision, int 
     return Scratch::bytes() + (backward ? 6 : 2) * rows_bytes(chunk);
 }
 // k == 0: node phase
-int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int k, int precision) {
+int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int64_t n_nodes, int k, int precision) {
     (void)mlp; (void)precision;
     if (k == 0) return Scratch::bytes() + 5 * rows_bytes(n);
     int64_t chunk = n * k < CHUNK_ROWS ? n * k : CHUNK_ROWS;
-    return Scratch::bytes() + 5 * rows_bytes(chunk) + 4 * rows_bytes(n);
+    return Scratch::bytes() + 5 * rows_bytes(chunk) + 2 * rows_bytes(n) + 2 * rows_bytes(n_nodes);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -126,16 +128,17 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
                       m.in_dim, m.hidden, m.out_dim, m.n_layers, a.k);
             return CGNN_ERR_UNSUPPORTED;
         }
-        const int64_t need = tc_edge_fwd_workspace(nullptr, a.n, precision);
+        const int64_t nn = a.n_nodes > 0 ? a.n_nodes : a.n;
+        const int64_t need = tc_edge_fwd_workspace(nullptr, nn, precision);
         if (ws == nullptr || wsb < need) {
             set_error("cgnn_mp_edge_fwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
             return CGNN_ERR_WORKSPACE;
         }
         Carver cv(ws);
         Scratch sc; sc.carve(cv);
-        float* Ps = cv.take<float>(a.n * TC_H);
-        float* Pr = cv.take<float>(a.n * TC_H);
-        int rc = project_nodes(ns, sc, m, a.h, a.n, Ps, Pr, s);
+        float* Ps = cv.take<float>(nn * TC_H);
+        float* Pr = cv.take<float>(nn * TC_H);
+        int rc = project_nodes(ns, sc, m, a.h, a.n, nn, Ps, Pr, s);
         if (rc) return rc;
         ChainOp op = base_op(ns, sc, a.n * a.k);
         op.n_layers = 3;
@@ -300,7 +303,7 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
     }
     if (a.mode == MODE_NODE) {
         if (!tc_shape_ok(m, 2)) return CGNN_ERR_UNSUPPORTED;
-        const int64_t need = tc_bwd_workspace(nullptr, a.n, 0, precision);
+        const int64_t need = tc_bwd_workspace(nullptr, a.n, a.n, 0, precision);
         if (ws == nullptr || wsb < need) {
             set_error("cgnn_mp_node_bwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
             return CGNN_ERR_WORKSPACE;
@@ -336,7 +339,8 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
     if (a.mode == MODE_EDGE) {
         if (!tc_shape_ok(m, 3) || a.k < 1 || 128 % a.k != 0 || a.t_rowptr == nullptr || a.t_perm == nullptr) return CGNN_ERR_UNSUPPORTED;
         const int64_t n = a.n, k = a.k, E = n * k;
-        const int64_t need = tc_bwd_workspace(nullptr, n, a.k, precision);
+        const int64_t nn = a.n_nodes > 0 ? a.n_nodes : a.n;
+        const int64_t need = tc_bwd_workspace(nullptr, n, nn, a.k, precision);
         if (ws == nullptr || wsb < need) {
             set_error("cgnn_mp_edge_bwd: workspace too small (%lld < %lld)", (long long)wsb, (long long)need);
             return CGNN_ERR_WORKSPACE;
@@ -346,9 +350,9 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         const int64_t chunk = E < CHUNK_ROWS ? E : CHUNK_ROWS;
         float* A1 = cv.take<float>(chunk * TC_H); float* A2 = cv.take<float>(chunk * TC_H); float* T = cv.take<float>(chunk * TC_H);
         float* G2 = cv.take<float>(chunk * TC_H); float* spare = cv.take<float>(chunk * TC_H); (void)spare;
-        float* Ps = cv.take<float>(n * TC_H); float* Pr = cv.take<float>(n * TC_H);
-        float* dPs = cv.take<float>(n * TC_H); float* dPr = cv.take<float>(n * TC_H);
-        if ((rc = project_nodes(ns, sc, m, a.h, n, Ps, Pr, s))) return rc;
+        float* Ps = cv.take<float>(nn * TC_H); float* Pr = cv.take<float>(n * TC_H);
+        float* dPs = cv.take<float>(nn * TC_H); float* dPr = cv.take<float>(n * TC_H);
+        if ((rc = project_nodes(ns, sc, m, a.h, n, nn, Ps, Pr, s))) return rc;
         for (int64_t r0 = 0, c = 0; r0 < E; r0 += chunk, ++c) {
             const int64_t rows = E - r0 < chunk ? E - r0 : chunk;       // chunk is a multiple of 256 and of k unless it is the whole graph
             const float* e_in = a.e_in + r0 * TC_H;
@@ -374,16 +378,23 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             }
         }
         // per-node sums of G1: by sender (transpose CSR, deterministic) and by receiver (dPr, from the chunks)
-        CGNN_CUDA(cudaMemsetAsync(dPs, 0, (size_t)n * TC_H * 4, s));
-        if ((rc = simt_scatter_to_senders(a.gs, 0, a.t_rowptr, a.t_perm, n, a.k, TC_H, dPs, s))) return rc;
-        if ((rc = run_wgrad(ns, dPs, a.h, n, g->W[0], 3 * TC_H, 0, nullptr, 0, sc.wg, s))) return rc;
+        CGNN_CUDA(cudaMemsetAsync(dPs, 0, (size_t)nn * TC_H * 4, s));
+        if ((rc = simt_scatter_to_senders(a.gs, 0, a.t_rowptr, a.t_perm, nn, a.k, TC_H, dPs, s))) return rc;
+        if ((rc = run_wgrad(ns, dPs, a.h, nn, g->W[0], 3 * TC_H, 0, nullptr, 0, sc.wg, s))) return rc;
         if ((rc = run_wgrad(ns, dPr, a.h, n, g->W[0], 3 * TC_H, TC_H, nullptr, 0, sc.wg, s))) return rc;
-        {   // dh += dPs W1s + dPr W1r
+        if (nn == n) {   // dh += dPs W1s + dPr W1r
             ChainOp op = base_op(ns, sc, n);
             op.in0 = dPs; op.in1 = dPr;
             op.blk[0] = {m.W[0], 3 * TC_H, 0, 0, 1}; op.blk[1] = {m.W[0], 3 * TC_H, 0, TC_H, 1};
             op.residual = a.dh; op.out = a.dh;
             if ((rc = run_chain(op, s))) return rc;
+        } else {         // halo rows only have the sender part
+            ChainOp op = base_op(ns, sc, nn);
+            op.in0 = dPs; op.blk[0] = {m.W[0], 3 * TC_H, 0, 0, 1}; op.residual = a.dh; op.out = a.dh;
+            if ((rc = run_chain(op, s))) return rc;
+            ChainOp op2 = base_op(ns, sc, n);
+            op2.in0 = dPr; op2.blk[0] = {m.W[0], 3 * TC_H, 0, TC_H, 1}; op2.residual = a.dh; op2.out = a.dh;
+            if ((rc = run_chain(op2, s))) return rc;
         }
         return CGNN_OK;
     }

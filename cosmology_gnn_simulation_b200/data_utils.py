@@ -16,7 +16,7 @@ import torch
 from . import ops
 from .graph import Data
 
-__all__ = ["extend_positions_torch", "generate_position_noise", "generate_temperature_noise", "preprocess"]
+__all__ = ["extend_positions_torch", "generate_position_noise", "generate_temperature_noise", "preprocess", "preprocess_slab"]
 
 
 def extend_positions_torch(positions, box_size):
@@ -72,19 +72,10 @@ def _cuda_device(device):
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def preprocess(position_seq, temperature_seq, metadata, target_position=None, target_temperature=None,
-               noise_std=0.0, num_neighbors=16, dt=None, box_size=None, *, edge_disp="raw", device=None):
-    """Builds the graph for one sample (data_utils.py:72-228).
-
-    position_seq [W,N,3], temperature_seq [W,N,1]; optional targets [1,N,3] / [1,N,1].
-    Returns a `Data` with x, edge_index, edge_attr, y_acc, y_temp_rate, pos, dt, box_size on the GPU.
-    `edge_disp="raw"` reproduces the reference's edge displacement (difference of wrapped positions,
-    data_utils.py:162); `"min_image"` uses the periodic image the neighbour was found at.
-    """
-    dt = float(dt)
-    box_size = float(box_size)
-    dev = _cuda_device(device if device is not None else (position_seq.device if position_seq.is_cuda else None))
-
+def _features_and_targets(position_seq, temperature_seq, metadata, target_position, target_temperature, noise_std, dt,
+                          box_size):
+    """Node features and normalised targets of one sample, in the reference's order of operations
+    (data_utils.py:86-145,166-214).  Returns (recent_pos [N,3], x [N,F], y_acc | None, y_temp | None)."""
     def md(key):
         return torch.tensor(metadata[key], dtype=torch.float32, device=position_seq.device)
 
@@ -129,6 +120,24 @@ def preprocess(position_seq, temperature_seq, metadata, target_position=None, ta
             tt = tt.reshape(recent_temp.shape)
         tt += temp_noise[:, -1]                      # in place (data_utils.py:206)
         y_temp = (((tt - recent_temp) / dt - md("temp_rate_mean")) / md("temp_rate_std")).float()
+    return recent_pos, x, y_acc, y_temp
+
+
+def preprocess(position_seq, temperature_seq, metadata, target_position=None, target_temperature=None,
+               noise_std=0.0, num_neighbors=16, dt=None, box_size=None, *, edge_disp="raw", device=None):
+    """Builds the graph for one sample (data_utils.py:72-228).
+
+    position_seq [W,N,3], temperature_seq [W,N,1]; optional targets [1,N,3] / [1,N,1].
+    Returns a `Data` with x, edge_index, edge_attr, y_acc, y_temp_rate, pos, dt, box_size on the GPU.
+    `edge_disp="raw"` reproduces the reference's edge displacement (difference of wrapped positions,
+    data_utils.py:162); `"min_image"` uses the periodic image the neighbour was found at.
+    """
+    dt = float(dt)
+    box_size = float(box_size)
+    dev = _cuda_device(device if device is not None else (position_seq.device if position_seq.is_cuda else None))
+    recent_pos, x, y_acc, y_temp = _features_and_targets(position_seq, temperature_seq, metadata, target_position,
+                                                         target_temperature, noise_std, dt, box_size)
+    n = recent_pos.shape[0]
 
     # ---- graph: cell-list k-NN + edge features on the GPU --------------------------------------
     pos_dev = recent_pos.contiguous().to(dev, non_blocking=True)
@@ -149,4 +158,48 @@ def preprocess(position_seq, temperature_seq, metadata, target_position=None, ta
     graph._cgnn_senders = senders            # int32 ELL neighbour table (edge e = receiver*k + rank)
     graph._cgnn_k = int(num_neighbors)
     graph._cgnn_nbr_ext = nbr_ext
+    return graph
+
+
+def preprocess_slab(position_seq, temperature_seq, metadata, target_position=None, target_temperature=None,
+                    noise_std=0.0, num_neighbors=16, dt=None, box_size=None, *, rank=0, world=1, group=None,
+                    edge_disp="raw", device=None):
+    """`preprocess` for one rank of a slab-sharded box (slab.py).  Every rank passes the SAME full sample;
+    it gets back the graph of its own x-slab: `x`, targets and `pos` for the owned particles, the k in-edges
+    of every owned particle (`edge_attr`, local int32 senders) and `halo` (the exchange plan).
+    `graph.order` [N] is the x-sort permutation (global id -> index in the input arrays) and
+    `graph.own_range` the owned global ids, so results can be scattered back to the input order."""
+    from . import slab as _slab
+    dt = float(dt)
+    box_size = float(box_size)
+    dev = _cuda_device(device if device is not None else (position_seq.device if position_seq.is_cuda else None))
+    recent_pos, x, y_acc, y_temp = _features_and_targets(position_seq, temperature_seq, metadata, target_position,
+                                                         target_temperature, noise_std, dt, box_size)
+    n = recent_pos.shape[0]
+    if n * 27 < num_neighbors:
+        raise ValueError(f"num_neighbors={num_neighbors} exceeds the 27*N={27 * n} periodic candidates")
+    pos_dev = recent_pos.contiguous().to(dev, non_blocking=True)
+    order = torch.sort(pos_dev[:, 0], stable=True)[1]                 # identical on every rank (same data)
+    pos_sorted = pos_dev[order].contiguous()
+    bounds = _slab.slab_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    nbr_ext = ops.knn_periodic(pos_sorted, box_size, int(num_neighbors), query_range=(lo, hi - lo))
+    senders_g, _, edge_attr = ops.edge_features(pos_sorted, nbr_ext, box_size, disp=edge_disp, want_edge_index=False, q0=lo)
+    plan, senders_local, halo_gid = _slab.plan_from_global_senders(senders_g, bounds, rank, world, group)
+    own = order[lo:hi]
+
+    def pick(t):
+        return None if t is None else t.to(dev, non_blocking=True)[own].contiguous()
+
+    graph = Data(
+        x=pick(x), edge_index=None, edge_attr=edge_attr, y_acc=pick(y_acc), y_temp_rate=pick(y_temp),
+        pos=pos_sorted[lo:hi].contiguous(), dt=torch.tensor([dt], dtype=torch.float32, device=dev),
+        box_size=torch.tensor([box_size], dtype=torch.float32, device=dev),
+    )
+    graph._cgnn_senders = senders_local.contiguous()
+    graph._cgnn_k = int(num_neighbors)
+    graph.halo = plan
+    graph.order = order
+    graph.own_range = (lo, hi)
+    graph.halo_gid = halo_gid
     return graph

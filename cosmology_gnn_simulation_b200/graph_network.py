@@ -73,7 +73,8 @@ class _Plan:
     """Static description of one forward call, shared by forward and backward."""
 
     def __init__(self, n_steps, message, precision, k, enc_node, enc_edge, proc_node, proc_edge, dec_acc,
-                 dec_temp, groups, edge_ckpt_every):
+                 dec_temp, groups, edge_ckpt_every, halo=None):
+        self.halo = halo                      # slab.HaloPlan of a sharded box, or None
         self.n_steps, self.message, self.precision, self.k = n_steps, message, precision, k
         self.enc_node, self.enc_edge = enc_node, enc_edge
         self.proc_node, self.proc_edge = proc_node, proc_edge
@@ -107,7 +108,18 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         train = any(ctx.needs_input_grad[3:])
         edge_mode = p.message == "edge"
 
-        h = ops.mlp_rows_fwd(p.enc_node, x, prec)
+        halo = p.halo
+        n_loc = n if halo is None else halo.n_loc          # node array of a slab rank: [owned | halo senders]
+
+        def with_halo(h_own_rows):
+            if halo is None:
+                return h_own_rows
+            full = torch.empty((n_loc, L), dtype=torch.float32, device=x.device)
+            full[:n] = h_own_rows
+            halo.exchange(full)
+            return full
+
+        h = with_halo(ops.mlp_rows_fwd(p.enc_node, x, prec))
         e = ops.mlp_rows_fwd(p.enc_edge, edge_attr, prec)
         hs, aggs, e_ckpt = [h], [], {}
         keep_e = train and edge_mode
@@ -127,15 +139,17 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
                 ops.aggregate_senders(h, senders, k, agg)
             # inference updates h in place: a node tile only reads its own rows of h
             h_next = torch.empty_like(h) if train else h
-            ops.mp_node_fwd(p.proc_node[t], h, agg, h_next, prec)
+            ops.mp_node_fwd(p.proc_node[t], h[:n], agg, h_next[:n], prec)
+            if halo is not None:
+                halo.exchange(h_next)                       # the one collective of a message-passing step
             h, e = h_next, e_next
             if train:
                 hs.append(h)
                 aggs.append(agg)
             if keep_e and (t + 1) % s == 0 and t + 1 < M:
                 e_ckpt[t + 1] = e
-        acc = ops.mlp_rows_fwd(p.dec_acc, h, prec)
-        temp = ops.mlp_rows_fwd(p.dec_temp, h, prec)
+        acc = ops.mlp_rows_fwd(p.dec_acc, h[:n], prec)
+        temp = ops.mlp_rows_fwd(p.dec_temp, h[:n], prec)
 
         if train:
             ctx.plan, ctx.senders, ctx.transpose_fn = plan, senders, transpose_fn
@@ -159,22 +173,32 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
             for i, g in enumerate(tensors):
                 grads[first + i] = g
 
-        n, L = hs[0].shape
+        n_loc, L = hs[0].shape
+        halo = p.halo
+        n = n_loc if halo is None else halo.n_own
         d_acc = d_acc.contiguous() if d_acc is not None else torch.zeros((n, p.dec_acc.out_dim), device=hs[0].device)
         d_temp = d_temp.contiguous() if d_temp is not None else torch.zeros((n, 1), device=hs[0].device)
 
-        g_acc, dh_a = ops.mlp_rows_bwd(p.dec_acc, hs[M], d_acc, True, prec)
-        g_temp, dh_t = ops.mlp_rows_bwd(p.dec_temp, hs[M], d_temp, True, prec)
+        g_acc, dh_a = ops.mlp_rows_bwd(p.dec_acc, hs[M][:n], d_acc, True, prec)
+        g_temp, dh_t = ops.mlp_rows_bwd(p.dec_temp, hs[M][:n], d_temp, True, prec)
         put(p.dec_acc, g_acc)
         put(p.dec_temp, g_temp)
-        dh = dh_a.add_(dh_t)
+        if halo is None:
+            dh = dh_a.add_(dh_t)
+        else:
+            dh = torch.zeros((n_loc, L), dtype=torch.float32, device=dh_a.device)
+            dh[:n] = dh_a.add_(dh_t)
         de = None
         rowptr, perm = ctx.transpose_fn()
 
         def step_backward(t, e_t, dh, de):
-            dh_new = torch.empty_like(dh)
-            dagg = torch.empty_like(dh)
-            put(p.proc_node[t], ops.mp_node_bwd(p.proc_node[t], hs[t], aggs[t], dh, dh_new, dagg, prec))
+            if halo is not None:
+                halo.reduce_grad(dh)              # gradients other ranks hold for my rows come home first
+                dh_new = torch.zeros_like(dh)
+            else:
+                dh_new = torch.empty_like(dh)
+            dagg = torch.empty((n, L), dtype=torch.float32, device=dh.device)
+            put(p.proc_node[t], ops.mp_node_bwd(p.proc_node[t], hs[t][:n], aggs[t], dh[:n], dh_new[:n], dagg, prec))
             if edge_mode:
                 de_new = torch.empty_like(e_t)
                 gs = torch.empty_like(e_t)
@@ -204,7 +228,9 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
                 dh, de = step_backward(t, None, dh, None)
 
         need_dx, need_dea = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
-        g_en, dx = ops.mlp_rows_bwd(p.enc_node, ctx.x, dh, need_dx, prec)
+        if halo is not None:
+            halo.reduce_grad(dh)
+        g_en, dx = ops.mlp_rows_bwd(p.enc_node, ctx.x, dh[:n].contiguous(), need_dx, prec)
         put(p.enc_node, g_en)
         dea = None
         if edge_mode:
@@ -269,8 +295,10 @@ class EncodeProcessDecode(nn.Module):
     def _graph_tables(self, graph, n: int):
         """int32 senders (ELL: edge e = receiver*k + rank) and a lazy sender-sorted transpose."""
         senders = getattr(graph, "_cgnn_senders", None)
-        edge_index = graph.edge_index
-        if senders is None or senders.device != edge_index.device:
+        edge_index = getattr(graph, "edge_index", None)
+        if senders is None and edge_index is None:
+            raise ValueError("cgnn: the graph has neither edge_index nor the int32 neighbour table of preprocess")
+        if edge_index is not None and (senders is None or senders.device != edge_index.device):
             key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version)
             hit = self._graph_cache.get("key") == key
             if not hit:
@@ -280,13 +308,15 @@ class EncodeProcessDecode(nn.Module):
         k = senders.numel() // n
         if senders.numel() != n * k or k < 1:
             raise ValueError("cgnn: edge count is not a multiple of the node count")
+        halo = getattr(graph, "halo", None)
+        n_nodes = n if halo is None else halo.n_loc          # transpose rows: owned + halo senders
         if self.num_neighbors is not None and k != self.num_neighbors:
             raise ValueError(f"graph has in-degree {k}, model was built with num_neighbors={self.num_neighbors}")
         holder = {}
 
         def transpose():
             if "t" not in holder:
-                holder["t"] = ops.csr_transpose(senders, n)
+                holder["t"] = ops.csr_transpose(senders, n_nodes)
             return holder["t"]
 
         return senders, k, transpose
@@ -322,6 +352,7 @@ class EncodeProcessDecode(nn.Module):
         n = x.shape[0]
         senders, k, transpose = self._graph_tables(input_graph, n)
         plan = _Plan(self._num_message_passing_steps, self.message, self.precision, k, enc_node, enc_edge,
-                     proc_node, proc_edge, dec_acc, dec_temp, groups, self.edge_ckpt_every)
+                     proc_node, proc_edge, dec_acc, dec_temp, groups, self.edge_ckpt_every,
+                     halo=getattr(input_graph, "halo", None))
         acc, temp = _EncodeProcessDecodeFn.apply(plan, senders, transpose, x, edge_attr, *flat)
         return {"acceleration": acc, "temp_rate": temp}

@@ -14,37 +14,40 @@ from ._lib import CgnnMlp, CgnnMlpGrad, PREC, DISP, check, lib, ptr, require_cud
 # ------------------------------------------------------------------------------------------------
 # graph build (K1, K2)
 # ------------------------------------------------------------------------------------------------
-def knn_periodic(pos: torch.Tensor, box_size: float, k: int) -> torch.Tensor:
+def knn_periodic(pos: torch.Tensor, box_size: float, k: int, query_range=None) -> torch.Tensor:
     """Replaces `extend_positions_torch` + `torch_cluster.knn` (data_utils.py:148-149).
-    pos [N,3] fp32 CUDA -> ext index [N,k] int32 (c = shift*N + j), rows ascending in (d2, c)."""
+    pos [N,3] fp32 CUDA -> ext index [N,k] int32 (c = shift*N + j), rows ascending in (d2, c).
+    `query_range=(q0, nq)`: answer only the queries q0 <= i < q0+nq (a rank's slab) -> [nq,k]."""
     require_cuda(pos, "pos", torch.float32)
     n = pos.shape[0]
     if pos.dim() != 2 or pos.shape[1] != 3:
         raise ValueError("pos must be [N,3]")
-    out = torch.empty((n, k), dtype=torch.int32, device=pos.device)
+    q0, nq = (0, n) if query_range is None else (int(query_range[0]), int(query_range[1]))
+    out = torch.empty((nq, k), dtype=torch.int32, device=pos.device)
     with torch.cuda.device(pos.device):
         nbytes = lib().cgnn_knn_workspace_bytes(n)
         ws = workspace.get(pos.device, "knn", nbytes)
-        check(lib().cgnn_knn_periodic(ptr(pos), n, float(box_size), int(k), ptr(out), ptr(ws), ws.numel(),
-                                      stream_ptr(pos.device)), "cgnn_knn_periodic")
+        check(lib().cgnn_knn_periodic_range(ptr(pos), n, float(box_size), int(k), q0, nq, ptr(out), ptr(ws), ws.numel(),
+                                            stream_ptr(pos.device)), "cgnn_knn_periodic")
     return out
 
 
 def edge_features(pos: torch.Tensor, nbr_ext: torch.Tensor, box_size: float, disp: str = "raw",
-                  want_edge_index: bool = True):
+                  want_edge_index: bool = True, q0: int = 0):
     """Replaces data_utils.py:150-164.  Returns (senders int32 [E], edge_index int64 [2,E] | None,
-    edge_attr fp32 [E,4])."""
+    edge_attr fp32 [E,4]).  `nbr_ext` may cover only the receivers q0 <= i < q0 + nbr_ext.shape[0]
+    (senders / edge_index then hold global ids)."""
     require_cuda(pos, "pos", torch.float32)
     require_cuda(nbr_ext, "nbr_ext", torch.int32)
-    n, k = nbr_ext.shape
-    e = n * k
+    nq, k = nbr_ext.shape
+    e = nq * k
     senders = torch.empty(e, dtype=torch.int32, device=pos.device)
     edge_index = torch.empty((2, e), dtype=torch.int64, device=pos.device) if want_edge_index else None
     edge_attr = torch.empty((e, 4), dtype=torch.float32, device=pos.device)
     with torch.cuda.device(pos.device):
-        check(lib().cgnn_edge_features(ptr(pos), ptr(nbr_ext), n, k, float(box_size), DISP[disp], ptr(senders),
-                                       ptr(edge_index), ptr(edge_attr), stream_ptr(pos.device)),
-              "cgnn_edge_features")
+        check(lib().cgnn_edge_features_range(ptr(pos), ptr(nbr_ext), pos.shape[0], k, float(box_size), DISP[disp],
+                                             int(q0), nq, ptr(senders), ptr(edge_index), ptr(edge_attr),
+                                             stream_ptr(pos.device)), "cgnn_edge_features")
     return senders, edge_index, edge_attr
 
 
@@ -190,7 +193,9 @@ EDGE_FWD_EVENTS = None
 
 
 def mp_edge_fwd(p: MlpParams, h, e_in, senders, k: int, e_out, agg_edge, precision: str = "fp32"):
+    """h may carry halo rows after the receivers (slab sharding): receivers = e_in rows / k, nodes = h rows."""
     m = p.c_struct()
+    n_recv = e_in.shape[0] // k
     with torch.cuda.device(h.device):
         ev = None
         if EDGE_FWD_EVENTS is not None:
@@ -200,7 +205,7 @@ def mp_edge_fwd(p: MlpParams, h, e_in, senders, k: int, e_out, agg_edge, precisi
         if nbytes < 0:
             check(-1, "cgnn_mp_edge_fwd_workspace_bytes")
         ws = workspace.get(h.device, "edge_fwd", nbytes) if nbytes > 0 else None
-        check(lib().cgnn_mp_edge_fwd(byref(m), ptr(h), ptr(e_in), ptr(senders), h.shape[0], k, ptr(e_out),
+        check(lib().cgnn_mp_edge_fwd(byref(m), ptr(h), ptr(e_in), ptr(senders), n_recv, h.shape[0], k, ptr(e_out),
                                      ptr(agg_edge), ptr(ws), 0 if ws is None else ws.numel(), PREC[precision],
                                      stream_ptr(h.device)), "cgnn_mp_edge_fwd")
         if ev is not None:
@@ -210,7 +215,7 @@ def mp_edge_fwd(p: MlpParams, h, e_in, senders, k: int, e_out, agg_edge, precisi
 
 def aggregate_senders(h, senders, k: int, agg):
     with torch.cuda.device(h.device):
-        check(lib().cgnn_aggregate_senders(ptr(h), ptr(senders), h.shape[0], k, h.shape[1], ptr(agg),
+        check(lib().cgnn_aggregate_senders(ptr(h), ptr(senders), agg.shape[0], k, h.shape[1], ptr(agg),
                                            stream_ptr(h.device)), "cgnn_aggregate_senders")
 
 
@@ -226,8 +231,8 @@ def mp_node_fwd(p: MlpParams, h, agg, h_out, precision: str = "fp32"):
               "cgnn_mp_node_fwd")
 
 
-def _mp_bwd_ws(mlp_c: CgnnMlp, n: int, k: int, precision: str, device):
-    nbytes = lib().cgnn_mp_bwd_workspace_bytes(byref(mlp_c), n, k, PREC[precision])
+def _mp_bwd_ws(mlp_c: CgnnMlp, n: int, k: int, precision: str, device, n_nodes=None):
+    nbytes = lib().cgnn_mp_bwd_workspace_bytes(byref(mlp_c), n, n if n_nodes is None else n_nodes, k, PREC[precision])
     if nbytes < 0:
         check(-1, "cgnn_mp_bwd_workspace_bytes")
     return workspace.get(device, "mlp_bwd", nbytes)
@@ -250,10 +255,11 @@ def mp_edge_bwd(p: MlpParams, h, e_in, senders, rowptr, perm, k: int, de_next, d
     (`rowptr`, `perm`: sender-sorted transpose from `csr_transpose`); `gs` [E,L] is scratch."""
     m = p.c_struct()
     g, grads = p.new_grads()
+    n_recv = e_in.shape[0] // k
     with torch.cuda.device(h.device):
-        ws = _mp_bwd_ws(m, h.shape[0], k, precision, h.device)
+        ws = _mp_bwd_ws(m, n_recv, k, precision, h.device, n_nodes=h.shape[0])
         check(lib().cgnn_mp_edge_bwd(byref(m), byref(g), ptr(h), ptr(e_in), ptr(senders), ptr(rowptr), ptr(perm),
-                                     h.shape[0], k, ptr(de_next), ptr(dagg), ptr(de), ptr(dh), ptr(gs), ptr(ws),
+                                     n_recv, h.shape[0], k, ptr(de_next), ptr(dagg), ptr(de), ptr(dh), ptr(gs), ptr(ws),
                                      ws.numel(), PREC[precision], stream_ptr(h.device)), "cgnn_mp_edge_bwd")
     return grads
 

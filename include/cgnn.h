@@ -82,6 +82,10 @@ int64_t cgnn_launch_count(void);
 int64_t cgnn_knn_workspace_bytes(int64_t n);
 int cgnn_knn_periodic(const float* pos, int64_t n, float box, int32_t k, int32_t* nbr_ext,
                       void* workspace, int64_t workspace_bytes, cgnn_stream stream);
+/* slab sharding: all N particles are candidates, only the queries q0 <= i < q0 + nq are answered
+ * (nbr_ext[nq][k]); a rank owns a contiguous index range of the x-sorted particles */
+int cgnn_knn_periodic_range(const float* pos, int64_t n, float box, int32_t k, int64_t q0, int64_t nq,
+                            int32_t* nbr_ext, void* workspace, int64_t workspace_bytes, cgnn_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2  graph products -- replaces data_utils.py:150-164.
@@ -93,6 +97,11 @@ int cgnn_knn_periodic(const float* pos, int64_t n, float box, int32_t k, int32_t
 int cgnn_edge_features(const float* pos, const int32_t* nbr_ext, int64_t n, int32_t k, float box,
                        int32_t disp_mode, int32_t* senders, int64_t* edge_index, float* edge_attr,
                        cgnn_stream stream);
+
+/* the same for the receivers q0 <= i < q0 + nq only (nbr_ext[nq][k]); senders / edge_index hold GLOBAL ids */
+int cgnn_edge_features_range(const float* pos, const int32_t* nbr_ext, int64_t n, int32_t k, float box,
+                             int32_t disp_mode, int64_t q0, int64_t nq, int32_t* senders, int64_t* edge_index,
+                             float* edge_attr, cgnn_stream stream);
 
 /* Sender-sorted transpose of the receiver-sorted graph (needed for the deterministic d/dh[sender]):
  * rowptr[N+1], perm[E] = edge ids grouped by sender, ascending inside each group. */
@@ -130,10 +139,13 @@ int cgnn_mlp_rows_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const floa
  */
 /* workspace of cgnn_mp_edge_fwd (0 for CGNN_PREC_FP32; the tensor-core modes stage split-bf16 weight
  * images and the per-node layer-1 partial products there) */
-int64_t cgnn_mp_edge_fwd_workspace_bytes(const cgnn_mlp* edge_mlp, int64_t n, int32_t precision);
+/* Slab sharding: a rank's node array is [n owned receivers | halo senders], n_nodes rows in all; the
+ * receivers are rows 0..n-1, `senders` index all n_nodes rows.  Single GPU: n_nodes == n. */
+int64_t cgnn_mp_edge_fwd_workspace_bytes(const cgnn_mlp* edge_mlp, int64_t n_nodes, int32_t precision);
 int cgnn_mp_edge_fwd(const cgnn_mlp* edge_mlp, const float* h, const float* e_in,
-                     const int32_t* senders, int64_t n, int32_t k, float* e_out, float* agg_edge,
-                     void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
+                     const int32_t* senders, int64_t n, int64_t n_nodes, int32_t k, float* e_out,
+                     float* agg_edge, void* workspace, int64_t workspace_bytes, int32_t precision,
+                     cgnn_stream stream);
 int cgnn_aggregate_senders(const float* h, const int32_t* senders, int64_t n, int32_t k,
                            int32_t latent, float* agg, cgnn_stream stream);
 int64_t cgnn_mp_node_fwd_workspace_bytes(const cgnn_mlp* node_mlp, int64_t n, int32_t precision);
@@ -152,14 +164,14 @@ int cgnn_mp_node_fwd(const cgnn_mlp* node_mlp, const float* h, const float* agg,
  *  cgnn_scatter_to_senders: dh[j] += sum over edges e with sender j (perm order) of src[e] (stride L)
  *      or of src[e / k] (src_is_per_receiver: message = sender, where src = dagg).
  */
-/* workspace of cgnn_mp_node_bwd (k = 0) / cgnn_mp_edge_bwd (k = in-degree) */
-int64_t cgnn_mp_bwd_workspace_bytes(const cgnn_mlp* mlp, int64_t n, int32_t k, int32_t precision);
+/* workspace of cgnn_mp_node_bwd (k = 0, n_nodes = n) / cgnn_mp_edge_bwd (k = in-degree) */
+int64_t cgnn_mp_bwd_workspace_bytes(const cgnn_mlp* mlp, int64_t n, int64_t n_nodes, int32_t k, int32_t precision);
 int cgnn_mp_node_bwd(const cgnn_mlp* node_mlp, const cgnn_mlp_grad* grad, const float* h,
                      const float* agg, const float* dh_next, int64_t n, float* dh, float* dagg,
                      void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
 int cgnn_mp_edge_bwd(const cgnn_mlp* edge_mlp, const cgnn_mlp_grad* grad, const float* h,
                      const float* e_in, const int32_t* senders, const int32_t* t_rowptr,
-                     const int32_t* t_perm, int64_t n, int32_t k,
+                     const int32_t* t_perm, int64_t n, int64_t n_nodes, int32_t k,
                      const float* de_next, const float* dagg, float* de, float* dh, float* gs,
                      void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
 int cgnn_scatter_to_senders(const float* src, int32_t src_is_per_receiver, const int32_t* rowptr,

@@ -1,0 +1,127 @@
+"""GPU: slab-sharded box (slab.py, preprocess_slab) against the single-GPU run of the same box.
+
+world = 1 runs everywhere (the x-sort permutation and the range k-NN / edge-feature entry points);
+world = 2 needs two GPUs (NCCL) and is skipped otherwise -- run it with `gpurun --gpus 2`."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _setup(n, k, L, M, seed=0):
+    from cosmology_gnn_simulation_b200 import synthetic
+    from oracle import model_ref
+    box = synthetic.make_box(n, "uniform", seed=seed)
+    params = model_ref.init_params(L, L, 2, M, 3, seed=seed)
+    return box, params
+
+
+def _run_full(box, params, k, L, M, message, precision, dev):
+    from cosmology_gnn_simulation_b200.data_utils import preprocess
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    md = box["metadata"]
+    g = preprocess(box["Coordinates"][:5], box["InternalEnergy"][:5], md, box["Coordinates"][5:6].clone(),
+                   box["InternalEnergy"][5:6].clone(), num_neighbors=k, dt=md["dt"], box_size=md["box_size"], device=dev)
+    model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision)
+    model.load_state_dict(params)
+    model = model.to(dev)
+    pred = model(g)
+    ls = combined_loss(pred, g, md["dt"], 1.0, 1.0, 0.1)
+    ls["loss"].backward()
+    grads = {k_: (None if p.grad is None else p.grad.detach().cpu()) for k_, p in model.named_parameters()}
+    return pred["acceleration"].detach().cpu(), pred["temp_rate"].detach().cpu(), float(ls["loss"]), grads
+
+
+def _run_slab(box, params, k, L, M, message, precision, dev, rank, world):
+    from cosmology_gnn_simulation_b200 import distributed as cd
+    from cosmology_gnn_simulation_b200.data_utils import preprocess_slab
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.slab import slab_loss
+    md = box["metadata"]
+    g = preprocess_slab(box["Coordinates"][:5], box["InternalEnergy"][:5], md, box["Coordinates"][5:6].clone(),
+                        box["InternalEnergy"][5:6].clone(), num_neighbors=k, dt=md["dt"], box_size=md["box_size"],
+                        rank=rank, world=world, device=dev)
+    model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision)
+    model.load_state_dict(params)
+    model = model.to(dev)
+    pred = model(g)
+    ls = slab_loss(pred, g, md["dt"], 1.0, 1.0, 0.1)
+    ls["loss"].backward()
+    cd.GradientBucket(model.parameters()).all_reduce(average=False)
+    grads = {k_: (None if p.grad is None else p.grad.detach().cpu()) for k_, p in model.named_parameters()}
+    lo, hi = g.own_range
+    own = g.order[lo:hi].cpu()
+    return own, pred["acceleration"].detach().cpu(), pred["temp_rate"].detach().cpu(), float(ls["loss"]), grads, g.halo.n_halo
+
+
+def _compare(full, slabs, n, tol, gtol):
+    acc_f, temp_f, loss_f, grads_f = full
+    acc = torch.empty_like(acc_f)
+    temp = torch.empty_like(temp_f)
+    seen = torch.zeros(n, dtype=torch.bool)
+    for own, a, t, loss, grads, _ in slabs:
+        acc[own], temp[own] = a, t
+        seen[own] = True
+        assert abs(loss - loss_f) < 10 * tol * abs(loss_f)
+    assert bool(seen.all())
+    assert rel_l2(acc, acc_f) < tol and rel_l2(temp, temp_f) < tol
+    grads = slabs[0][4]
+    for name, gf in grads_f.items():
+        if gf is None:
+            assert grads[name] is None, name
+        else:
+            assert rel_l2(grads[name], gf) < gtol, (name, rel_l2(grads[name], gf))
+
+
+@pytest.mark.parametrize("message", ["edge", "sender"])
+def test_slab_world1_equals_plain_graph(message):
+    dev = torch.device("cuda", 0)
+    n, k, L, M = 3000, 16, 64, 3
+    box, params = _setup(n, k, L, M)
+    full = _run_full(box, params, k, L, M, message, "fp32", dev)
+    one = _run_slab(box, params, k, L, M, message, "fp32", dev, 0, 1)
+    assert one[5] == 0
+    _compare(full, [one], n, 2e-5, 1e-3)
+
+
+def _worker(rank, world, port, out, message, precision):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from cosmology_gnn_simulation_b200 import distributed as cd
+    cd.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    n, k, L, M = 6000, 16, 128, 3
+    box, params = _setup(n, k, L, M)
+    res = _run_slab(box, params, k, L, M, message, precision, dev, rank, world)
+    torch.save(res, f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("message,precision", [("edge", "fp32"), ("sender", "fp32"), ("edge", "bf16x3")])
+def test_slab_world2_equals_single_gpu(tmp_path, message, precision):
+    world = 2
+    out = str(tmp_path / "res")
+    mp.spawn(_worker, args=(world, _free_port(), out, message, precision), nprocs=world, join=True)
+    slabs = [torch.load(f"{out}.{r}") for r in range(world)]
+    assert all(s[5] > 0 for s in slabs)                       # both ranks really have halo rows
+    dev = torch.device("cuda", 0)
+    n, k, L, M = 6000, 16, 128, 3
+    box, params = _setup(n, k, L, M)
+    full = _run_full(box, params, k, L, M, message, precision, dev)
+    tol, gtol = (2e-5, 1e-3) if precision == "fp32" else (1e-3, 1e-2)
+    _compare(full, slabs, n, tol, gtol)
