@@ -169,19 +169,26 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, args.message, "fp32 (CPU)", args.gpus),
+        "config": workload_config(args.workload, args.message, "fp32 (CPU)", args.gpus, args.sharding),
         "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, message, precision, gpus):
+def workload_config(name, message, precision, gpus, sharding="slab"):
     n, k, L, M, kind = WORKLOADS[name]
-    return {"workload": f"{name}: training step, {n} particles ({kind} periodic box), k={k}, latent={L}, "
+    if gpus == 1:
+        par = "single GPU"
+    elif sharding == "slab":
+        par = (f"slab{gpus}: ONE box of {gpus}x{n} particles cut into {gpus} equal-count x-slabs; per MP step one halo "
+               f"exchange of boundary latents (NCCL P2P), 5-float loss all-reduce, gradient all-reduce(SUM)")
+    else:
+        par = f"dp{gpus} (one box replica per GPU, gradient all-reduce)"
+    return {"workload": f"{name}: training step, {n} particles per GPU ({kind} periodic box), k={k}, latent={L}, "
                         f"{M} MP steps, acc+temp+momentum loss",
             "particles_per_gpu": n, "k": k, "latent": L, "mp_steps": M, "message": message, "precision": precision,
-            "parallelism": f"dp{gpus} (one box replica per GPU, gradient all-reduce)" if gpus > 1 else "single GPU",
+            "parallelism": par,
             "l2": "inputs larger than L2 (edge latent stream alone exceeds 126 MB)" if n * k * L * 4 > 126e6
                   else "L2 flushed between timed steps (256 MB write)"}
 
@@ -192,9 +199,10 @@ def workload_config(name, message, precision, gpus):
 def run_gpu(args):
     from cosmology_gnn_simulation_b200 import _lib, ops, synthetic
     from cosmology_gnn_simulation_b200 import distributed as cd
-    from cosmology_gnn_simulation_b200.data_utils import preprocess
+    from cosmology_gnn_simulation_b200.data_utils import preprocess, preprocess_slab
     from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
     from cosmology_gnn_simulation_b200.loss import combined_loss
+    from cosmology_gnn_simulation_b200.slab import slab_loss
     import torch.distributed as dist
 
     rank, world, local = cd.init_from_env()
@@ -205,7 +213,10 @@ def run_gpu(args):
     n, k, L, M, kind = WORKLOADS[args.workload]
     message, precision = args.message, args.precision
 
-    box = synthetic.make_box(n, kind, seed=rank)
+    slab = world > 1 and args.sharding == "slab"
+    # slab: every rank holds the same box of world * n particles and owns one x-slab of it (weak scaling);
+    # replica: every rank has its own box of n particles
+    box = synthetic.make_box(n * world, kind, seed=0) if slab else synthetic.make_box(n, kind, seed=rank)
     md = box["metadata"]
     coords_host = box["Coordinates"].pin_memory()
     energy_host = box["InternalEnergy"].pin_memory()
@@ -217,6 +228,9 @@ def run_gpu(args):
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev) if n * k * L * 4 <= 126e6 else None
 
     def build_graph(coords, energy):
+        if slab:
+            return preprocess_slab(coords[:5], energy[:5], md, coords[5:6], energy[5:6], noise_std=0.0, num_neighbors=k,
+                                   dt=md["dt"], box_size=md["box_size"], rank=rank, world=world, device=dev)
         return preprocess(coords[:5], energy[:5], md, coords[5:6], energy[5:6], noise_std=0.0, num_neighbors=k,
                           dt=md["dt"], box_size=md["box_size"], device=dev)
 
@@ -226,9 +240,14 @@ def run_gpu(args):
         for p in model.parameters():
             p.grad = None
         pred = model(g)
-        ls = combined_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
-        ls["loss"].backward()
-        bucket.all_reduce(average=True)
+        if slab:
+            ls = slab_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
+            ls["loss"].backward()
+            bucket.all_reduce(average=False)          # every rank holds the partial gradient of ONE global loss
+        else:
+            ls = combined_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
+            ls["loss"].backward()
+            bucket.all_reduce(average=True)
         return ls
 
     def barrier():
@@ -279,7 +298,7 @@ def run_gpu(args):
     e2e_value = world * n * args.steps / e2e_s
 
     # ---- graph build alone (reported apart; not part of the model application) -----
-    pos_dev = graph.pos
+    pos_dev = graph.pos.contiguous()
     for _ in range(2):
         ops.knn_periodic(pos_dev, md["box_size"], k)
     torch.cuda.synchronize(dev)
@@ -310,7 +329,7 @@ def run_gpu(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16 operands, f32 accumulate/storage)", "bf16": "bf16"}[precision],
         "data": "synthetic",
-        "config": workload_config(args.workload, message, precision, world),
+        "config": workload_config(args.workload, message, precision, world, args.sharding),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
                 "includes": "H2D of the 6 frames, graph build (k-NN + features), forward, loss, backward, D2H of the 4 loss scalars"},
@@ -350,6 +369,9 @@ def main():
     ap.add_argument("--message", default="edge", choices=["sender", "edge"],
                     help="edge: the Interaction Network of the north star (default); sender: what PyG's default message() computes")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--sharding", default="slab", choices=["slab", "replica"],
+                    help="N > 1: slab = one box of N x particles cut into x-slabs with halo exchange (default); "
+                         "replica = one independent box per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cgnn" else args.warmup
