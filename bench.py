@@ -359,6 +359,41 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_rollout(args):
+    """Inference rollout (BASELINE configs[3] shape at one GPU's share): per step the k-NN graph is rebuilt, the
+    model runs forward only and the integrator advances the box, all device resident (rollout.py)."""
+    from cosmology_gnn_simulation_b200 import _lib, synthetic
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.rollout import rollout
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    n, k, L, M, kind = WORKLOADS[args.workload]
+    box = synthetic.make_box(n, kind, seed=0)
+    md = box["metadata"]
+    torch.manual_seed(0)
+    model = EncodeProcessDecode(L, L, 2, M, 3, message=args.message, precision=args.precision).to(dev)
+    data = {"Coordinates": box["Coordinates"][:6].to(dev), "InternalEnergy": box["InternalEnergy"][:6].to(dev)}
+    rollout(model, data, md, 0.0, md["dt"], md["box_size"], window_size=5, num_neighbors=k, n_steps=max(args.warmup, 3))
+    torch.cuda.synchronize(dev)
+    l0 = _lib.launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        s.record()
+        out = rollout(model, data, md, 0.0, md["dt"], md["box_size"], window_size=5, num_neighbors=k, n_steps=args.steps)
+        e.record()
+        torch.cuda.synchronize(dev)
+    ms = s.elapsed_time(e)
+    line = {"metric": "particle-steps/sec of an inference rollout (k-NN rebuild + forward + integrator per step)",
+            "value": n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"rollout of {args.workload}: {n} particles, k={k}, latent={L}, {M} MP steps, "
+                                   f"graph rebuilt every step, device-resident trajectory", "message": args.message},
+            "clocks": clocks.summary(), "gpu_launches": int(_lib.launch_count() - l0),
+            "finite": bool(torch.isfinite(out["Coordinates"]).all())}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -373,9 +408,12 @@ def main():
                     help="N > 1: slab = one box of N x particles cut into x-slabs with halo exchange (default); "
                          "replica = one independent box per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rollout", action="store_true", help="time an inference rollout of the workload instead of a training step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cgnn" else args.warmup
-    if args.impl == "reference":
+    if args.rollout:
+        run_rollout(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
