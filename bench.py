@@ -30,6 +30,8 @@ WORKLOADS = {
     "config1": (4096, 16, 64, 5, "uniform"),
     "config2": (32 ** 3, 16, 128, 10, "uniform"),
     "config3": (128 ** 3, 32, 128, 10, "uniform"),
+    "config2-clustered": (32 ** 3, 16, 128, 10, "clustered"),
+    "config3-clustered": (128 ** 3, 32, 128, 10, "clustered"),
     "tiny": (2048, 8, 32, 2, "uniform"),
 }
 W_ACC, W_TEMP, W_MOM = 1.0, 1.0, 0.1
@@ -169,8 +171,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, args.message, "fp32 (CPU)", args.gpus, args.sharding),
-        "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "config": workload_config(args.workload, args.message, args.precision, args.gpus, args.sharding),
+        "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
+                         "arithmetic": "fp32 torch CPU ops (the reference's own), all host threads"},
         "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

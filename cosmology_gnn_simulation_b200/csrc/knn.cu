@@ -8,6 +8,10 @@
 //   * distances use the reference's fp32 recipe with explicit _rn intrinsics (no FMA contraction),
 //   * 64-bit keys (float_bits(d2) << 32 | c) make the order independent of the visiting order,
 //   * a ring is only skipped when its cells provably cannot hold a key below the current k-th.
+// Clustered boxes: the particles are binned into a small pyramid of grids (cell width halving per level)
+// and every query searches on the coarsest level whose own cell holds at most ~k particles, so a dense
+// clump is walked on a fine grid and a void on the coarse one -- same exhaustive-up-to-the-bound search,
+// same result, but O(k) candidates per ring instead of O(clump size).
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -35,9 +39,9 @@ __device__ __forceinline__ int cell_coord(float x, float inv_w, int nc) {
 }
 
 __global__ void knn_count_cells(const float* __restrict__ pos, int64_t n, float inv_w, int nc,
-                                int* __restrict__ cell_of, int* __restrict__ count) {
+                                int* __restrict__ cell_of, int* __restrict__ count, const int* __restrict__ enable) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (enable != nullptr && *enable == 0)) return;
     int cx = cell_coord(pos[3 * i + 0], inv_w, nc);
     int cy = cell_coord(pos[3 * i + 1], inv_w, nc);
     int cz = cell_coord(pos[3 * i + 2], inv_w, nc);
@@ -47,11 +51,20 @@ __global__ void knn_count_cells(const float* __restrict__ pos, int64_t n, float 
 }
 
 __global__ void knn_scatter(const float* __restrict__ pos, int64_t n, const int* __restrict__ cell_of,
-                            int* __restrict__ cursor, float4* __restrict__ sorted) {
+                            int* __restrict__ cursor, float4* __restrict__ sorted, const int* __restrict__ enable) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (enable != nullptr && *enable == 0)) return;
     int slot = atomicAdd(&cursor[cell_of[i]], 1);
     sorted[slot] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], __int_as_float((int)i));
+}
+
+// need_next = 1 when some cell of this level holds more than 4k particles (a finer level pays off; below that the
+// brute-force scan of the 27 cells is cheaper than building another grid)
+__global__ void knn_crowded(const int* __restrict__ cell_of, const int* __restrict__ count, int64_t n, int k,
+                            const int* __restrict__ enable, int* __restrict__ need_next) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n || (enable != nullptr && *enable == 0)) return;
+    if (count[cell_of[i]] > 4 * k) *need_next = 1;      // benign race: every writer stores the same value
 }
 
 // ---- warp-level top-k ------------------------------------------------------------------------
@@ -159,20 +172,42 @@ __device__ __forceinline__ void visit_cells(const float4* __restrict__ sorted, c
     }
 }
 
+constexpr int KNN_MAX_LEVELS = 5;
+constexpr int64_t KNN_MAX_CELLS = 1ll << 23;        // per refined level (32 MiB per int array)
+
+struct KnnLevels {
+    int n_levels;
+    const int* need;            // need[l] != 0: level l was built
+    int nc[KNN_MAX_LEVELS];
+    const float4* sorted[KNN_MAX_LEVELS];
+    const int* start[KNN_MAX_LEVELS];
+};
+
 __global__ void __launch_bounds__(KNN_THREADS)
-knn_query(const float4* __restrict__ sorted, const int* __restrict__ cell_start, int nc, int64_t n,
-          float box, float inv_w, int k, int64_t q0, int64_t nq, int32_t* __restrict__ nbr_ext) {
+knn_query(KnnLevels lv, int64_t n, float box, int k, int64_t q0, int64_t nq, int32_t* __restrict__ nbr_ext) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (gridDim.x * (int64_t)blockDim.x) >> 5;
-    const float w = box / (float)nc;
     const float margin = 1e-5f * box;
     for (int64_t q = warp0; q < n; q += n_warps) {
-        float4 me = sorted[q];
+        float4 me = lv.sorted[0][q];
         float qx = me.x, qy = me.y, qz = me.z;
         int qi = __float_as_int(me.w);
         if (qi < q0 || qi >= q0 + nq) continue;          // only the queries of this rank's slab (warp-uniform)
-        int cx = cell_coord(qx, inv_w, nc), cy = cell_coord(qy, inv_w, nc), cz = cell_coord(qz, inv_w, nc);
+        // coarsest level whose own cell is not crowded (warp-uniform: every lane sees the same query)
+        int L = 0, nc = lv.nc[0], cx = 0, cy = 0, cz = 0;
+        float inv_w = (float)nc / box;
+        for (;; ++L) {
+            nc = lv.nc[L];
+            inv_w = (float)nc / box;
+            cx = cell_coord(qx, inv_w, nc); cy = cell_coord(qy, inv_w, nc); cz = cell_coord(qz, inv_w, nc);
+            if (L + 1 >= lv.n_levels || lv.need[L + 1] == 0) break;
+            const int c = (cx * nc + cy) * nc + cz;
+            if (lv.start[L][c + 1] - lv.start[L][c] <= k) break;
+        }
+        const float4* __restrict__ sorted = lv.sorted[L];
+        const int* __restrict__ cell_start = lv.start[L];
+        const float w = box / (float)nc;
         unsigned long long best = KEY_INF;
         for (int R = 1;; ++R) {
             visit_cells(sorted, cell_start, nc, n, box, qx, qy, qz, cx, cy, cz, R, R == 1 ? 0 : R, k, lane, best);
@@ -199,15 +234,55 @@ knn_query(const float4* __restrict__ sorted, const int* __restrict__ cell_start,
 }
 
 struct KnnPlan {
-    int nc;
-    int64_t n_cells, n_tiles;
+    int n_levels;
+    int nc[KNN_MAX_LEVELS];
+    int64_t n_cells[KNN_MAX_LEVELS], n_tiles_max;
 };
+// level 0 is the uniform-box grid of cells_per_dim(); every further level halves the cell width while the grid
+// stays below KNN_MAX_CELLS cells
 KnnPlan plan_for(int64_t n, int k) {
     KnnPlan p;
-    p.nc = cells_per_dim(n, k);
-    p.n_cells = (int64_t)p.nc * p.nc * p.nc;
-    p.n_tiles = scan_tiles(p.n_cells + 1);
+    int nc = cells_per_dim(n, k);
+    p.n_levels = 0;
+    p.n_tiles_max = 0;
+    while (p.n_levels < KNN_MAX_LEVELS) {
+        const int64_t cells = (int64_t)nc * nc * nc;
+        if (p.n_levels > 0 && cells > KNN_MAX_CELLS) break;
+        p.nc[p.n_levels] = nc;
+        p.n_cells[p.n_levels] = cells;
+        const int64_t t = scan_tiles(cells + 1);
+        if (t > p.n_tiles_max) p.n_tiles_max = t;
+        ++p.n_levels;
+        if (nc * 2 > 2000) break;
+        nc *= 2;
+    }
     return p;
+}
+
+// workspace layout for the worst case over k (k = 1 gives the finest level-0 grid and the largest pyramid)
+struct KnnCarve {
+    int* count; int* cursor; int* tile_sum; int* cell_of; int* need;
+    int* start[KNN_MAX_LEVELS];
+    float4* sorted[KNN_MAX_LEVELS];
+    int64_t bytes;
+};
+KnnCarve carve(void* ws, int64_t n) {
+    // any k: level 0 is at most as fine as for k = 1, every refined level has at most KNN_MAX_CELLS cells
+    KnnPlan pmax = plan_for(n, 1);
+    int64_t max_cells = pmax.n_cells[0] > KNN_MAX_CELLS ? pmax.n_cells[0] : KNN_MAX_CELLS;
+    Carver c(ws);
+    KnnCarve o;
+    o.count = c.take<int>(max_cells + 1);
+    o.cursor = c.take<int>(max_cells + 1);
+    o.tile_sum = c.take<int>(scan_tiles(max_cells + 1) + 1);
+    o.cell_of = c.take<int>(n);
+    o.need = c.take<int>(KNN_MAX_LEVELS + 1);
+    for (int l = 0; l < KNN_MAX_LEVELS; ++l) {
+        o.start[l] = c.take<int>(max_cells + 1);
+        o.sorted[l] = c.take<float4>(n);
+    }
+    o.bytes = c.off;
+    return o;
 }
 
 }  // namespace
@@ -217,16 +292,7 @@ KnnPlan plan_for(int64_t n, int k) {
 using namespace cgnn;
 
 extern "C" int64_t cgnn_knn_workspace_bytes(int64_t n) {
-    // sized for the finest grid any k in [1,32] can ask for (k = 1..5 -> occupancy 2)
-    KnnPlan p = plan_for(n, 1);
-    Carver c(nullptr);
-    c.take<int>(p.n_cells + 1);     // count
-    c.take<int>(p.n_cells + 1);     // start
-    c.take<int>(p.n_cells + 1);     // cursor
-    c.take<int>(p.n_tiles + 1);     // tile sums
-    c.take<int>(n);                 // cell_of
-    c.take<float4>(n);              // sorted
-    return c.off;
+    return carve(nullptr, n).bytes;
 }
 
 extern "C" int cgnn_knn_periodic(const float* pos, int64_t n, float box, int32_t k, int32_t* nbr_ext,
@@ -250,29 +316,37 @@ extern "C" int cgnn_knn_periodic_range(const float* pos, int64_t n, float box, i
         return CGNN_ERR_WORKSPACE;
     }
     KnnPlan p = plan_for(n, k);
-    KnnPlan pmax = plan_for(n, 1);
-    Carver c(workspace);
-    int* count = c.take<int>(pmax.n_cells + 1);
-    int* start = c.take<int>(pmax.n_cells + 1);
-    int* cursor = c.take<int>(pmax.n_cells + 1);
-    int* tile_sum = c.take<int>(pmax.n_tiles + 1);
-    int* cell_of = c.take<int>(n);
-    float4* sorted = c.take<float4>(n);
-
-    float inv_w = (float)p.nc / box;
-    CGNN_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (p.n_cells + 1), stream));
+    KnnCarve c = carve(workspace, n);
+    KnnLevels lv;
+    lv.n_levels = p.n_levels;
+    lv.need = c.need;
     int blocks_n = (int)((n + 255) / 256);
-    knn_count_cells<<<blocks_n, 256, 0, stream>>>(pos, n, inv_w, p.nc, cell_of, count);
-    CGNN_LAUNCH_CHECK();
-    // count[n_cells] == 0, so start[n_cells] = N
-    int rc = exclusive_scan_i32(count, p.n_cells + 1, start, cursor, tile_sum, stream);
-    if (rc != CGNN_OK) return rc;
-    knn_scatter<<<blocks_n, 256, 0, stream>>>(pos, n, cell_of, cursor, sorted);
-    CGNN_LAUNCH_CHECK();
+    CGNN_CUDA(cudaMemsetAsync(c.need, 0, sizeof(int) * (KNN_MAX_LEVELS + 1), stream));
+    for (int l = 0; l < p.n_levels; ++l) {
+        // a refined level is only built when the level above it has a crowded cell (device-side flag, no host sync)
+        const int* enable = l == 0 ? nullptr : c.need + l;
+        const float inv_w = (float)p.nc[l] / box;
+        CGNN_CUDA(cudaMemsetAsync(c.count, 0, sizeof(int) * (p.n_cells[l] + 1), stream));
+        knn_count_cells<<<blocks_n, 256, 0, stream>>>(pos, n, inv_w, p.nc[l], c.cell_of, c.count, enable);
+        CGNN_LAUNCH_CHECK();
+        if (l + 1 < p.n_levels) {
+            knn_crowded<<<blocks_n, 256, 0, stream>>>(c.cell_of, c.count, n, k, enable, c.need + l + 1);
+            CGNN_LAUNCH_CHECK();
+        }
+        // count[n_cells] == 0, so start[n_cells] = N
+        int rc = exclusive_scan_i32(c.count, p.n_cells[l] + 1, c.start[l], c.cursor, c.tile_sum, stream, enable);
+        if (rc != CGNN_OK) return rc;
+        knn_scatter<<<blocks_n, 256, 0, stream>>>(pos, n, c.cell_of, c.cursor, c.sorted[l], enable);
+        CGNN_LAUNCH_CHECK();
+        lv.nc[l] = p.nc[l];
+        lv.sorted[l] = c.sorted[l];
+        lv.start[l] = c.start[l];
+    }
+    for (int l = p.n_levels; l < KNN_MAX_LEVELS; ++l) { lv.nc[l] = 0; lv.sorted[l] = nullptr; lv.start[l] = nullptr; }
     int64_t want_blocks = (n * 32 + KNN_THREADS - 1) / KNN_THREADS;
     int64_t max_blocks = (int64_t)num_sms() * 8;
     int q_blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
-    knn_query<<<q_blocks, KNN_THREADS, 0, stream>>>(sorted, start, p.nc, n, box, inv_w, k, q0, nq, nbr_ext);
+    knn_query<<<q_blocks, KNN_THREADS, 0, stream>>>(lv, n, box, k, q0, nq, nbr_ext);
     CGNN_LAUNCH_CHECK();
     return CGNN_OK;
 }

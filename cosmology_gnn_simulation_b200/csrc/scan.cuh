@@ -38,9 +38,12 @@ static __device__ int block_exclusive_scan(int v, int* total, int* smem /* [32] 
     return res;
 }
 
-static __global__ void scan_tile_sums(const int* __restrict__ count, int64_t m, int* __restrict__ tile_sum) {
+// `enable` (nullable): device flag; a launch whose flag is 0 returns at once (used to skip grid levels nobody needs)
+static __global__ void scan_tile_sums(const int* __restrict__ count, int64_t m, int* __restrict__ tile_sum,
+                                      const int* __restrict__ enable) {
     __shared__ int smem[32];
     __shared__ int total;
+    if (enable != nullptr && *enable == 0) return;
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     int s = 0;
 #pragma unroll
@@ -49,10 +52,11 @@ static __global__ void scan_tile_sums(const int* __restrict__ count, int64_t m, 
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
 }
 
-static __global__ void scan_tile_offsets(int* __restrict__ tile_sum, int n_tiles) {
+static __global__ void scan_tile_offsets(int* __restrict__ tile_sum, int n_tiles, const int* __restrict__ enable) {
     // single block: serial over chunks of SCAN_BLOCK tiles
     __shared__ int smem[32];
     __shared__ int total;
+    if (enable != nullptr && *enable == 0) return;
     int carry = 0;
     for (int base = 0; base < n_tiles; base += SCAN_BLOCK) {
         int i = base + threadIdx.x;
@@ -65,9 +69,10 @@ static __global__ void scan_tile_offsets(int* __restrict__ tile_sum, int n_tiles
 }
 
 static __global__ void scan_apply(const int* __restrict__ count, int64_t m, const int* __restrict__ tile_off,
-                           int* __restrict__ start, int* __restrict__ cursor) {
+                           int* __restrict__ start, int* __restrict__ cursor, const int* __restrict__ enable) {
     __shared__ int smem[32];
     __shared__ int total;
+    if (enable != nullptr && *enable == 0) return;
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
     int s = 0;
@@ -87,13 +92,13 @@ static inline int64_t scan_tiles(int64_t m) { return (m + SCAN_TILE - 1) / SCAN_
 // start[i] = cursor[i] = sum(count[0..i)) for i in [0, m).  tile_sum: scratch of scan_tiles(m) ints.
 // `cursor` may be NULL.
 static inline int exclusive_scan_i32(const int* count, int64_t m, int* start, int* cursor, int* tile_sum,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, const int* enable = nullptr) {
     int n_tiles = (int)scan_tiles(m);
-    scan_tile_sums<<<n_tiles, SCAN_BLOCK, 0, stream>>>(count, m, tile_sum);
+    scan_tile_sums<<<n_tiles, SCAN_BLOCK, 0, stream>>>(count, m, tile_sum, enable);
     CGNN_LAUNCH_CHECK();
-    scan_tile_offsets<<<1, SCAN_BLOCK, 0, stream>>>(tile_sum, n_tiles);
+    scan_tile_offsets<<<1, SCAN_BLOCK, 0, stream>>>(tile_sum, n_tiles, enable);
     CGNN_LAUNCH_CHECK();
-    scan_apply<<<n_tiles, SCAN_BLOCK, 0, stream>>>(count, m, tile_sum, start, cursor);
+    scan_apply<<<n_tiles, SCAN_BLOCK, 0, stream>>>(count, m, tile_sum, start, cursor, enable);
     CGNN_LAUNCH_CHECK();
     return CGNN_OK;
 }
