@@ -258,36 +258,53 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident throughput (`value`) -------------------------------------------------
-    for _ in range(args.warmup):
-        train_step(graph)
-    barrier()
-    ops.EDGE_FWD_EVENTS = []
-    launches0 = _lib.launch_count()
-    step_ms = []
-    with ClockSampler(local) as clocks:
-        for _ in range(args.steps):
-            if flush is not None:
-                flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            train_step(graph)
-            e.record()
-            step_ms.append((s, e))
+    # One GPU: the ~2000 launches of a step are captured once into a CUDA graph and replayed (graphed.py); the
+    # capture has to come before any eager step on the default stream.  N > 1 (NCCL point-to-point inside the
+    # step) stays eager.
+    graphed = None
+    launches_per_graphed_step = 0
+    if world == 1 and not args.no_cuda_graph:
+        from cosmology_gnn_simulation_b200.graphed import GraphedTrainStep
+        graphed = GraphedTrainStep(model, lambda pred, g: combined_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM))
+        l0 = _lib.launch_count()
+        graphed.capture(graph)
+        launches_per_graphed_step = graphed.launches_per_step
+        del l0
+    run_step = graphed if graphed is not None else train_step
+
+    def timed_loop(step_fn, collect_edge_events):
+        for _ in range(args.warmup):
+            step_fn(graph)
         barrier()
-    launches = _lib.launch_count() - launches0
-    events, ops.EDGE_FWD_EVENTS = ops.EDGE_FWD_EVENTS, None
-    total_ms = sum(s.elapsed_time(e) for s, e in step_ms)
-    total_ms = cd.max_over_ranks(total_ms, dev)
+        ops.EDGE_FWD_EVENTS = [] if collect_edge_events else None
+        l0 = _lib.launch_count()
+        marks = []
+        with ClockSampler(local) as clk:
+            for _ in range(args.steps):
+                if flush is not None:
+                    flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                step_fn(graph)
+                e.record()
+                marks.append((s, e))
+            barrier()
+        ev, ops.EDGE_FWD_EVENTS = ops.EDGE_FWD_EVENTS, None
+        ms = cd.max_over_ranks(sum(s.elapsed_time(e) for s, e in marks), dev)
+        return ms, _lib.launch_count() - l0, ev, clk
+
+    # ---- device-resident throughput (`value`) -------------------------------------------------
+    total_ms, launches, events, clocks = timed_loop(run_step, graphed is None)
+    if graphed is not None:
+        launches = launches_per_graphed_step * args.steps
     value = world * n * args.steps / (total_ms * 1e-3)
-    edge_ms = sum(a.elapsed_time(b) for a, b in events) / max(len(events), 1)
 
     # ---- end to end through the public API with host buffers (`e2e`) ---------------------------
     def e2e_step():
         c = coords_host.to(dev, non_blocking=True)
         u = energy_host.to(dev, non_blocking=True)
         g = build_graph(c, u)
-        ls = train_step(g)
+        ls = run_step(g)
         return torch.stack([ls["loss"].detach(), ls["acc_loss"], ls["temp_rate_loss"], ls["momentum_loss"]]).cpu()
 
     for _ in range(min(args.warmup, 3)):
@@ -299,6 +316,13 @@ def run_gpu(args):
     barrier()
     e2e_s = cd.max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = world * n * args.steps / e2e_s
+
+    # ---- the dominant kernel, bracketed by CUDA events: an eager replica of the timed region (launches inside a
+    # replayed CUDA graph cannot be bracketed one by one) -----------------------------------------
+    eager_ms = None
+    if graphed is not None:
+        eager_ms, _, events, _ = timed_loop(train_step, True)
+    edge_ms = sum(a.elapsed_time(b) for a, b in events) / max(len(events), 1)
 
     # ---- graph build alone (reported apart; not part of the model application) -----
     pos_dev = graph.pos.contiguous()
@@ -344,7 +368,10 @@ def run_gpu(args):
                      if precision != "fp32" else fl,
                      "flop_per_launch": fl, "ms_per_launch": edge_ms, "launches_timed": len(events),
                      "peak_source": peaks["source"] + " (bf16 dense, sustained)",
-                     "share_of_step": edge_ms * M / (total_ms / args.steps)},
+                     "share_of_step": edge_ms * M / ((eager_ms if eager_ms is not None else total_ms) / args.steps),
+                     "timed": "eager replica of the timed region, same process" if eager_ms is not None else "the timed region"},
+        "cuda_graph": graphed is not None,
+        "eager_ms_per_step": None if eager_ms is None else eager_ms / args.steps,
         "model_tflops": flops_application(n, k, L, M, message) / (total_ms / args.steps * 1e-3) / 1e12,
         "graph_build": {"ms": knn_ms, "particles_per_s": n / (knn_ms * 1e-3),
                         "what": "cgnn_knn_periodic + cgnn_edge_features, device resident"},
@@ -411,6 +438,7 @@ def main():
                     help="N > 1: slab = one box of N x particles cut into x-slabs with halo exchange (default); "
                          "replica = one independent box per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="one GPU: issue every launch eagerly instead of replaying a captured step")
     ap.add_argument("--rollout", action="store_true", help="time an inference rollout of the workload instead of a training step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cgnn" else args.warmup
