@@ -33,6 +33,7 @@ SIGNATURES = {
     "cgnn_last_error": (c_char_p, []),
     "cgnn_version": (c_char_p, []),
     "cgnn_launch_count": (c_int64, []),
+    "cgnn_debug_stamps": (None, [c_void_p, c_int32, c_int32]),
     "cgnn_knn_workspace_bytes": (c_int64, [c_int64]),
     "cgnn_knn_periodic": (c_int, [c_void_p, c_int64, c_float, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "cgnn_knn_periodic_range": (c_int, [c_void_p, c_int64, c_float, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_int64,

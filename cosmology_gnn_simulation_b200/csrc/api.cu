@@ -39,6 +39,8 @@ int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp);
 int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int64_t n_nodes, int k, int precision);
 int64_t tc_rows_workspace(const cgnn_mlp* mlp, int64_t rows, int precision, int backward);
 
+void set_debug_stamps(unsigned long long* buf, int tiles, int launches);
+
 static bool is_tc(int precision) { return precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16; }
 
 static int run_fwd(MlpTask& a, int precision, cudaStream_t s, void* ws = nullptr, int64_t wsb = 0) {
@@ -70,6 +72,9 @@ using namespace cgnn;
 extern "C" const char* cgnn_last_error(void) { return g_error; }
 extern "C" const char* cgnn_version(void) { return "cgnn 0.1 (sm_100a)"; }
 extern "C" int64_t cgnn_launch_count(void) { return g_launches.load(); }
+extern "C" void cgnn_debug_stamps(unsigned long long* stamps, int32_t tiles, int32_t launches) {
+    set_debug_stamps(stamps, stamps ? tiles : 0, stamps ? launches : 0);
+}
 
 extern "C" int64_t cgnn_mlp_rows_workspace_bytes(const cgnn_mlp* mlp, int64_t rows, int32_t precision, int32_t backward) {
     if (mlp_validate(mlp, "cgnn_mlp_rows_workspace_bytes")) return -1;

@@ -1,4 +1,4 @@
-// Tensor-core (tcgen05) implementation of the fused processor MLP tiles, forward.
+// Tensor-core (tcgen05) implementation of the fused MLP tiles (forward chains and the chains of the backward).
 //
 // One kernel, `tc_chain_fwd<NS>`, runs a chain of Linear layers over 256-row tiles on a CTA PAIR
 // (cta_group::2, UMMA 256x128x16, BF16 operands, FP32 accumulators in TMEM):
@@ -13,14 +13,20 @@
 //     is hi*hi + lo*hi + hi*lo (three MMAs, ~2^-17 relative error, FP32-like results);
 //     NS = 1 ("bf16"): single pass;
 //   * two tiles are in flight per CTA (TMEM columns [0,256) and [256,512)): while the tensor core works
-//     on one, the four epilogue warps of the other do bias/ReLU/split or the LayerNorm epilogue;
+//     on one, the four epilogue warps of the other do bias/ReLU/split or the final epilogue;
 //   * the edge phase uses W1 = [W1s | W1r | W1e] (graph_network.py:89 concat order): P_s = h W1s^T and
 //     P_r = h W1r^T + b1 are computed once per NODE by this same kernel (a 1-layer chain) and the
 //     per-edge layer 1 is e W1e^T + P_s[sender] + P_r[receiver]  (5 L^2 -> 3 L^2 MACs per edge);
-//   * inputs stream in through TMA (2-D tensor maps, 16-column boxes, 64-byte swizzle), the sender rows
-//     of P_s through per-row bulk copies, outputs leave through TMA stores.
+//   * the chain input streams in through TMA (2-D tensor maps, 128 rows x 32 columns, 128-byte swizzle);
+//     EVERY OTHER row stream -- gathered P_s / P_r rows, ReLU-mask sources, residuals, upstream gradients,
+//     and all outputs -- is read / written by the epilogue threads themselves in the "thread = row" mapping
+//     with 256-bit global loads / stores (each lane touches one full 32-byte sector of its own 512-byte
+//     row; measured 5.9 TB/s with 8 warps per SM, tools/micro/rowstream.cu), loads prefetched one 16-column
+//     chunk ahead.  There is no shared-memory staging, no named barrier and no TMA store in the epilogue;
+//   * per-receiver sums (k consecutive rows = k consecutive lanes) are a butterfly of warp shuffles that halves
+//     the number of live values at each step (15 shuffles per 16 columns at k = 16), fixed order, deterministic.
 //
-// Reference semantics: InteractionNetwork.forward + residuals, graph_network.py:83-101,177-183.
+// Reference semantics: InteractionNetwork.forward + residuals, graph_network.py:83-101,177-183, and its autograd.
 #include "tc_common.cuh"
 
 namespace cgnn {
@@ -28,10 +34,13 @@ namespace {
 
 using namespace ptx;
 
-constexpr int TC_THREADS = 320;           // 8 epilogue warps (2 groups of 4) + producer warp + MMA warp
-constexpr int MAXRING = 16;               // input ring depth is chosen per launch from the shared memory left (3 .. 16)
+constexpr int TC_THREADS = 384;           // 8 epilogue warps (2 groups of 4) + a control warpgroup: producer warp, MMA warp, 2 idle
+constexpr int EPI_REGS = 232, CTL_REGS = 40;   // setmaxnreg: the control warpgroup hands its registers to the epilogue warps
+constexpr int CW = 32;                    // columns per streamed input chunk (128-byte rows, SWIZZLE_128B)
+constexpr int NCW = TC_H / CW;            // 4 chunks per 128-column tile
+constexpr int CW_BYTES = 128 * CW * 4;    // 16384
+constexpr int MAXRING = 12;               // input ring depth is chosen per launch from the shared memory left (2 .. 12)
 constexpr int WIMG = 64 * TC_H * 2;       // bytes of one weight image half (64 output rows x 128 k, bf16)
-constexpr int PS_STRIDE = TC_H * 4 + 16;  // padded row stride of the gathered P_s rows (conflict-free row reads)
 constexpr int MAX_BLOCKS = 4;             // weight blocks (MMA phases) per tile
 constexpr float LN_EPS = 1e-5f;
 
@@ -40,33 +49,48 @@ struct TcParams {
     int64_t n_pair_tiles;       // ceil(n_rows / 256)
     int n_in;                   // input phases (1: in0; 2: in0 then in1)
     int n_layers;               // Linear layers (1 or 3)
-    int k;                      // > 0: rows per receiver (gather / segmented sum)
-    int has_ln;
+    int k;                      // rows per receiver (gather / per-receiver sums), a power of two <= 32; 1 when unused
+    int kshift;                 // log2(k)
+    int ln_mode;                // 0: none, 1: LayerNorm forward, 2: LayerNorm backward (the result is dY)
     int gather;                 // layer-1 pre-activation += Ps[sender] + Pr[receiver]
     int relu_out;               // ReLU on the result (before mask / residual)
     const float* mask_src;      // [n_rows][128]: result = mask_src > 0 ? result : 0 (nullable)
     const float* residual;      // [n_rows][128] added to the result (nullable)
-    float* agg_out;             // edge mode: [n_rows / k][128] per-receiver sum of the result before the residual (nullable)
-    const int32_t* senders;     // edge mode
-    const float* Ps;            // edge mode: [N][128]
-    const float* Pr;            // edge mode: [N][128] (includes the layer-1 bias)
-    int n_ring;                 // input ring depth (3 .. MAXRING)
-    int n_ps;                   // gather staging buffers: 2 (one per group) when shared memory allows, else 1
+    float* agg_out;             // [n_rows / k][128] per-receiver sum of the result before the residual (nullable)
+    const int32_t* senders;     // gather
+    const float* Ps;            // gather: [N][128]
+    const float* Pr;            // gather: [N][128] (includes the layer-1 bias)
+    // hidden layers of a 3-layer chain (index = hidden layer 0, 1)
+    const float* hid_mask[2];   // activation = hid_mask > 0 ? v : 0 instead of ReLU (nullable)
+    float* hid_out[2];          // [n_rows][128]: the activation is also written here (nullable)
+    float* hid_agg[2];          // [n_rows / k][128]: per-receiver sum of the activation (nullable)
+    // LayerNorm backward (ln_mode 2): dU = du_rows[row] + du_recv[row / k] (each nullable)
+    const float* du_rows;
+    const float* du_recv;
+    float* ln_partials;         // [gridDim.x * 8][2][128]: per-warp column sums of dU * xhat and dU
+    float* out;                 // [n_rows][128]
+    int n_ring;                 // input ring depth
     const uint8_t* w_images;    // [n_blocks][NSI][2 halves][WIMG]
     const float* vec;           // [5][128]: bias of layer 1, 2, 3, gamma, beta
+    unsigned long long* stamps; // debug (cgnn_debug_stamps): clock64 of CTA 0's groups, [2][stamp_tiles][16] (nullable)
+    int stamp_tiles;
 };
+
+// debug hook: when set, the next chain launches record the stage time stamps of block 0
+unsigned long long* g_stamps = nullptr;
+int g_stamp_tiles = 0, g_stamp_launches = 0, g_stamp_next = 0;
 
 // shared-memory layout (dynamic, 1024-byte aligned base)
 struct Smem {
-    static constexpr int sbuf = 0;                                 // 2 groups * 2 * CH_BYTES (output staging)
-    static constexpr int vec = sbuf + 4 * CH_BYTES;                // 5 * 128 floats
-    static constexpr int bars = vec + 5 * TC_H * 4;                // barriers (512 bytes)
+    static constexpr int vec = 0;                                  // 5 * 128 floats
+    static constexpr int lnacc = vec + 5 * TC_H * 4;               // 8 warps * 2 * 128 floats (LayerNorm backward column sums)
+    static constexpr int bars = lnacc + 8 * 2 * TC_H * 4;          // barriers (512 bytes)
     static constexpr int weights = bars + 512;                     // n_blocks * NSI * WIMG
-    // then: n_ps * 128 * PS_STRIDE gather staging, then (1024-aligned) n_ring * CH_BYTES input ring
+    // then (1024-aligned) n_ring * CW_BYTES input ring
 };
-static_assert(Smem::weights % 128 == 0 && Smem::sbuf % 1024 == 0, "chunk buffers need 1024-byte, weight images 128-byte alignment");
-__host__ __device__ constexpr uint32_t ring_offset(int n_blocks, int nsi, int n_ps) {
-    return (uint32_t)((Smem::weights + n_blocks * nsi * WIMG + n_ps * 128 * PS_STRIDE + 1023) / 1024 * 1024);
+static_assert(Smem::weights % 128 == 0, "weight images need 128-byte alignment");
+__host__ __device__ constexpr uint32_t ring_offset(int n_blocks, int nsi) {
+    return (uint32_t)((Smem::weights + n_blocks * nsi * WIMG + 1023) / 1024 * 1024);
 }
 
 struct Bars {
@@ -74,31 +98,105 @@ struct Bars {
     // "full" barriers are per consumer group: a group only ever waits on barriers whose uses are all its own,
     // so the phase parity it tracks can never alias a phase that belongs to the other group's tiles
     uint64_t in_full[2][MAXRING], in_empty[MAXRING];
-    uint64_t ps_full[2], ps_empty[2];
     uint64_t a_ready[2];        // used in the leader CTA: 8 arrivals (4 warps x 2 CTAs)
     uint64_t mma_done[2];       // per CTA, one tcgen05.commit arrival
     uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 512, "barrier block");
 
-template <int NS>
+// byte offset of the 16-byte piece j (0..7) of row r inside a 128-byte-swizzled chunk buffer
+__device__ __forceinline__ uint32_t swz128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+// 256-bit global accesses: one full 32-byte sector per lane
+__device__ __forceinline__ void ld256(const float* p, float* v) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void st256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld16(const float* p, float* v) { ld256(p, v); ld256(p + 8, v + 8); }
+__device__ __forceinline__ void st16(float* p, const float* v) { st256(p, v); st256(p + 8, v + 8); }
+
+// tcgen05.wait::ld that also carries a data dependency on the 16 registers of the load it completes, so the
+// compiler cannot move their uses above the wait when loads are software-pipelined
+__device__ __forceinline__ void tmem_ld_wait16(float* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                   "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :: "memory");
+}
+
+// Sums 16 columns over the k lanes (rows) of a receiver, k a power of two <= 32 (m = k/2, k/4, ... 1 lane distance):
+// every step exchanges half of the live values with the partner lane, so 16 -> 8 -> 4 -> 2 -> 1 values stay live.
+// On return v[0 .. nv) hold complete sums, nv = max(16 / k, 1): columns (lane & (k-1)) * nv + j for k <= 16, column
+// (lane & 31) >> 1 for k = 32 (both lanes of a pair hold it).  Fixed tree order: deterministic.
+__device__ __forceinline__ void receiver_sum16(float* v, int k, int lane) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int m = k >> (s + 1);
+        if (m >= 1) {
+            const bool upper = (lane & m) != 0;
+            if (s < 4) {
+                const int half = 8 >> s;
+#pragma unroll
+                for (int j = 0; j < half; ++j) {
+                    const float send = upper ? v[j] : v[j + half];
+                    const float keep = upper ? v[j + half] : v[j];
+                    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                }
+            } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+            }
+        }
+    }
+}
+// stores the sums receiver_sum16 left in v for columns [c, c + 16) of receiver row `dst`
+__device__ __forceinline__ void receiver_store16(float* dst, int c, const float* v, int k, int lane) {
+    if (k == 32) {
+        if ((lane & 1) == 0) dst[c + (lane >> 1)] = v[0];
+    } else if (k == 16) {
+        dst[c + (lane & 15)] = v[0];
+    } else if (k == 8) {
+        *reinterpret_cast<float2*>(dst + c + (lane & 7) * 2) = make_float2(v[0], v[1]);
+    } else if (k == 4) {
+        *reinterpret_cast<float4*>(dst + c + (lane & 3) * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (k == 2) {
+        float* d = dst + c + (lane & 1) * 8;
+        *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+}
+
+// CFG: compile-time shape of the chain, so that every instantiation carries only the code and the registers (row-stream
+// buffers) it uses: C_L3 three layers (else one), C_LN / C_LNB LayerNorm forward / backward after the last layer,
+// C_SA / C_SB the final epilogue reads row stream a (P_s | dU rows | mask source) / b (P_r | dU per receiver |
+// residual), C_HS the hidden epilogues read row streams (gather or mask sources), C_AGG per-receiver sums.
+constexpr int C_L3 = 1, C_LN = 2, C_LNB = 4, C_SA = 8, C_SB = 16, C_HS = 32, C_AGG = 64;
+template <int NS, int CFG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
-             const __grid_constant__ CUtensorMap tm_out, const TcParams p) {
+tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1, const TcParams p) {
     constexpr int NSI = NS == 3 ? 2 : 1;                    // weight / activation images per value (hi [, lo])
+    constexpr bool L3 = (CFG & C_L3) != 0, SA = (CFG & C_SA) != 0, SB = (CFG & C_SB) != 0, HS = (CFG & C_HS) != 0, AGG = (CFG & C_AGG) != 0;
+    constexpr int LN = (CFG & C_LNB) ? 2 : ((CFG & C_LN) ? 1 : 0);
+    constexpr bool LNB = LN == 2;
+    constexpr int N_LAYERS = L3 ? 3 : 1;
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars* bars = reinterpret_cast<Bars*>(smem + Smem::bars);
     float* sVec = reinterpret_cast<float*>(smem + Smem::vec);
-    const int n_blocks = p.n_in + p.n_layers - 1;           // MMA phases per tile
+    const int n_blocks = p.n_in + N_LAYERS - 1;             // MMA phases per tile
     uint8_t* sW = smem + Smem::weights;
-    uint8_t* sPs0 = sW + n_blocks * NSI * WIMG;             // gather only: n_ps * 128 * PS_STRIDE
-    uint8_t* sRing = smem + ring_offset(n_blocks, NSI, p.gather ? p.n_ps : 0);
+    uint8_t* sRing = smem + ring_offset(n_blocks, NSI);
     const int NRING = p.n_ring;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int64_t n_it = p.n_pair_tiles > cluster_id ? (p.n_pair_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
-    const bool gather_on = p.gather != 0;
 
     // ---- one-time setup ---------------------------------------------------------------------------
     if (tid == 0) {
@@ -108,19 +206,16 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             mbar_init(&bars->in_full[1][i], 1);
             mbar_init(&bars->in_empty[i], 4);
         }
-        mbar_init(&bars->ps_full[0], 1);
-        mbar_init(&bars->ps_full[1], 1);
-        mbar_init(&bars->ps_empty[0], 4);
-        mbar_init(&bars->ps_empty[1], 4);
         for (int s = 0; s < 2; ++s) { mbar_init(&bars->a_ready[s], 8); mbar_init(&bars->mma_done[s], 1); }
         fence_mbar_init();
     }
     for (int i = tid; i < 5 * TC_H; i += TC_THREADS) sVec[i] = p.vec[i];
+    if (LNB)
+        for (int i = tid; i < 8 * 2 * TC_H; i += TC_THREADS) reinterpret_cast<float*>(smem + Smem::lnacc)[i] = 0.0f;
     if (warp == 9) tmem_alloc<2>(&bars->tmem_base, 512);
     if (warp == 8 && lane == 0) {
         prefetch_tmap(&tm_in0);
         prefetch_tmap(&tm_in1);
-        prefetch_tmap(&tm_out);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -128,46 +223,26 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     tc_fence_after_sync();
     const uint32_t tmem = bars->tmem_base;
 
+    if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTL_REGS));
     if (warp == 8) {
-        // ============================ producer: weights, input chunks, sender gathers ============================
+        // ============================ producer: weights, input chunks ============================================
         if (lane == 0) {
             mbar_expect_tx(&bars->w_full, (uint32_t)(n_blocks * NSI * WIMG));
             for (int b = 0; b < n_blocks; ++b)
                 for (int sp = 0; sp < NSI; ++sp)
                     bulk_g2s(sW + (b * NSI + sp) * WIMG, p.w_images + ((size_t)(b * NSI + sp) * 2 + rank) * WIMG, WIMG, &bars->w_full);
-        }
-        uint32_t seq = 0;
-        for (int64_t it = 0; it < n_it; ++it) {
-            const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
-            if (lane == 0) {
+            uint32_t seq = 0;
+            for (int64_t it = 0; it < n_it; ++it) {
+                const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
                 for (int ip = 0; ip < p.n_in; ++ip)
-                    for (int q = 0; q < NCH; ++q, ++seq) {
+                    for (int q = 0; q < NCW; ++q, ++seq) {
                         const uint32_t buf = seq % NRING, use = seq / NRING;
                         mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 100 + buf);
                         uint64_t* full = &bars->in_full[it & 1][buf];
-                        mbar_expect_tx(full, CH_BYTES);
-                        tma_load_2d(sRing + buf * CH_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CH, (int)row0, full);
+                        mbar_expect_tx(full, CW_BYTES);
+                        tma_load_2d(sRing + buf * CW_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CW, (int)row0, full);
                     }
-            }
-            if (gather_on) {
-                int64_t valid = p.n_rows - row0;
-                valid = valid < 0 ? 0 : (valid > 128 ? 128 : valid);
-                int32_t snd[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) snd[j] = lane + 32 * j < (int)valid ? p.senders[row0 + lane + 32 * j] : 0;
-                const int pb = (int)(it & (p.n_ps - 1));                    // staging buffer
-                const int64_t use = p.n_ps == 2 ? (it >> 1) : it;           // how often it has been used before
-                if (lane == 0) {
-                    mbar_wait_or_trap(&bars->ps_empty[pb], (uint32_t)((use & 1) ^ 1), 110);
-                    mbar_expect_tx(&bars->ps_full[it & 1], (uint32_t)(valid * TC_H * 4));
-                }
-                __syncwarp();
-                uint8_t* dstPs = sPs0 + pb * (128 * PS_STRIDE);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = lane + 32 * j;
-                    if (r < (int)valid) bulk_g2s(dstPs + r * PS_STRIDE, p.Ps + (size_t)snd[j] * TC_H, TC_H * 4, &bars->ps_full[it & 1]);
-                }
             }
         }
     } else if (warp == 9) {
@@ -195,18 +270,20 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     const uint32_t a_hi = d + 128, a_lo = d + 192;
                     const uint32_t w_hi = w_base + (ph * NSI) * WIMG, w_lo = w_hi + WIMG;
                     uint32_t acc = (ph > 0 && ph < p.n_in) ? 1u : 0u;       // later input phases accumulate into layer 1
-#pragma unroll
+                    // rolled loops: the descriptors advance by one K step (256 bytes of image, 8 TMEM columns) per MMA
+                    const uint64_t dw_hi = umma_desc(w_hi, 128, TC_H * 16), dw_lo = umma_desc(w_lo, 128, TC_H * 16);
+#pragma unroll 1
                     for (int ks = 0; ks < TC_H / 16; ++ks) {
-                        umma_bf16_ts<2>(d, a_hi + ks * 8, umma_desc(w_hi + ks * 256, 128, TC_H * 16), idesc, acc);
+                        umma_bf16_ts<2>(d, a_hi + ks * 8, dw_hi + (uint64_t)(ks * 16), idesc, acc);
                         acc = 1u;
                     }
                     if (NS == 3) {
-#pragma unroll
+#pragma unroll 1
                         for (int ks = 0; ks < TC_H / 16; ++ks)
-                            umma_bf16_ts<2>(d, a_lo + ks * 8, umma_desc(w_hi + ks * 256, 128, TC_H * 16), idesc, 1u);
-#pragma unroll
+                            umma_bf16_ts<2>(d, a_lo + ks * 8, dw_hi + (uint64_t)(ks * 16), idesc, 1u);
+#pragma unroll 1
                         for (int ks = 0; ks < TC_H / 16; ++ks)
-                            umma_bf16_ts<2>(d, a_hi + ks * 8, umma_desc(w_lo + ks * 256, 128, TC_H * 16), idesc, 1u);
+                            umma_bf16_ts<2>(d, a_hi + ks * 8, dw_lo + (uint64_t)(ks * 16), idesc, 1u);
                     }
                     umma_commit<2>(&bars->mma_done[s]);
                     par[s] ^= 1u;
@@ -218,25 +295,45 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 }
             }
         }
+    }
     } else {
         // ============================ epilogue groups: thread = row ==============================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
         const int g = warp >> 2;                        // group = TMEM slot
         const int wq = warp & 3;                        // lane quarter this warp may touch
         const int r = wq * 32 + lane;                   // row inside the CTA's 128-row tile
         const int gt = tid - g * 128;                   // thread index inside the group
         const uint32_t tslot = tmem + ((uint32_t)(wq * 32) << 16) + g * 256;
         const uint32_t tD = tslot, tAhi = tslot + 128, tAlo = tslot + 192;
-        uint8_t* sS = smem + Smem::sbuf + g * 2 * CH_BYTES;
+        float* lnacc = reinterpret_cast<float*>(smem + Smem::lnacc) + warp * 2 * TC_H;
         uint32_t pm = 0;                                // parity of mma_done[g]
         uint32_t in_par = 0;                            // bit b: parity of this group's next use of in_full[g][b]
-        const int bar_id = 1 + g;
+        const int k = p.k;
         mbar_wait_or_trap(&bars->w_full, 0, 130);       // a_ready from this CTA also tells the leader its weights landed
+        const bool stamping = p.stamps != nullptr && blockIdx.x == 0 && gt == 0;
+#define CGNN_STAMP(slot)                                                                               \
+    do {                                                                                               \
+        if (stamping && (it >> 1) < p.stamp_tiles) p.stamps[((size_t)g * p.stamp_tiles + (it >> 1)) * 16 + (slot)] = clock64(); \
+    } while (0)
 
         for (int64_t it = g; it < n_it; it += 2) {
             const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
-            uint32_t seq = (uint32_t)it * (uint32_t)(NCH * p.n_in);
-            const int pb = (int)(it & (p.n_ps - 1));
-            const uint8_t* sPs = sPs0 + pb * (128 * PS_STRIDE);
+            uint32_t seq = (uint32_t)it * (uint32_t)(NCW * p.n_in);
+            const bool valid = row0 + r < p.n_rows;
+            const int64_t grow = valid ? row0 + r : p.n_rows - 1;           // clamped: loads of padded rows stay in bounds
+            const int64_t recv = grow >> p.kshift;
+            const size_t rowoff = (size_t)grow * TC_H, recvoff = (size_t)recv * TC_H;
+            CGNN_STAMP(0);
+            // the per-row HBM streams of this tile's epilogues start their way into L2 now
+            {
+                const float* streams[5] = {p.hid_mask[0], p.hid_mask[1], LNB ? p.du_rows : p.mask_src, LNB ? nullptr : p.residual, nullptr};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (streams[i] != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(streams[i] + rowoff + 32 * j));
+                    }
+            }
             // ---- input phases: stream chunks, split, write the A operand -------------------------------------
             for (int ip = 0; ip < p.n_in; ++ip) {
                 if (ip > 0) {                            // A is still being read by the previous phase's MMA
@@ -244,255 +341,270 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     pm ^= 1u;
                     tc_fence_after_sync();
                 }
-                for (int q = 0; q < NCH; ++q, ++seq) {
+                for (int q = 0; q < NCW; ++q, ++seq) {
                     const uint32_t buf = seq % NRING;
                     mbar_wait_or_trap(&bars->in_full[g][buf], (in_par >> buf) & 1u, 150 + buf);
                     in_par ^= 1u << buf;
-                    const uint8_t* src = sRing + buf * CH_BYTES;
-                    uint32_t hi[8], lo[8];
+                    const uint8_t* src = sRing + buf * CW_BYTES;
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 v = *reinterpret_cast<const float4*>(src + swz64(r, j));
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 v = *reinterpret_cast<const float4*>(src + swz128(r, j));
                         split2(v.x, v.y, hi[2 * j], lo[2 * j]);
                         split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
-                    tmem_st_32x32b_x8(tAhi + q * 8, hi);
-                    if (NS == 3) tmem_st_32x32b_x8(tAlo + q * 8, lo);
+                    tmem_st_32x32b_x16(tAhi + q * 16, hi);
+                    if (NS == 3) tmem_st_32x32b_x16(tAlo + q * 16, lo);
                 }
+                CGNN_STAMP(1);
                 tmem_st_wait();
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&bars->a_ready[g], 0);
+                if (lane == 0) mbar_arrive_cluster_relaxed(&bars->a_ready[g], 0);
+                CGNN_STAMP(2);
             }
             // ---- hidden layers ------------------------------------------------------------------------------------
-            for (int l = 0; l + 1 < p.n_layers; ++l) {
+            for (int l = 0; l + 1 < N_LAYERS; ++l) {
+                const bool gather = p.gather && l == 0;
+                // row streams of this layer, thread = row: a = P_s[sender] | mask source, b = P_r[receiver]
+                const float* pa = !HS ? nullptr : gather ? p.Ps + (size_t)__ldg(p.senders + grow) * TC_H : (p.hid_mask[l] ? p.hid_mask[l] + rowoff : nullptr);
+                const float* pb = HS && gather ? p.Pr + recvoff : nullptr;
+                const bool masked = !gather && pa != nullptr;
+                float* hout = p.hid_out[l] ? p.hid_out[l] + rowoff : nullptr;
+                float* hagg = AGG && p.hid_agg[l] ? p.hid_agg[l] + recvoff : nullptr;
+                const float* bias = sVec + l * TC_H;
+                // operands of the row streams: four 16-column chunk buffers per stream, each reloaded four chunks (64 columns) ahead
+                // (stream b = the P_r row, shared by the k lanes of a receiver and L2-hot: two buffers, reloaded two chunks ahead)
+                float a0[16], a1[16], a2[16], a3[16], b0[16], b1[16];
+                if (pa) { ld16(pa, a0); ld16(pa + 16, a1); ld16(pa + 32, a2); ld16(pa + 48, a3); }
+                if (pb) { ld16(pb, b0); ld16(pb + 16, b1); }
                 mbar_wait_or_trap(&bars->mma_done[g], pm, 160 + l);
                 pm ^= 1u;
                 tc_fence_after_sync();
-                const bool gather = gather_on && l == 0;
-                if (gather) mbar_wait_or_trap(&bars->ps_full[g], (uint32_t)((it >> 1) & 1), 170);
-                const float* bias = sVec + l * TC_H;
-                int64_t grow = row0 + r;
-                const float* pr_row = nullptr;
-                if (gather) {
-                    if (grow >= p.n_rows) grow = p.n_rows - 1;       // clamp (results of padded rows are never stored)
-                    pr_row = p.Pr + (size_t)(grow / p.k) * TC_H;
-                }
+                CGNN_STAMP(3 + 4 * l);
+                float va[16], vb[16];
+                tmem_ld_32x32b_x16(tD, va);
 #pragma unroll 1
-                for (int c0 = 0; c0 < TC_H; c0 += 32) {
-                    float v[32];
-                    float4 prv[8];
-                    if (gather) {
+                for (int c = 0; c < TC_H; c += 64) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) prv[j] = __ldg(reinterpret_cast<const float4*>(pr_row + c0 + 4 * j));
-                    }
-                    tmem_ld_32x32b_x32(tD + c0, v);
-                    tmem_ld_wait();
+                    for (int hh = 0; hh < 4; ++hh) {
+                        float* v = (hh & 1) == 0 ? va : vb;
+                        float* ca = hh == 0 ? a0 : hh == 1 ? a1 : hh == 2 ? a2 : a3;
+                        float* cb = (hh & 1) == 0 ? b0 : b1;
+                        const int cc = c + 16 * hh;
+                        tmem_ld_wait16(v);
+                        if (cc + 16 < TC_H) tmem_ld_32x32b_x16(tD + cc + 16, (hh & 1) == 0 ? vb : va);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
-                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                    }
-                    if (gather) {
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(bias + cc + j);
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                        if (gather) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 a = *reinterpret_cast<const float4*>(sPs + r * PS_STRIDE + (c0 + j) * 4);
-                            const float4 b = prv[j >> 2];
-                            v[j] += a.x + b.x; v[j + 1] += a.y + b.y; v[j + 2] += a.z + b.z; v[j + 3] += a.w + b.w;
+                            for (int j = 0; j < 16; ++j) v[j] += ca[j] + cb[j];
+                        }
+                        if (masked) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = ca[j] > 0.0f ? v[j] : 0.0f;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+                        }
+                        if (pa && cc + 64 < TC_H) ld16(pa + cc + 64, ca);
+                        if (pb && cc + 32 < TC_H) ld16(pb + cc + 32, cb);
+                        if (hout && valid) st16(hout + cc, v);
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+                        tmem_st_32x32b_x8(tAhi + cc / 2, hi);
+                        if (NS == 3) tmem_st_32x32b_x8(tAlo + cc / 2, lo);
+                        if (hagg) {
+                            receiver_sum16(v, k, lane);
+                            if (valid) receiver_store16(hagg, cc, v, k, lane);
                         }
                     }
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) split2(fmaxf(v[2 * j], 0.0f), fmaxf(v[2 * j + 1], 0.0f), hi[j], lo[j]);
-                    tmem_st_32x32b_x16(tAhi + c0 / 2, hi);
-                    if (NS == 3) tmem_st_32x32b_x16(tAlo + c0 / 2, lo);
                 }
+                CGNN_STAMP(5 + 4 * l);
                 tmem_st_wait();
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) {
-                    if (gather) mbar_arrive_local(&bars->ps_empty[pb]);
-                    mbar_arrive_cluster(&bars->a_ready[g], 0);
-                }
+                if (lane == 0) mbar_arrive_cluster_relaxed(&bars->a_ready[g], 0);
+                CGNN_STAMP(6 + 4 * l);
             }
-            // ---- final layer: bias, [gather], [LayerNorm], [ReLU], [mask], segmented sum, residual, store -------
+            // ---- final layer: bias, [gather], [LayerNorm fwd / bwd], [ReLU], [mask], per-receiver sum, residual, store ----
+            const bool fgather = !L3 && SA && SB && p.gather;       // one-layer chain: the gather lands here
+            constexpr bool lnb = LNB;
+            // row streams, thread = row:  a = P_s[sender] | dU rows | mask source,  b = P_r[receiver] | dU per receiver | residual
+            const float* pa = !SA     ? nullptr
+                              : fgather ? p.Ps + (size_t)__ldg(p.senders + grow) * TC_H
+                              : lnb   ? (p.du_rows ? p.du_rows + rowoff : nullptr)
+                                      : (p.mask_src ? p.mask_src + rowoff : nullptr);
+            const float* pb = !SB     ? nullptr
+                              : fgather ? p.Pr + recvoff
+                              : lnb   ? (p.du_recv ? p.du_recv + recvoff : nullptr)
+                                      : (p.residual ? p.residual + rowoff : nullptr);
+            float* outp = p.out + rowoff;
+            float* aggp = AGG && p.agg_out ? p.agg_out + recvoff : nullptr;
+            // four 16-column chunk buffers per stream, each reloaded four chunks (64 columns) ahead
+            float a0[16], a1[16], a2[16], a3[16], b0[16], b1[16], b2[16], b3[16];
+            if (pa) { ld16(pa, a0); ld16(pa + 16, a1); ld16(pa + 32, a2); ld16(pa + 48, a3); }
+            if (pb) { ld16(pb, b0); ld16(pb + 16, b1); ld16(pb + 32, b2); ld16(pb + 48, b3); }
             mbar_wait_or_trap(&bars->mma_done[g], pm, 180);
             pm ^= 1u;
             tc_fence_after_sync();
-            const float* bias = sVec + (p.n_layers - 1) * TC_H;
-            const bool fgather = gather_on && p.n_layers == 1;      // one-layer chain: the gather lands here
-            const float* pr_row = nullptr;
-            if (fgather) {
-                mbar_wait_or_trap(&bars->ps_full[g], (uint32_t)((it >> 1) & 1), 171);
-                int64_t grow = row0 + r;
-                if (grow >= p.n_rows) grow = p.n_rows - 1;
-                pr_row = p.Pr + (size_t)(grow / p.k) * TC_H;
-            }
-            float mean = 0.0f, rstd = 1.0f;
-            if (p.has_ln) {
-                float s = 0.0f;
-#pragma unroll 1
-                for (int c0 = 0; c0 < TC_H; c0 += 32) {
-                    float v[32];
-                    tmem_ld_32x32b_x32(tD + c0, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
-                        s += (v[j] + b.x) + (v[j + 1] + b.y) + (v[j + 2] + b.z) + (v[j + 3] + b.w);
-                    }
-                }
-                mean = s * (1.0f / TC_H);
-                float q2 = 0.0f;
-#pragma unroll 1
-                for (int c0 = 0; c0 < TC_H; c0 += 32) {
-                    float v[32];
-                    tmem_ld_32x32b_x32(tD + c0, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
-                        const float d0 = v[j] + b.x - mean, d1 = v[j + 1] + b.y - mean, d2 = v[j + 2] + b.z - mean, d3 = v[j + 3] + b.w - mean;
-                        q2 = fmaf(d0, d0, q2); q2 = fmaf(d1, d1, q2); q2 = fmaf(d2, d2, q2); q2 = fmaf(d3, d3, q2);
-                    }
-                }
-                rstd = 1.0f / sqrtf(q2 * (1.0f / TC_H) + LN_EPS);
-            }
+            CGNN_STAMP(11);
+            const float* bias = sVec + (N_LAYERS - 1) * TC_H;
             const float* gamma = sVec + 3 * TC_H;
             const float* beta = sVec + 4 * TC_H;
-            const int pj = gt & 3;                           // coalesced passes: 4 threads per row (16 bytes each), 32 rows per pass
+            float mean = 0.0f, rstd = 1.0f, gm1 = 0.0f, gm2 = 0.0f;
+            if (LN != 0) {
+                // one pass over the accumulator: moments of y shifted by the row's first element y0 (robust against
+                // |mean| >> std) and, for the backward, sum g and sum g (y - y0) with g = dU * gamma
+                float y0 = 0.0f, s1 = 0.0f, s2 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+                float va[16], vb[16];
+                tmem_ld_32x32b_x16(tD, va);
 #pragma unroll 1
-            for (int q = 0; q < NCH; q += 2) {                // two 16-column chunks (both staging buffers) per iteration
-                // operands of the coalesced passes and of the gather: issued first, consumed after the TMEM read
-                float4 mk[2][4], rs[2][4], prv[8];
-                if (p.mask_src != nullptr) {
+                for (int c = 0; c < TC_H; c += 64) {
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
+                    for (int hh = 0; hh < 4; ++hh) {
+                        float* v = (hh & 1) == 0 ? va : vb;
+                        float* ca = hh == 0 ? a0 : hh == 1 ? a1 : hh == 2 ? a2 : a3;
+                        float* cb = hh == 0 ? b0 : hh == 1 ? b1 : hh == 2 ? b2 : b3;
+                        const int cc = c + 16 * hh;
+                        tmem_ld_wait16(v);
+                        if (cc + 16 < TC_H) tmem_ld_32x32b_x16(tD + cc + 16, (hh & 1) == 0 ? vb : va);
 #pragma unroll
-                        for (int pass = 0; pass < 4; ++pass) {
-                            const int64_t grow = row0 + (gt >> 2) + pass * 32;
-                            mk[c][pass] = grow < p.n_rows ? __ldg(reinterpret_cast<const float4*>(p.mask_src + grow * TC_H + (q + c) * CH + pj * 4))
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(bias + cc + j);
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                         }
-                }
-                if (p.residual != nullptr) {
+                        if (cc == 0) y0 = v[0];
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int pass = 0; pass < 4; ++pass) {
-                            const int64_t grow = row0 + (gt >> 2) + pass * 32;
-                            rs[c][pass] = grow < p.n_rows ? __ldg(reinterpret_cast<const float4*>(p.residual + grow * TC_H + (q + c) * CH + pj * 4))
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int j = 0; j < 16; ++j) {
+                            const float d = v[j] - y0;
+                            s1 += d;
+                            s2 = fmaf(d, d, s2);
                         }
-                }
-                if (fgather) {
+                        if (lnb) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) prv[j] = __ldg(reinterpret_cast<const float4*>(pr_row + q * CH + 4 * j));
-                }
-                float v[32];
-                tmem_ld_32x32b_x32(tD + q * CH, v);
-                tmem_ld_wait();
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 gmv = *reinterpret_cast<const float4*>(gamma + cc + j);
+                                const float gmj[4] = {gmv.x, gmv.y, gmv.z, gmv.w};
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(bias + q * CH + j);
-                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                }
-                if (fgather) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 a = *reinterpret_cast<const float4*>(sPs + r * PS_STRIDE + (q * CH + j) * 4);
-                        const float4 b = prv[j >> 2];
-                        v[j] += a.x + b.x; v[j + 1] += a.y + b.y; v[j + 2] += a.z + b.z; v[j + 3] += a.w + b.w;
-                    }
-                }
-                if (p.has_ln) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 gm = *reinterpret_cast<const float4*>(gamma + q * CH + j);
-                        const float4 bt = *reinterpret_cast<const float4*>(beta + q * CH + j);
-                        v[j] = (v[j] - mean) * rstd * gm.x + bt.x;
-                        v[j + 1] = (v[j + 1] - mean) * rstd * gm.y + bt.y;
-                        v[j + 2] = (v[j + 2] - mean) * rstd * gm.z + bt.z;
-                        v[j + 3] = (v[j + 3] - mean) * rstd * gm.w + bt.w;
-                    }
-                }
-                if (p.relu_out) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-                }
-                if (gt == 0) bulk_wait_read<0>();            // the stores of the previous pair have read both buffers
-                named_bar_sync(bar_id, 128);
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<float4*>(sS + c * CH_BYTES + swz64(r, j)) =
-                            make_float4(v[16 * c + 4 * j], v[16 * c + 4 * j + 1], v[16 * c + 4 * j + 2], v[16 * c + 4 * j + 3]);
-                named_bar_sync(bar_id, 128);
-                if (p.mask_src != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int pass = 0; pass < 4; ++pass) {
-                            const int rr = (gt >> 2) + pass * 32;
-                            float4* dst = reinterpret_cast<float4*>(sS + c * CH_BYTES + swz64(rr, pj));
-                            float4 u = *dst;
-                            const float4 m = mk[c][pass];
-                            u.x = m.x > 0.0f ? u.x : 0.0f; u.y = m.y > 0.0f ? u.y : 0.0f;
-                            u.z = m.z > 0.0f ? u.z : 0.0f; u.w = m.w > 0.0f ? u.w : 0.0f;
-                            *dst = u;
-                        }
-                    if (p.agg_out != nullptr) named_bar_sync(bar_id, 128);
-                }
-                if (p.agg_out != nullptr) {
-                    // per-receiver sum of the k rows, rank order (deterministic): thread <-> (receiver, column of the pair)
-                    const int c32 = gt & 31;
-                    const uint8_t* Sc = sS + (c32 >> 4) * CH_BYTES;
-                    const int c = c32 & 15;
-                    const int nrecv = 128 / p.k;
-                    for (int rv = gt >> 5; rv < nrecv; rv += 4) {
-                        const int64_t recv = row0 / p.k + rv;
-                        if (recv * p.k < p.n_rows) {
-                            float sum = 0.0f;
-                            for (int j = 0; j < p.k; ++j) {
-                                const int rr = rv * p.k + j;
-                                sum += *reinterpret_cast<const float*>(Sc + swz64(rr, c >> 2) + (c & 3) * 4);
+                                for (int u = 0; u < 4; ++u) {
+                                    const float t = ((pa ? ca[j + u] : 0.0f) + (pb ? cb[j + u] : 0.0f)) * gmj[u];
+                                    g1 += t;
+                                    g2 = fmaf(t, v[j + u] - y0, g2);
+                                }
                             }
-                            p.agg_out[recv * TC_H + q * CH + c32] = sum;
+                            // next chunks of dU; the pass ends by re-loading chunks 0 and 1 for the output pass (L2 hits)
+                            const int nc = (cc + 64) & (TC_H - 1);
+                            if (pa) ld16(pa + nc, ca);
+                            if (pb) ld16(pb + nc, cb);
                         }
                     }
-                    if (p.residual != nullptr) named_bar_sync(bar_id, 128);   // agg reads the value before the residual lands
                 }
-                if (p.residual != nullptr) {
+                const float m1 = s1 * (1.0f / TC_H);
+                mean = y0 + m1;
+                const float var = fmaxf(s2 * (1.0f / TC_H) - m1 * m1, 0.0f);
+                rstd = 1.0f / sqrtf(var + LN_EPS);
+                gm1 = g1 * (1.0f / TC_H);                                  // mean of g
+                gm2 = (g2 - m1 * g1) * rstd * (1.0f / TC_H);               // mean of g * xhat
+            }
+            CGNN_STAMP(12);
+            {
+                float va[16], vb[16];
+                tmem_ld_32x32b_x16(tD, va);
+#pragma unroll 1
+                for (int c = 0; c < TC_H; c += 64) {
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
+                    for (int hh = 0; hh < 4; ++hh) {
+                        float* v = (hh & 1) == 0 ? va : vb;
+                        const int cc = c + 16 * hh;
+                        tmem_ld_wait16(v);
+                        if (cc + 16 < TC_H) tmem_ld_32x32b_x16(tD + cc + 16, (hh & 1) == 0 ? vb : va);
+                        float* ca = hh == 0 ? a0 : hh == 1 ? a1 : hh == 2 ? a2 : a3;
+                        float* cb = hh == 0 ? b0 : hh == 1 ? b1 : hh == 2 ? b2 : b3;
 #pragma unroll
-                        for (int pass = 0; pass < 4; ++pass) {
-                            const int rr = (gt >> 2) + pass * 32;
-                            float4* dst = reinterpret_cast<float4*>(sS + c * CH_BYTES + swz64(rr, pj));
-                            float4 u = *dst;
-                            const float4 e = rs[c][pass];
-                            u.x += e.x; u.y += e.y; u.z += e.z; u.w += e.w;
-                            *dst = u;
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(bias + cc + j);
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                         }
-                }
-                fence_proxy_async_smem();
-                named_bar_sync(bar_id, 128);
-                if (gt == 0) {
-                    tma_store_2d(&tm_out, sS, q * CH, (int)row0);
-                    tma_store_2d(&tm_out, sS + CH_BYTES, (q + 1) * CH, (int)row0);
-                    bulk_commit();
+                        if (fgather) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += ca[j] + cb[j];
+                        }
+                        if (LN == 1) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 gmv = *reinterpret_cast<const float4*>(gamma + cc + j);
+                                const float4 bt = *reinterpret_cast<const float4*>(beta + cc + j);
+                                v[j] = (v[j] - mean) * rstd * gmv.x + bt.x;
+                                v[j + 1] = (v[j + 1] - mean) * rstd * gmv.y + bt.y;
+                                v[j + 2] = (v[j + 2] - mean) * rstd * gmv.z + bt.z;
+                                v[j + 3] = (v[j + 3] - mean) * rstd * gmv.w + bt.w;
+                            }
+                        } else if (lnb) {
+                            // dY = rstd (g - mean(g) - xhat mean(g xhat));  column sums of dU xhat (d gamma) and dU (d beta)
+                            float du[16], dgx[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) du[j] = valid ? (pa ? ca[j] : 0.0f) + (pb ? cb[j] : 0.0f) : 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 gmv = *reinterpret_cast<const float4*>(gamma + cc + j);
+                                const float gmj[4] = {gmv.x, gmv.y, gmv.z, gmv.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float xh = (v[j + u] - mean) * rstd;
+                                    dgx[j + u] = du[j + u] * xh;
+                                    v[j + u] = rstd * (du[j + u] * gmj[u] - gm1 - xh * gm2);
+                                }
+                            }
+                            receiver_sum16(dgx, 32, lane);
+                            receiver_sum16(du, 32, lane);
+                            if ((lane & 1) == 0) {
+                                lnacc[cc + (lane >> 1)] += dgx[0];
+                                lnacc[TC_H + cc + (lane >> 1)] += du[0];
+                            }
+                        }
+                        if (p.relu_out) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+                        }
+                        if (!fgather && !lnb && pa) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = ca[j] > 0.0f ? v[j] : 0.0f;
+                        }
+                        if (!fgather && !lnb && pb) {
+                            // residual: the sum goes out from the stream's own registers, v stays free for the per-receiver sum
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) cb[j] += v[j];
+                            if (valid) st16(outp + cc, cb);
+                        } else if (valid) {
+                            st16(outp + cc, v);
+                        }
+                        if (aggp) {
+                            receiver_sum16(v, k, lane);
+                            if (valid) receiver_store16(aggp, cc, v, k, lane);
+                        }
+                        if (cc + 64 < TC_H) {
+                            if (pa) ld16(pa + cc + 64, ca);
+                            if (pb) ld16(pb + cc + 64, cb);
+                        }
+                    }
                 }
             }
-            if (fgather) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_local(&bars->ps_empty[pb]);
-            }
+            CGNN_STAMP(13);
             // D and A of this slot are free again: the next tile of this group starts with its input phase
         }
-        if (gt == 0) bulk_wait_all<0>();
+        if (LNB) {
+            // this warp's column sums -> its row of the partials (summed in fixed order by ln_partials_reduce)
+            __syncwarp();
+            float* dst = p.ln_partials + ((size_t)blockIdx.x * 8 + warp) * 2 * TC_H;
+            for (int i = lane; i < 2 * TC_H; i += 32) dst[i] = lnacc[i];
+        }
     }
 
     // ---- teardown -----------------------------------------------------------------------------------------
@@ -543,6 +655,29 @@ __global__ void tc_prep_kernel(PrepArgs a, uint8_t* __restrict__ images, float* 
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
+bool gather_final(const ChainOp& op) { return op.Ps != nullptr && op.n_layers == 1; }
+
+// sums the per-warp LayerNorm-backward column sums [n_rows_p][2][128] in fixed order: block <-> 32 columns,
+// 8 row slices per block combined through shared memory
+__global__ void __launch_bounds__(256) ln_partials_reduce_kernel(const float* __restrict__ partials, int n_rows_p,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+    __shared__ float sm[8][32];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5;
+    float s = 0.0f;
+    for (int r = part; r < n_rows_p; r += 8) s += partials[(size_t)r * 2 * TC_H + c];
+    sm[part][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (part == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+        float* base = c < TC_H ? dgamma : dbeta;
+        if (base != nullptr) {
+            float* d = base + (c < TC_H ? c : c - TC_H);
+            *d = accumulate ? *d + t : t;
+        }
+    }
+}
 
 template <int NS>
 int run_chain_t(const ChainOp& op, cudaStream_t stream) {
@@ -552,60 +687,113 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     CGNN_CHECK_ARG(op.n_layers == 1 || op.n_layers == 3, "tensor-core chain: 1 or 3 layers");
     CGNN_CHECK_ARG(n_blocks <= MAX_BLOCKS && op.rows >= 1 && op.in0 && op.out && op.images && op.vec, "tensor-core chain: bad arguments");
     const bool gather = op.Ps != nullptr;
-    if (gather || op.agg_out) CGNN_CHECK_ARG(op.k >= 1 && 128 % op.k == 0, "tensor-core chain: k must divide 128 (got %d)", op.k);
-    PrepArgs pa{};
-    pa.n_blocks = n_blocks;
-    for (int b = 0; b < n_blocks; ++b) pa.blk[b] = op.blk[b];
-    if (op.n_layers == 1) {
-        pa.vec_src[0] = op.bias[0];
-    } else {
-        pa.vec_src[0] = op.bias[0]; pa.vec_src[1] = op.bias[1]; pa.vec_src[2] = op.bias[2];
+    const bool uses_k = gather || op.agg_out || op.du_recv || op.hid_agg[0] || op.hid_agg[1];
+    int k = 1, kshift = 0;
+    if (uses_k) {
+        CGNN_CHECK_ARG(op.k >= 1 && op.k <= 32 && (op.k & (op.k - 1)) == 0, "tensor-core chain: k must be a power of two <= 32 (got %d)", op.k);
+        k = op.k;
+        while ((1 << kshift) < k) ++kshift;
     }
-    pa.vec_src[3] = op.gamma; pa.vec_src[4] = op.beta;
-    for (int v = 0; v < 5; ++v) pa.vec_len[v] = TC_H;
-    if (op.out_valid > 0) pa.vec_len[op.n_layers - 1] = op.out_valid;       // bias of a narrow last layer
-    dim3 pg((TC_H * (TC_H / 8) + 255) / 256, n_blocks);
-    tc_prep_kernel<NS><<<pg, 256, 0, stream>>>(pa, op.images, op.vec);
-    CGNN_LAUNCH_CHECK();
+    if (op.ln_bwd) {
+        CGNN_CHECK_ARG(op.gamma && (op.du_rows || op.du_recv) && op.ln_ws && !gather_final(op) && !op.mask_src && !op.residual && !op.agg_out,
+                       "tensor-core chain: bad LayerNorm-backward arguments");
+    } else if (gather && op.n_layers == 1) {
+        CGNN_CHECK_ARG(!op.mask_src && !op.residual, "tensor-core chain: a one-layer gather chain takes no mask / residual");
+    }
+    if (!op.prepared) {
+        PrepArgs pa{};
+        pa.n_blocks = n_blocks;
+        for (int b = 0; b < n_blocks; ++b) pa.blk[b] = op.blk[b];
+        if (op.n_layers == 1) {
+            pa.vec_src[0] = op.bias[0];
+        } else {
+            pa.vec_src[0] = op.bias[0]; pa.vec_src[1] = op.bias[1]; pa.vec_src[2] = op.bias[2];
+        }
+        pa.vec_src[3] = op.gamma; pa.vec_src[4] = op.beta;
+        for (int v = 0; v < 5; ++v) pa.vec_len[v] = TC_H;
+        if (op.out_valid > 0) pa.vec_len[op.n_layers - 1] = op.out_valid;       // bias of a narrow last layer
+        dim3 pg((TC_H * (TC_H / 8) + 255) / 256, n_blocks);
+        tc_prep_kernel<NS><<<pg, 256, 0, stream>>>(pa, op.images, op.vec);
+        CGNN_LAUNCH_CHECK();
+    }
     TcParams p{};
     p.n_rows = op.rows; p.n_pair_tiles = (op.rows + 255) / 256;
-    p.n_in = n_in; p.n_layers = op.n_layers; p.k = op.k; p.has_ln = op.gamma != nullptr;
+    p.n_in = n_in; p.n_layers = op.n_layers; p.k = k; p.kshift = kshift;
+    p.ln_mode = op.ln_bwd ? 2 : (op.gamma != nullptr ? 1 : 0);
     p.gather = gather; p.relu_out = op.relu_out; p.mask_src = op.mask_src; p.residual = op.residual;
     p.agg_out = op.agg_out; p.senders = op.senders; p.Ps = op.Ps; p.Pr = op.Pr;
+    for (int l = 0; l < 2; ++l) { p.hid_mask[l] = op.hid_mask[l]; p.hid_out[l] = op.hid_out[l]; p.hid_agg[l] = op.hid_agg[l]; }
+    p.du_rows = op.du_rows; p.du_recv = op.du_recv; p.ln_partials = static_cast<float*>(op.ln_ws);
+    p.out = op.out;
     p.w_images = op.images; p.vec = op.vec;
-    CUtensorMap m0, m1, mo;
+    if (g_stamps != nullptr && g_stamp_next < g_stamp_launches) {
+        p.stamps = g_stamps + (size_t)(g_stamp_next++) * 2 * g_stamp_tiles * 16;
+        p.stamp_tiles = g_stamp_tiles;
+    }
+    CUtensorMap m0, m1;
     int rc;
-    if ((rc = make_row_map(&m0, op.in0, op.rows))) return rc;
-    if ((rc = make_row_map(&m1, op.in1 ? op.in1 : op.in0, op.rows))) return rc;
-    if ((rc = make_row_map(&mo, op.out, op.rows))) return rc;
-    // spend the shared memory the weights leave on a second gather buffer, then on input-ring depth
-    p.n_ps = 1;
-    if (gather && ring_offset(n_blocks, NSI, 2) + 3 * CH_BYTES <= SMEM_MAX) p.n_ps = 2;
-    const size_t ring_off = ring_offset(n_blocks, NSI, gather ? p.n_ps : 0);
-    CGNN_CHECK_ARG(ring_off + 3 * CH_BYTES <= SMEM_MAX, "tensor-core chain: shared memory need %zu exceeds 227 KB", ring_off + 3 * CH_BYTES);
-    p.n_ring = (int)((SMEM_MAX - ring_off) / CH_BYTES);
+    if ((rc = make_row_map32(&m0, op.in0, op.rows))) return rc;
+    if ((rc = make_row_map32(&m1, op.in1 ? op.in1 : op.in0, op.rows))) return rc;
+    // the shared memory the weights leave goes to the input ring
+    const size_t ring_off = ring_offset(n_blocks, NSI);
+    CGNN_CHECK_ARG(ring_off + 2 * CW_BYTES <= SMEM_MAX, "tensor-core chain: shared memory need %zu exceeds 227 KB", ring_off + 2 * CW_BYTES);
+    p.n_ring = (int)((SMEM_MAX - ring_off) / CW_BYTES);
     if (p.n_ring > MAXRING) p.n_ring = MAXRING;
-    const size_t smem = ring_off + (size_t)p.n_ring * CH_BYTES;
-    auto kern = tc_chain_fwd<NS>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    const size_t smem = ring_off + (size_t)p.n_ring * CW_BYTES;
+    // the instantiation for this chain's shape
+    const bool any_hidden = op.n_layers == 3 && (gather || op.hid_mask[0] || op.hid_mask[1]);
+    const bool fin_a = (gather && op.n_layers == 1) || (op.ln_bwd ? op.du_rows != nullptr : op.mask_src != nullptr);
+    const bool fin_b = (gather && op.n_layers == 1) || (op.ln_bwd ? op.du_recv != nullptr : op.residual != nullptr);
+    const bool any_agg = op.agg_out || op.hid_agg[0] || op.hid_agg[1];
+    const int cfg = (op.n_layers == 3 ? C_L3 : 0) | (op.ln_bwd ? C_LNB : (op.gamma ? C_LN : 0)) | (fin_a ? C_SA : 0) | (fin_b ? C_SB : 0) |
+                    (any_hidden ? C_HS : 0) | (any_agg ? C_AGG : 0);
+    void (*kern)(CUtensorMap, CUtensorMap, TcParams) = nullptr;
+    int slot = -1;
+#define CGNN_CHAIN_CFG(i, c) else if (cfg == (c)) { kern = tc_chain_fwd<NS, (c)>; slot = (i); }
+    if (false) {}
+    CGNN_CHAIN_CFG(0, 0)                                              // 1 layer: plain / ReLU / two inputs
+    CGNN_CHAIN_CFG(1, C_SA | C_SB)                                    // 1 layer + gather (A1 of the edge backward)
+    CGNN_CHAIN_CFG(2, C_SA)                                           // 1 layer + mask (dgrad)
+    CGNN_CHAIN_CFG(3, C_SA | C_AGG)                                   // 1 layer + mask + per-receiver sum
+    CGNN_CHAIN_CFG(4, C_SB)                                           // 1 layer + residual
+    CGNN_CHAIN_CFG(5, C_L3)                                           // decoders
+    CGNN_CHAIN_CFG(6, C_L3 | C_LN)                                    // encoders
+    CGNN_CHAIN_CFG(7, C_L3 | C_LN | C_SB)                             // node phase forward
+    CGNN_CHAIN_CFG(8, C_L3 | C_LN | C_SB | C_HS)                      // edge phase forward without the per-receiver sum
+    CGNN_CHAIN_CFG(9, C_L3 | C_LN | C_SB | C_HS | C_AGG)              // edge phase forward
+    CGNN_CHAIN_CFG(10, C_L3 | C_LNB | C_SA | C_SB | C_HS)             // edge backward, recompute + LayerNorm backward
+    CGNN_CHAIN_CFG(11, C_L3 | C_LNB | C_SA)                           // node backward, recompute + LayerNorm backward
+    CGNN_CHAIN_CFG(12, C_L3 | C_SB | C_HS | C_AGG)                    // edge backward, dgrad chain
+    CGNN_CHAIN_CFG(13, C_L3 | C_HS)                                   // node backward, dgrad chain
+    CGNN_CHAIN_CFG(14, C_AGG)                                         // 1 layer + per-receiver sum
+#undef CGNN_CHAIN_CFG
+    if (kern == nullptr) {
+        set_error("tensor-core chain: no kernel instantiated for configuration 0x%x", cfg);
+        return CGNN_ERR_UNSUPPORTED;
+    }
+    static size_t configured[16] = {0};
+    if (smem > configured[slot]) {
         CGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[slot] = smem;
     }
     int64_t pairs = num_sms() / 2;
     if (p.n_pair_tiles < pairs) pairs = p.n_pair_tiles;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(pairs * 2));
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)(pairs * 2));
+    lc.blockDim = dim3(TC_THREADS);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    CGNN_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mo, p));
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    CGNN_CUDA(cudaLaunchKernelEx(&lc, kern, m0, m1, p));
     count_launch();
+    if (op.ln_bwd) {
+        ln_partials_reduce_kernel<<<2 * TC_H / 32, 256, 0, stream>>>(p.ln_partials, (int)(pairs * 2 * 8), op.dgamma, op.dbeta, op.accumulate);
+        CGNN_LAUNCH_CHECK();
+    }
     return CGNN_OK;
 }
 
@@ -615,7 +803,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_row_map(CUtensorMap* m, const float* base, int64_t rows) {
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz);
+int make_row_map(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, CH, CU_TENSOR_MAP_SWIZZLE_64B); }
+
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz) {
     static EncodeTiledFn fn = nullptr;
     if (fn == nullptr) {
         void* f = nullptr;
@@ -626,16 +817,22 @@ int make_row_map(CUtensorMap* m, const float* base, int64_t rows) {
     }
     cuuint64_t dims[2] = {(cuuint64_t)TC_H, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)TC_H * 4};
-    cuuint32_t box[2] = {(cuuint32_t)CH, 128};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, 128};
     cuuint32_t es[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (base %p, rows %lld)", (int)r, (const void*)base, (long long)rows);
         return CGNN_ERR_CUDA;
     }
     return CGNN_OK;
+}
+
+int make_row_map32(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B); }
+
+void set_debug_stamps(unsigned long long* buf, int tiles, int launches) {
+    g_stamps = buf; g_stamp_tiles = tiles; g_stamp_launches = launches; g_stamp_next = 0;
 }
 
 int64_t chain_image_bytes() { return (int64_t)MAX_BLOCKS * 2 * 2 * WIMG; }

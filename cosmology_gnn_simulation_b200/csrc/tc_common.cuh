@@ -35,6 +35,8 @@ __device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 
 
 // 2-D tensor map over a row-major FP32 [rows][128] array: boxes of 128 rows x 16 columns, 64-byte swizzle
 int make_row_map(CUtensorMap* m, const float* base, int64_t rows);
+// boxes of 128 rows x 32 columns, 128-byte swizzle (the chain kernel's input ring)
+int make_row_map32(CUtensorMap* m, const float* base, int64_t rows);
 
 // ---- building blocks used by the backward orchestration (defined in mp_tc.cu / wgrad_tc.cu) -----------
 // B[n][k] = W[(row0 + n) * ld + col0 + k] (transpose: W[(row0 + k) * ld + col0 + n]); zero where n >= nmax or k >= kmax (0 = 128)
@@ -57,6 +59,12 @@ struct ChainOp {
     float* agg_out;               // [rows / k][128] = per-receiver sum of the result before the residual (nullable)
     float* out;                   // [rows][128]
     uint8_t* images; float* vec;  // workspace (chain_image_bytes(), chain_vec_bytes())
+    int prepared;                 // images / vec already hold this chain's weight images (skip the prep launch)
+    // hidden layers of a 3-layer chain (index 0, 1): mask instead of ReLU, extra output, per-receiver sum of the activation
+    const float* hid_mask[2]; float* hid_out[2]; float* hid_agg[2];
+    // LayerNorm backward instead of forward after the last layer: out = dY of (Y, dU), dU = du_rows[row] + du_recv[row / k];
+    // d gamma / d beta (=|+=) their column sums (fixed-order reduction through ln_ws, ln_bwd_workspace_bytes())
+    int ln_bwd; const float* du_rows; const float* du_recv; float* dgamma; float* dbeta; int accumulate; void* ln_ws;
 };
 int64_t chain_image_bytes();
 int64_t chain_vec_bytes();

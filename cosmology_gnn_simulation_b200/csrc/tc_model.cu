@@ -19,6 +19,7 @@ namespace {
 
 constexpr int64_t CHUNK_ROWS = 1 << 21;      // edge rows per backward chunk (1 GiB per FP32 buffer)
 
+bool tc_k_ok(int k) { return k >= 1 && k <= 32 && (k & (k - 1)) == 0; }
 bool tc_shape_ok(const MlpDev& m, int in_mult) {
     return m.n_layers == 3 && m.hidden == TC_H && m.out_dim == TC_H && m.in_dim == in_mult * TC_H && m.gamma != nullptr;
 }
@@ -123,8 +124,8 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
     const int ns = precision == CGNN_PREC_BF16X3 ? 3 : 1;
     const MlpDev& m = a.mlp;
     if (a.mode == MODE_EDGE) {
-        if (!tc_shape_ok(m, 3) || a.k < 1 || 128 % a.k != 0) {
-            set_error("tensor-core edge phase supports latent = hidden = 128, 2 hidden layers and k dividing 128 (got in %d hidden %d out %d layers %d k %d)",
+        if (!tc_shape_ok(m, 3) || !tc_k_ok(a.k)) {
+            set_error("tensor-core edge phase supports latent = hidden = 128, 2 hidden layers and k a power of two <= 32 (got in %d hidden %d out %d layers %d k %d)",
                       m.in_dim, m.hidden, m.out_dim, m.n_layers, a.k);
             return CGNN_ERR_UNSUPPORTED;
         }
@@ -337,7 +338,7 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         return CGNN_OK;
     }
     if (a.mode == MODE_EDGE) {
-        if (!tc_shape_ok(m, 3) || a.k < 1 || 128 % a.k != 0 || a.t_rowptr == nullptr || a.t_perm == nullptr) return CGNN_ERR_UNSUPPORTED;
+        if (!tc_shape_ok(m, 3) || !tc_k_ok(a.k) || a.t_rowptr == nullptr || a.t_perm == nullptr) return CGNN_ERR_UNSUPPORTED;
         const int64_t n = a.n, k = a.k, E = n * k;
         const int64_t nn = a.n_nodes > 0 ? a.n_nodes : a.n;
         const int64_t need = tc_bwd_workspace(nullptr, n, nn, a.k, precision);

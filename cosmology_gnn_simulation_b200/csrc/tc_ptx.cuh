@@ -34,15 +34,27 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n\t}"
         ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
+// same, without memory ordering: for arrivals that only publish tcgen05 (TMEM) writes, which tcgen05.wait::st +
+// tcgen05.fence::before_thread_sync have already completed -- a release at cluster scope would also wait for every
+// outstanding global store of the thread to become visible
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 raddr;\n\t"
+        "mapa.shared::cluster.u32 raddr, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [raddr];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// blocks until the phase with the given parity has completed (acquire at cluster scope)
+// blocks until the phase with the given parity has completed.  Default semantics (acquire at CTA scope): every barrier
+// here is completed by TMA transactions, tcgen05.commit or arrivals that publish only TMEM writes; a cluster-scope
+// acquire would add an L1 invalidation (CCTL.IVALL) to every wait
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
@@ -53,7 +65,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;

@@ -293,7 +293,8 @@ int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, i
     return CGNN_OK;
 }
 
-int64_t ln_bwd_workspace_bytes() { return align_up((int64_t)LNB_BLOCKS * 2 * TC_H * 4, 256); }
+// also holds the per-warp partials of the chain kernel's LayerNorm-backward epilogue (148 CTAs x 8 warps)
+int64_t ln_bwd_workspace_bytes() { return align_up((int64_t)(LNB_BLOCKS > 148 * 8 ? LNB_BLOCKS : 148 * 8) * 2 * TC_H * 4, 256); }
 
 // dY may alias Y.  dgamma / dbeta: written (or accumulated into) after a fixed-order reduction.
 int run_ln_bwd(const float* Y, const float* dU_rows, const float* dU_recv, int k, const float* gamma, int64_t rows,

@@ -70,6 +70,11 @@ const char* cgnn_last_error(void);
 const char* cgnn_version(void);
 /* number of kernels launched by this library in this process so far (for bench `gpu_launches`) */
 int64_t cgnn_launch_count(void);
+/* debug / profiling hook (tools/chain_stamps.py): `stamps` is a device buffer of launches * 2 * tiles * 16 uint64;
+ * the next `launches` tensor-core chain launches record clock64() of the stages of block 0's first `tiles` tiles
+ * per epilogue group into consecutive slices of it.  NULL switches the recording off (the default).  Not used
+ * by the product path. */
+void cgnn_debug_stamps(unsigned long long* stamps, int32_t tiles, int32_t launches);
 
 /* ---------------------------------------------------------------------------------------------
  * K1  periodic k-NN  -- replaces extend_positions_torch + torch_cluster.knn + index remap,
