@@ -657,20 +657,21 @@ __global__ void tc_prep_kernel(PrepArgs a, uint8_t* __restrict__ images, float* 
 constexpr size_t SMEM_MAX = 227 * 1024;
 bool gather_final(const ChainOp& op) { return op.Ps != nullptr && op.n_layers == 1; }
 
-// sums the per-warp LayerNorm-backward column sums [n_rows_p][2][128] in fixed order: block <-> 32 columns,
-// 8 row slices per block combined through shared memory
+// sums the per-warp LayerNorm-backward column sums [n_rows_p][2][128] in fixed order: block <-> 8 columns x 32 row slices,
+// combined through shared memory
 __global__ void __launch_bounds__(256) ln_partials_reduce_kernel(const float* __restrict__ partials, int n_rows_p,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
-    __shared__ float sm[8][32];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5;
+    __shared__ float sm[32][8];
+    const int cl = threadIdx.x & 7, part = threadIdx.x >> 3;
+    const int c = blockIdx.x * 8 + cl;
     float s = 0.0f;
-    for (int r = part; r < n_rows_p; r += 8) s += partials[(size_t)r * 2 * TC_H + c];
-    sm[part][threadIdx.x & 31] = s;
+    for (int r = part; r < n_rows_p; r += 32) s += partials[(size_t)r * 2 * TC_H + c];
+    sm[part][cl] = s;
     __syncthreads();
     if (part == 0) {
         float t = 0.0f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+        for (int w = 0; w < 32; ++w) t += sm[w][cl];
         float* base = c < TC_H ? dgamma : dbeta;
         if (base != nullptr) {
             float* d = base + (c < TC_H ? c : c - TC_H);
@@ -766,12 +767,18 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     CGNN_CHAIN_CFG(12, C_L3 | C_SB | C_HS | C_AGG)                    // edge backward, dgrad chain
     CGNN_CHAIN_CFG(13, C_L3 | C_HS)                                   // node backward, dgrad chain
     CGNN_CHAIN_CFG(14, C_AGG)                                         // 1 layer + per-receiver sum
+    CGNN_CHAIN_CFG(15, C_L3 | C_LNB | C_SB | C_HS)                    // edge backward recompute, no gradient on the edge output
+    CGNN_CHAIN_CFG(16, C_L3 | C_HS | C_AGG)                           // edge backward dgrad, no gradient on the edge output
+    CGNN_CHAIN_CFG(17, C_L3 | C_SB | C_HS)                            // node backward dgrad
+    CGNN_CHAIN_CFG(18, C_LNB | C_SA | C_SB)                           // 1 layer + LayerNorm backward (dU per row and per receiver)
+    CGNN_CHAIN_CFG(19, C_LNB | C_SA)
+    CGNN_CHAIN_CFG(20, C_LNB | C_SB)
 #undef CGNN_CHAIN_CFG
     if (kern == nullptr) {
         set_error("tensor-core chain: no kernel instantiated for configuration 0x%x", cfg);
         return CGNN_ERR_UNSUPPORTED;
     }
-    static size_t configured[16] = {0};
+    static size_t configured[24] = {0};
     if (smem > configured[slot]) {
         CGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[slot] = smem;
@@ -791,7 +798,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     CGNN_CUDA(cudaLaunchKernelEx(&lc, kern, m0, m1, p));
     count_launch();
     if (op.ln_bwd) {
-        ln_partials_reduce_kernel<<<2 * TC_H / 32, 256, 0, stream>>>(p.ln_partials, (int)(pairs * 2 * 8), op.dgamma, op.dbeta, op.accumulate);
+        ln_partials_reduce_kernel<<<2 * TC_H / 8, 256, 0, stream>>>(p.ln_partials, (int)(pairs * 2 * 8), op.dgamma, op.dbeta, op.accumulate);
         CGNN_LAUNCH_CHECK();
     }
     return CGNN_OK;

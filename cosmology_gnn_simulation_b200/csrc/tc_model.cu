@@ -12,6 +12,8 @@
 //   per-node sums of G1 (sender-sorted transpose / k consecutive rows).
 //
 // Reference semantics: graph_network.py:83-101,177-183 and its autograd (train.py:264).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace cgnn {
@@ -217,44 +219,100 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// Shared tail of both phases for one row range: given the layer-1 pre-activation inputs already applied
-// (A1 = relu(pre1) in bufA1) it recomputes A2, Y, runs LayerNorm backward and the dgrad chain down to
-// G1 = dL/dpre1 (written to g1_out, optionally with its per-receiver sum), and accumulates dW2, dW3, db2,
-// db3, d gamma, d beta.   Buffers: A1, A2, T (Y then dY), G2.
-static int backward_tail(int ns, const Scratch& sc, const MlpDev& m, const cgnn_mlp_grad* g, int64_t rows,
-                         float* A1, float* A2, float* T, float* G2, const float* dU_rows, const float* dU_recv, int k,
-                         float* g1_out, float* g1_agg, int accumulate, cudaStream_t s) {
-    int rc;
-    {   // A2 = relu(A1 W2^T + b2)
-        ChainOp op = base_op(ns, sc, rows);
-        op.in0 = A1; op.blk[0] = {m.W[1], TC_H, 0, 0, 0}; op.bias[0] = m.b[1]; op.relu_out = 1; op.out = A2;
-        if ((rc = run_chain(op, s))) return rc;
+// 0: one-layer chains everywhere (each runs at the HBM rate) with the LayerNorm backward fused into the Y chain;
+// 1: the two fused 3-layer chains of fused_backward (fewer row-stream passes, but bound by the per-tile latency chain)
+static int bwd_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("CGNN_BWD_FUSED");
+        mode = e ? atoi(e) : 0;
     }
-    if (m.gamma != nullptr) {
-        {   // Y = A2 W3^T + b3
+    return mode;
+}
+
+// Backward of one 3-layer MLP (+ LayerNorm) over a row range as TWO fused chains plus the weight gradients:
+//   R  recompute:  in -> A1 -> A2 -> Y, LayerNorm backward of (Y, dU) in the final epilogue -> dY (T);
+//                  A1, A2 are written from the hidden epilogues (the dgrad masks and the wgrad operands),
+//                  d gamma / d beta come out of the same launch
+//   D  dgrad:      dY -> G2 = (dY W3) * [A2 > 0] -> G1 = (G2 W2) * [A1 > 0] (+ per-receiver sum)
+//                  -> d_in = G1 * last^T (+ residual); G2, G1 are written from the hidden epilogues
+//   dW3 = dY^T A2, dW2 = G2^T A1 (+ biases) here; dW1 = G1^T in by the caller (its input layout differs per phase).
+// `r` carries the input side of R (in0 / in1, their weight blocks, bias[0] or the gather); without a LayerNorm
+// (decoders) the caller has put dY, zero padded to 128 columns, into T.
+static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn_mlp_grad* g, int64_t rows, ChainOp r,
+                          float* A1, float* A2, float* T, float* G2, const float* du_rows, const float* du_recv, int k,
+                          ChainBlock last, const float* residual, float* d_in, float* g1_out, float* g1_agg,
+                          int accumulate, cudaStream_t s) {
+    int rc;
+    const int n_in = r.in1 ? 2 : 1;
+    if (bwd_mode() == 0) {
+        // A1 = relu(layer 1), A2 = relu(A1 W2^T + b2)
+        r.ns = ns; r.rows = rows; r.n_layers = 1; r.images = sc.images; r.vec = sc.vec;
+        r.relu_out = 1; r.out = A1;
+        if ((rc = run_chain(r, s))) return rc;
+        {
             ChainOp op = base_op(ns, sc, rows);
-            op.in0 = A2; op.blk[0] = {m.W[2], TC_H, 0, 0, 0}; op.bias[0] = m.b[2]; op.out = T;
+            op.in0 = A1; op.blk[0] = {m.W[1], TC_H, 0, 0, 0}; op.bias[0] = m.b[1]; op.relu_out = 1; op.out = A2;
             if ((rc = run_chain(op, s))) return rc;
         }
-        // dY = LNbwd(Y, dU)  (in place), d gamma, d beta
-        if ((rc = run_ln_bwd(T, dU_rows, dU_recv, k, m.gamma, rows, T, g->ln_gamma, g->ln_beta, accumulate, sc.lnb, s))) return rc;
-    }   // else: no LayerNorm (decoders) -- the caller put dY, zero-padded to 128 columns, into T
+        if (m.gamma != nullptr) {   // dY = LayerNorm backward of (Y = A2 W3^T + b3, dU), in the chain's final epilogue
+            ChainOp op = base_op(ns, sc, rows);
+            op.in0 = A2; op.blk[0] = {m.W[2], TC_H, 0, 0, 0}; op.bias[0] = m.b[2];
+            op.gamma = m.gamma; op.beta = m.beta; op.ln_bwd = 1; op.k = k;
+            op.du_rows = du_rows; op.du_recv = du_recv; op.dgamma = g->ln_gamma; op.dbeta = g->ln_beta; op.accumulate = accumulate; op.ln_ws = sc.lnb;
+            op.out = T;
+            if ((rc = run_chain(op, s))) return rc;
+        }
+        if ((rc = run_wgrad(ns, T, A2, rows, g->W[2], TC_H, 0, g->b[2], accumulate, sc.wg, s, m.out_dim, 0))) return rc;
+        {   // G2 = (dY W3) * [A2 > 0]
+            ChainOp op = base_op(ns, sc, rows);
+            op.in0 = T; op.blk[0] = {m.W[2], TC_H, 0, 0, 1, 0, m.out_dim}; op.mask_src = A2; op.out = G2;
+            if ((rc = run_chain(op, s))) return rc;
+        }
+        if ((rc = run_wgrad(ns, G2, A1, rows, g->W[1], TC_H, 0, g->b[1], accumulate, sc.wg, s))) return rc;
+        {   // G1 = (G2 W2) * [A1 > 0]   (+ per-receiver sum)
+            ChainOp op = base_op(ns, sc, rows);
+            op.in0 = G2; op.blk[0] = {m.W[1], TC_H, 0, 0, 1}; op.mask_src = A1; op.out = g1_out;
+            op.k = k; op.agg_out = g1_agg;
+            if ((rc = run_chain(op, s))) return rc;
+        }
+        if (d_in != nullptr) {   // d_in = G1 last^T (+ residual)
+            ChainOp op = base_op(ns, sc, rows);
+            op.in0 = g1_out; op.blk[0] = last; op.residual = residual; op.out = d_in;
+            if ((rc = run_chain(op, s))) return rc;
+        }
+        return CGNN_OK;
+    }
+    r.ns = ns; r.rows = rows; r.n_layers = 3; r.images = sc.images; r.vec = sc.vec;
+    r.blk[n_in] = {m.W[1], TC_H, 0, 0, 0};
+    r.blk[n_in + 1] = {m.W[2], TC_H, 0, 0, 0, m.out_dim, 0};
+    r.bias[1] = m.b[1]; r.bias[2] = m.b[2];
+    r.out_valid = m.out_dim < TC_H ? m.out_dim : 0;
+    r.hid_out[0] = A1; r.hid_out[1] = A2;
+    if (m.gamma != nullptr) {
+        r.gamma = m.gamma; r.beta = m.beta; r.ln_bwd = 1; r.k = k;
+        r.du_rows = du_rows; r.du_recv = du_recv; r.dgamma = g->ln_gamma; r.dbeta = g->ln_beta; r.accumulate = accumulate; r.ln_ws = sc.lnb;
+        r.out = T;
+    } else {
+        r.out = G2;                                   // Y itself is not needed: parked in G2, which D overwrites
+    }
+    if ((rc = run_chain(r, s))) return rc;
     // dW3 = dY^T A2, db3
     if ((rc = run_wgrad(ns, T, A2, rows, g->W[2], TC_H, 0, g->b[2], accumulate, sc.wg, s, m.out_dim, 0))) return rc;
-    {   // G2 = (dY W3) * [A2 > 0]
-        ChainOp op = base_op(ns, sc, rows);
-        op.in0 = T; op.blk[0] = {m.W[2], TC_H, 0, 0, 1, 0, m.out_dim}; op.mask_src = A2; op.out = G2;
-        if ((rc = run_chain(op, s))) return rc;
-    }
+    ChainOp d = base_op(ns, sc, rows);
+    d.n_layers = 3;
+    d.in0 = T;
+    d.blk[0] = {m.W[2], TC_H, 0, 0, 1, 0, m.out_dim};
+    d.blk[1] = {m.W[1], TC_H, 0, 0, 1};
+    d.blk[2] = last;
+    d.hid_mask[0] = A2; d.hid_mask[1] = A1;
+    d.hid_out[0] = G2; d.hid_out[1] = g1_out;
+    d.k = k; d.hid_agg[1] = g1_agg;
+    d.residual = residual;
+    d.out = d_in ? d_in : T;                          // no input gradient wanted: the last product lands on its own input tile
+    if ((rc = run_chain(d, s))) return rc;
     // dW2 = G2^T A1, db2
-    if ((rc = run_wgrad(ns, G2, A1, rows, g->W[1], TC_H, 0, g->b[1], accumulate, sc.wg, s))) return rc;
-    {   // G1 = (G2 W2) * [A1 > 0]   (+ per-receiver sum)
-        ChainOp op = base_op(ns, sc, rows);
-        op.in0 = G2; op.blk[0] = {m.W[1], TC_H, 0, 0, 1}; op.mask_src = A1; op.out = g1_out;
-        op.k = k; op.agg_out = g1_agg;
-        if ((rc = run_chain(op, s))) return rc;
-    }
-    return CGNN_OK;
+    return run_wgrad(ns, G2, A1, rows, g->W[1], TC_H, 0, g->b[1], accumulate, sc.wg, s);
 }
 
 int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s) {
@@ -282,23 +340,17 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
                 if ((rc = pad_rows(in, m.in_dim, rows, Xp, s))) return rc;
                 in = Xp;
             }
-            {   // A1 = relu(x W1^T + b1)
-                ChainOp op = base_op(ns, sc, rows);
-                op.in0 = in; op.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim}; op.bias[0] = m.b[0]; op.relu_out = 1; op.out = A1;
-                if ((rc = run_chain(op, s))) return rc;
-            }
             const float* dU = a.dout + r0 * m.out_dim;
             if (m.gamma == nullptr) {                       // no LayerNorm: dY = dout, zero padded
                 if (m.out_dim < TC_H) { if ((rc = pad_rows(dU, m.out_dim, rows, T, s))) return rc; }
                 else CGNN_CUDA(cudaMemcpyAsync(T, dU, (size_t)rows * TC_H * 4, cudaMemcpyDeviceToDevice, s));
             }
-            if ((rc = backward_tail(ns, sc, m, g, rows, A1, A2, T, G2, dU, nullptr, 1, G1, nullptr, acc, s))) return rc;
+            ChainOp r{};
+            r.in0 = in; r.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim}; r.bias[0] = m.b[0];
+            // dx = G1 W1 (in_dim == 128) comes out of the dgrad chain's last layer
+            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, dU, nullptr, 1, {m.W[0], m.in_dim, 0, 0, 1, m.in_dim, 0},
+                                     nullptr, a.dx ? a.dx + r0 * TC_H : nullptr, G1, nullptr, acc, s))) return rc;
             if ((rc = run_wgrad(ns, G1, in, rows, g->W[0], m.in_dim, 0, g->b[0], acc, sc.wg, s, 0, m.in_dim))) return rc;
-            if (a.dx != nullptr) {                         // dx = G1 W1   (in_dim == 128)
-                ChainOp op = base_op(ns, sc, rows);
-                op.in0 = G1; op.blk[0] = {m.W[0], TC_H, 0, 0, 1}; op.out = a.dx + r0 * TC_H;
-                if ((rc = run_chain(op, s))) return rc;
-            }
         }
         return CGNN_OK;
     }
@@ -314,22 +366,16 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         const int64_t n = a.n;
         float* A1 = cv.take<float>(n * TC_H); float* A2 = cv.take<float>(n * TC_H); float* T = cv.take<float>(n * TC_H);
         float* G2 = cv.take<float>(n * TC_H); float* G1 = cv.take<float>(n * TC_H);
-        {   // A1 = relu([h | agg] W1^T + b1)
-            ChainOp op = base_op(ns, sc, n);
-            op.in0 = a.h; op.in1 = a.agg;
-            op.blk[0] = {m.W[0], 2 * TC_H, 0, 0, 0}; op.blk[1] = {m.W[0], 2 * TC_H, 0, TC_H, 0};
-            op.bias[0] = m.b[0]; op.relu_out = 1; op.out = A1;
-            if ((rc = run_chain(op, s))) return rc;
-        }
-        if ((rc = backward_tail(ns, sc, m, g, n, A1, A2, T, G2, a.dout, nullptr, 1, G1, nullptr, 0, s))) return rc;
+        ChainOp r{};
+        r.in0 = a.h; r.in1 = a.agg;
+        r.blk[0] = {m.W[0], 2 * TC_H, 0, 0, 0}; r.blk[1] = {m.W[0], 2 * TC_H, 0, TC_H, 0};
+        r.bias[0] = m.b[0];
+        // dh = dh_next + G1 W1[:, 0:L] is the dgrad chain's last layer
+        if ((rc = fused_backward(ns, sc, m, g, n, r, A1, A2, T, G2, a.dout, nullptr, 1, {m.W[0], 2 * TC_H, 0, 0, 1}, a.dout, a.dh, G1,
+                                 nullptr, 0, s))) return rc;
         // dW1 = G1^T [h | agg], db1
         if ((rc = run_wgrad(ns, G1, a.h, n, g->W[0], 2 * TC_H, 0, g->b[0], 0, sc.wg, s))) return rc;
         if ((rc = run_wgrad(ns, G1, a.agg, n, g->W[0], 2 * TC_H, TC_H, nullptr, 0, sc.wg, s))) return rc;
-        {   // dh = dh_next + G1 W1[:, 0:L]
-            ChainOp op = base_op(ns, sc, n);
-            op.in0 = G1; op.blk[0] = {m.W[0], 2 * TC_H, 0, 0, 1}; op.residual = a.dout; op.out = a.dh;
-            if ((rc = run_chain(op, s))) return rc;
-        }
         {   // dagg = G1 W1[:, L:2L]
             ChainOp op = base_op(ns, sc, n);
             op.in0 = G1; op.blk[0] = {m.W[0], 2 * TC_H, 0, TC_H, 1}; op.out = a.dagg_out;
@@ -360,23 +406,15 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             const float* de_next = a.de_next ? a.de_next + r0 * TC_H : nullptr;
             float* G1 = a.gs + r0 * TC_H;
             const int acc = c > 0;
-            {   // A1 = relu(e W1e^T + Ps[sender] + Pr[receiver])
-                ChainOp op = base_op(ns, sc, rows);
-                op.in0 = e_in; op.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 0};
-                op.k = a.k; op.senders = a.senders + r0; op.Ps = Ps; op.Pr = Pr + (r0 / k) * TC_H;
-                op.relu_out = 1; op.out = A1;
-                if ((rc = run_chain(op, s))) return rc;
-            }
-            // dU = de_next + dagg[receiver]
-            if ((rc = backward_tail(ns, sc, m, g, rows, A1, A2, T, G2, de_next, a.dagg + (r0 / k) * TC_H, a.k, G1,
-                                    dPr + (r0 / k) * TC_H, acc, s))) return rc;
+            // recompute with e W1e^T + Ps[sender] + Pr[receiver] as layer 1; dU = de_next + dagg[receiver];
+            // de = de_next + G1 W1e is the dgrad chain's last layer, the per-receiver sum of G1 is d P_r
+            ChainOp r{};
+            r.in0 = e_in; r.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 0};
+            r.k = a.k; r.senders = a.senders + r0; r.Ps = Ps; r.Pr = Pr + (r0 / k) * TC_H;
+            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, de_next, a.dagg + (r0 / k) * TC_H, a.k,
+                                     {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}, de_next, a.de + r0 * TC_H, G1, dPr + (r0 / k) * TC_H, acc, s))) return rc;
             // dW1e = G1^T e, db1
             if ((rc = run_wgrad(ns, G1, e_in, rows, g->W[0], 3 * TC_H, 2 * TC_H, g->b[0], acc, sc.wg, s))) return rc;
-            {   // de = de_next + G1 W1e
-                ChainOp op = base_op(ns, sc, rows);
-                op.in0 = G1; op.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}; op.residual = de_next; op.out = a.de + r0 * TC_H;
-                if ((rc = run_chain(op, s))) return rc;
-            }
         }
         // per-node sums of G1: by sender (transpose CSR, deterministic) and by receiver (dPr, from the chunks)
         CGNN_CUDA(cudaMemsetAsync(dPs, 0, (size_t)nn * TC_H * 4, s));

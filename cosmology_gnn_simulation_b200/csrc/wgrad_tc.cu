@@ -18,16 +18,21 @@ namespace {
 
 using namespace ptx;
 
-constexpr int WG_THREADS = 192;           // 4 converter warps + producer warp + MMA warp
-constexpr int WG_RING = 8;
+constexpr int WG_THREADS = 320;           // 8 converter warps (two per row quarter, alternating chunks) + producer warp + MMA warp
+constexpr int WG_PROD = 8, WG_MMA = 9;
+constexpr int WG_RING = 4;                // input ring: 128 rows x 32 columns (128-byte rows, SWIZZLE_128B) per chunk.  EVEN, so that
+                                          // a ring slot is always consumed by the same converter set (chunk parity) and the phase
+                                          // parity a set waits on can never alias a phase that belongs to the other set
+constexpr int CW = 32, NCW = TC_H / CW, CW_BYTES = 128 * CW * 4;
 constexpr int OP_BYTES = 128 * 128 * 2;   // one BF16 operand image (128 mn x 128 k)
 constexpr int ONES_BYTES = 16 * 128 * 2;
 constexpr int PW = 132;                   // floats per partial row: 128 dW columns + db + pad
 constexpr float LN_EPS = 1e-5f;
 
+static_assert(WG_RING % 2 == 0, "ring slots must keep the chunk parity");
 struct WgSmem {
     static constexpr int ring = 0;
-    static constexpr int bars = ring + WG_RING * CH_BYTES;
+    static constexpr int bars = ring + WG_RING * CW_BYTES;
     static constexpr int ones = bars + 256;
     static constexpr int ops = ones + ONES_BYTES;          // X images (NSI), then A images (NSI)
 };
@@ -56,7 +61,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 
     if (tid == 0) {
         for (int i = 0; i < WG_RING; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 4); }
-        mbar_init(&bars->ops_full, 4);
+        mbar_init(&bars->ops_full, 8);
         mbar_init(&bars->ops_empty, 1);
         fence_mbar_init();
     }
@@ -64,30 +69,30 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     __syncthreads();
     for (int k = tid; k < 128; k += WG_THREADS)
         *reinterpret_cast<uint16_t*>(sOnes + (k >> 3) * 128 + (k & 7) * 16) = 0x3F80;     // bf16(1.0) at mn = 0
-    if (warp == 5) tmem_alloc<1>(&bars->tmem_base, 256);
-    if (warp == 4 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_a); }
+    if (warp == WG_MMA) tmem_alloc<1>(&bars->tmem_base, 256);
+    if (warp == WG_PROD && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_a); }
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp == 4) {
+    if (warp == WG_PROD) {
         // ---- producer: X chunks then A chunks of every tile --------------------------------------------
         if (lane == 0) {
             uint32_t seq = 0;
             for (int64_t it = 0; it < n_it; ++it) {
                 const int64_t row0 = (blockIdx.x + it * gridDim.x) * 128;
                 for (int op = 0; op < 2; ++op)
-                    for (int q = 0; q < NCH; ++q, ++seq) {
+                    for (int q = 0; q < NCW; ++q, ++seq) {
                         const uint32_t buf = seq % WG_RING, use = seq / WG_RING;
                         mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 200 + buf);
-                        mbar_expect_tx(&bars->in_full[buf], CH_BYTES);
-                        tma_load_2d(smem + WgSmem::ring + buf * CH_BYTES, op == 0 ? &tm_x : &tm_a, q * CH, (int)row0, &bars->in_full[buf]);
+                        mbar_expect_tx(&bars->in_full[buf], CW_BYTES);
+                        tma_load_2d(smem + WgSmem::ring + buf * CW_BYTES, op == 0 ? &tm_x : &tm_a, q * CW, (int)row0, &bars->in_full[buf]);
                     }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == WG_MMA) {
         // ---- MMA issuer ---------------------------------------------------------------------------------------
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16_major(128, TC_H, 1, 1);
@@ -116,33 +121,35 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
         }
     } else {
-        // ---- converters: thread = row of the tile ---------------------------------------------------------
-        const int r = tid;
+        // ---- converters: thread = row of the tile; warps 0-3 take the even chunks, warps 4-7 the odd ones, so every
+        //      scheduler has two converter warps to interleave ---------------------------------------------------
+        const int r = tid & 127;
+        const int cpar = tid >> 7;
         uint32_t seq = 0;
         for (int64_t it = 0; it < n_it; ++it) {
             if (it > 0) mbar_wait_or_trap(&bars->ops_empty, (uint32_t)((it - 1) & 1), 220);      // previous tile's MMAs read the images
             for (int op = 0; op < 2; ++op) {
                 uint8_t* img = op == 0 ? sX : sA;
-                for (int q = 0; q < NCH; ++q, ++seq) {
+                for (int q = 0; q < NCW; ++q, ++seq) {
+                    if ((q & 1) != cpar) continue;
                     const uint32_t buf = seq % WG_RING, use = seq / WG_RING;
                     mbar_wait_or_trap(&bars->in_full[buf], use & 1, 230 + buf);
-                    const uint8_t* src = smem + WgSmem::ring + buf * CH_BYTES;
-                    uint32_t hi[8], lo[8];
+                    const uint8_t* src = smem + WgSmem::ring + buf * CW_BYTES;
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 v = *reinterpret_cast<const float4*>(src + swz64(r, j));
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 v = *reinterpret_cast<const float4*>(src + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)));
                         split2(v.x, v.y, hi[2 * j], lo[2 * j]);
                         split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
-                    // columns 16q .. 16q+15 = mn groups 2q, 2q+1; k = r
-                    uint8_t* dst = img + (2 * q) * 2048 + (r >> 3) * 128 + (r & 7) * 16;
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(dst + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    if (NS == 3) {
-                        *reinterpret_cast<uint4*>(dst + OP_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<uint4*>(dst + OP_BYTES + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    // columns 32q .. 32q+31 = mn groups 4q .. 4q+3; k = r
+                    uint8_t* dst = img + (4 * q) * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        *reinterpret_cast<uint4*>(dst + j * 2048) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        if (NS == 3) *reinterpret_cast<uint4*>(dst + OP_BYTES + j * 2048) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
                 }
             }
@@ -156,9 +163,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             tc_fence_after_sync();
         }
         float* dst = partials + ((size_t)blockIdx.x * 128 + r) * PW;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 144; c0 += 16) {
+        for (int c0 = cpar * 16; c0 < 144; c0 += 32) {
             float v[16];
             if (n_it > 0) {
                 tmem_ld_32x32b_x16(trow + c0, v);
@@ -177,22 +184,30 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 5) tmem_dealloc<1>(tmem, 256);
+    if (warp == WG_MMA) tmem_dealloc<1>(tmem, 256);
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int n_cta, float* __restrict__ dW, int ld, int col0,
-                                    float* __restrict__ db, int accumulate, int nrows, int ncols) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 128 * 129) return;
+// sums the per-CTA partials in fixed order: block <-> 64 outputs x 4 slices of the CTA list, combined through shared memory
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, int n_cta, float* __restrict__ dW, int ld, int col0,
+                                                           float* __restrict__ db, int accumulate, int nrows, int ncols) {
+    __shared__ float sm[4][64];
+    const int o = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const int idx = blockIdx.x * 64 + o;
     const int n = idx / 129, c = idx % 129;
-    if (n >= nrows || (c < 128 && c >= ncols)) return;
+    const bool live = idx < 128 * 129 && n < nrows && (c == 128 || c < ncols);
     float s = 0.0f;
-    for (int g = 0; g < n_cta; ++g) s += partials[((size_t)g * 128 + n) * PW + c];
-    if (c < 128) {
-        float* d = dW + (size_t)n * ld + col0 + c;
-        *d = accumulate ? *d + s : s;
-    } else if (db != nullptr) {
-        db[n] = accumulate ? db[n] + s : s;
+    if (live)
+        for (int g = sl; g < n_cta; g += 4) s += partials[((size_t)g * 128 + n) * PW + c];
+    sm[sl][o] = s;
+    __syncthreads();
+    if (sl == 0 && live) {
+        s = (sm[0][o] + sm[1][o]) + (sm[2][o] + sm[3][o]);
+        if (c < 128) {
+            float* d = dW + (size_t)n * ld + col0 + c;
+            *d = accumulate ? *d + s : s;
+        } else if (db != nullptr) {
+            db[n] = accumulate ? db[n] + s : s;
+        }
     }
 }
 
@@ -273,8 +288,8 @@ int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, i
     if (n_tiles < grid) grid = (int)n_tiles;
     CUtensorMap mx, ma;
     int rc;
-    if ((rc = make_row_map(&mx, X, rows))) return rc;
-    if ((rc = make_row_map(&ma, A, rows))) return rc;
+    if ((rc = make_row_map32(&mx, X, rows))) return rc;
+    if ((rc = make_row_map32(&ma, A, rows))) return rc;
     const size_t smem = (size_t)WgSmem::ops + (size_t)2 * nsi * OP_BYTES;
     float* partials = static_cast<float*>(ws);
     if (ns == 3) {
@@ -287,7 +302,7 @@ int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, i
         tc_wgrad_kernel<1><<<grid, WG_THREADS, smem, stream>>>(mx, ma, n_tiles, partials);
     }
     CGNN_LAUNCH_CHECK();
-    wgrad_reduce_kernel<<<(128 * 129 + 255) / 256, 256, 0, stream>>>(partials, grid, dW, ld, col0, db, accumulate,
+    wgrad_reduce_kernel<<<(128 * 129 + 63) / 64, 256, 0, stream>>>(partials, grid, dW, ld, col0, db, accumulate,
                                                                      nrows > 0 ? nrows : 128, ncols > 0 ? ncols : 128);
     CGNN_LAUNCH_CHECK();
     return CGNN_OK;
