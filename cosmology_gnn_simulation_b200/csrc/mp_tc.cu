@@ -70,8 +70,9 @@ struct TcParams {
     float* ln_partials;         // [gridDim.x * 8][2][128]: per-warp column sums of dU * xhat and dU
     float* out;                 // [n_rows][128]
     int n_ring;                 // input ring depth
-    const uint8_t* w_images;    // [n_blocks][NSI][2 halves][WIMG]
-    const float* vec;           // [5][128]: bias of layer 1, 2, 3, gamma, beta
+    ChainBlock blk[MAX_BLOCKS]; // weight blocks in FP32 (torch layout): every CTA builds its BF16 images in shared memory itself
+    const float* vec_src[5];    // bias of layer 1, 2, 3, gamma, beta (nullable -> zeros / ones for gamma)
+    int vec_len[5];             // valid entries (zero padded to 128)
     unsigned long long* stamps; // debug (cgnn_debug_stamps): clock64 of CTA 0's groups, [2][stamp_tiles][16] (nullable)
     int stamp_tiles;
 };
@@ -94,7 +95,6 @@ __host__ __device__ constexpr uint32_t ring_offset(int n_blocks, int nsi) {
 }
 
 struct Bars {
-    uint64_t w_full;
     // "full" barriers are per consumer group: a group only ever waits on barriers whose uses are all its own,
     // so the phase parity it tracks can never alias a phase that belongs to the other group's tiles
     uint64_t in_full[2][MAXRING], in_empty[MAXRING];
@@ -200,7 +200,6 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 
     // ---- one-time setup ---------------------------------------------------------------------------
     if (tid == 0) {
-        mbar_init(&bars->w_full, 1);
         for (int i = 0; i < MAXRING; ++i) {
             mbar_init(&bars->in_full[0][i], 1);
             mbar_init(&bars->in_full[1][i], 1);
@@ -209,7 +208,40 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
         for (int s = 0; s < 2; ++s) { mbar_init(&bars->a_ready[s], 8); mbar_init(&bars->mma_done[s], 1); }
         fence_mbar_init();
     }
-    for (int i = tid; i < 5 * TC_H; i += TC_THREADS) sVec[i] = p.vec[i];
+    for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
+        const int v = i / TC_H, c = i % TC_H;
+        sVec[i] = (p.vec_src[v] != nullptr && c < p.vec_len[v]) ? __ldg(p.vec_src[v] + c) : (v == 3 ? 1.0f : 0.0f);
+    }
+    // This CTA's half (64 output rows) of every weight block as K-major BF16 image(s):  B[n][k] = W[(row0 + n) * ld + col0 + k]
+    // (transposed: W[(row0 + k) * ld + col0 + n]), element (n, k) at (n / 8) * 2048 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2.
+    // 16-byte pieces (n, k8); 14 MB of L2 reads per launch instead of a separate preparation kernel.
+    for (int piece = tid; piece < n_blocks * 64 * (TC_H / 8); piece += TC_THREADS) {
+        const int b = piece / (64 * (TC_H / 8)), rem = piece % (64 * (TC_H / 8));
+        const int nl = rem / (TC_H / 8), k8 = rem % (TC_H / 8);
+        const int n = (int)rank * 64 + nl;
+        const ChainBlock& B = p.blk[b];
+        const int nmax = B.nmax ? B.nmax : TC_H, kmax = B.kmax ? B.kmax : TC_H;
+        float x[8];
+        if (!B.transpose && n < nmax && k8 * 8 + 8 <= kmax && ((B.ld | B.col0) & 3) == 0) {
+            const float4* src = reinterpret_cast<const float4*>(B.W + (size_t)(B.row0 + n) * B.ld + B.col0 + k8 * 8);
+            const float4 u0 = __ldg(src), u1 = __ldg(src + 1);
+            x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w; x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k8 * 8 + j;
+                const bool ok = n < nmax && k < kmax;
+                x[j] = !ok ? 0.0f : B.transpose ? __ldg(B.W + (size_t)(B.row0 + k) * B.ld + B.col0 + n) : __ldg(B.W + (size_t)(B.row0 + n) * B.ld + B.col0 + k);
+            }
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+        const uint32_t off = (uint32_t)((nl >> 3) * (TC_H * 16) + k8 * 128 + (nl & 7) * 16);
+        *reinterpret_cast<uint4*>(sW + (b * NSI) * WIMG + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (NS == 3) *reinterpret_cast<uint4*>(sW + (b * NSI + 1) * WIMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    fence_proxy_async_smem();                                // the MMAs (async proxy, both CTAs of the pair) read these images
     if (LNB)
         for (int i = tid; i < 8 * 2 * TC_H; i += TC_THREADS) reinterpret_cast<float*>(smem + Smem::lnacc)[i] = 0.0f;
     if (warp == 9) tmem_alloc<2>(&bars->tmem_base, 512);
@@ -228,10 +260,6 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     if (warp == 8) {
         // ============================ producer: weights, input chunks ============================================
         if (lane == 0) {
-            mbar_expect_tx(&bars->w_full, (uint32_t)(n_blocks * NSI * WIMG));
-            for (int b = 0; b < n_blocks; ++b)
-                for (int sp = 0; sp < NSI; ++sp)
-                    bulk_g2s(sW + (b * NSI + sp) * WIMG, p.w_images + ((size_t)(b * NSI + sp) * 2 + rank) * WIMG, WIMG, &bars->w_full);
             uint32_t seq = 0;
             for (int64_t it = 0; it < n_it; ++it) {
                 const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
@@ -248,7 +276,6 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     } else if (warp == 9) {
         // ============================ MMA issuer (leader CTA, one thread) =======================================
         if (rank == 0 && lane == 0) {
-            mbar_wait_or_trap(&bars->w_full, 0, 120);
             const uint32_t idesc = umma_idesc_bf16(256, TC_H);
             const uint32_t w_base = smem_u32(sW);
             int64_t it_s[2] = {0, 1};
@@ -309,7 +336,6 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
         uint32_t pm = 0;                                // parity of mma_done[g]
         uint32_t in_par = 0;                            // bit b: parity of this group's next use of in_full[g][b]
         const int k = p.k;
-        mbar_wait_or_trap(&bars->w_full, 0, 130);       // a_ready from this CTA also tells the leader its weights landed
         const bool stamping = p.stamps != nullptr && blockIdx.x == 0 && gt == 0;
 #define CGNN_STAMP(slot)                                                                               \
     do {                                                                                               \
@@ -324,16 +350,6 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             const int64_t recv = grow >> p.kshift;
             const size_t rowoff = (size_t)grow * TC_H, recvoff = (size_t)recv * TC_H;
             CGNN_STAMP(0);
-            // the per-row HBM streams of this tile's epilogues start their way into L2 now
-            {
-                const float* streams[5] = {p.hid_mask[0], p.hid_mask[1], LNB ? p.du_rows : p.mask_src, LNB ? nullptr : p.residual, nullptr};
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (streams[i] != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(streams[i] + rowoff + 32 * j));
-                    }
-            }
             // ---- input phases: stream chunks, split, write the A operand -------------------------------------
             for (int ip = 0; ip < p.n_in; ++ip) {
                 if (ip > 0) {                            // A is still being read by the previous phase's MMA
@@ -488,24 +504,31 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             s2 = fmaf(d, d, s2);
                         }
                         if (lnb) {
+                            // dU of this chunk; stashed in the A-operand columns of this TMEM slot (free once the last MMA is done)
+                            // for the output pass, so the dU streams are read from global memory only once
+                            float du[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) du[j] = valid ? (pa ? ca[j] : 0.0f) + (pb ? cb[j] : 0.0f) : 0.0f;
+                            tmem_st_32x32b_x16(tAhi + cc, reinterpret_cast<const uint32_t*>(du));
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
                                 const float4 gmv = *reinterpret_cast<const float4*>(gamma + cc + j);
                                 const float gmj[4] = {gmv.x, gmv.y, gmv.z, gmv.w};
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
-                                    const float t = ((pa ? ca[j + u] : 0.0f) + (pb ? cb[j + u] : 0.0f)) * gmj[u];
+                                    const float t = du[j + u] * gmj[u];
                                     g1 += t;
                                     g2 = fmaf(t, v[j + u] - y0, g2);
                                 }
                             }
-                            // next chunks of dU; the pass ends by re-loading chunks 0 and 1 for the output pass (L2 hits)
-                            const int nc = (cc + 64) & (TC_H - 1);
-                            if (pa) ld16(pa + nc, ca);
-                            if (pb) ld16(pb + nc, cb);
+                            if (cc + 64 < TC_H) {
+                                if (pa) ld16(pa + cc + 64, ca);
+                                if (pb) ld16(pb + cc + 64, cb);
+                            }
                         }
                     }
                 }
+                if (lnb) tmem_st_wait();
                 const float m1 = s1 * (1.0f / TC_H);
                 mean = y0 + m1;
                 const float var = fmaxf(s2 * (1.0f / TC_H) - m1 * m1, 0.0f);
@@ -549,8 +572,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         } else if (lnb) {
                             // dY = rstd (g - mean(g) - xhat mean(g xhat));  column sums of dU xhat (d gamma) and dU (d beta)
                             float du[16], dgx[16];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) du[j] = valid ? (pa ? ca[j] : 0.0f) + (pb ? cb[j] : 0.0f) : 0.0f;
+                            tmem_ld_32x32b_x16(tAhi + cc, du);
+                            tmem_ld_wait16(du);
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
                                 const float4 gmv = *reinterpret_cast<const float4*>(gamma + cc + j);
@@ -589,7 +612,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             receiver_sum16(v, k, lane);
                             if (valid) receiver_store16(aggp, cc, v, k, lane);
                         }
-                        if (cc + 64 < TC_H) {
+                        if (!lnb && cc + 64 < TC_H) {
                             if (pa) ld16(pa + cc + 64, ca);
                             if (pb) ld16(pb + cc + 64, cb);
                         }
@@ -612,46 +635,6 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     __syncthreads();
     cluster_sync_all();
     if (warp == 9) tmem_dealloc<2>(tmem, 512);
-}
-
-// Builds the shared-memory weight images of a chain: for block b the K-major BF16 image(s) of the 128 x 128
-// matrix B[n][k] = W[(row0 + n) * ld + col0 + k]  (or, transposed, W[(row0 + k) * ld + col0 + n]),
-// split by output row n into two halves of 64 rows (one per CTA of the pair).
-struct PrepArgs {
-    ChainBlock blk[MAX_BLOCKS];
-    int n_blocks;
-    const float* vec_src[5];      // bias1, bias2, bias3, gamma, beta (nullable -> zeros / ones for gamma)
-    int vec_len[5];               // valid entries (zero padded to 128)
-};
-
-template <int NS>
-__global__ void tc_prep_kernel(PrepArgs a, uint8_t* __restrict__ images, float* __restrict__ vec) {
-    constexpr int NSI = NS == 3 ? 2 : 1;
-    const int b = blockIdx.y;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte piece: (n, k8)
-    if (b < a.n_blocks && idx < TC_H * (TC_H / 8)) {
-        const int n = idx / (TC_H / 8), k8 = idx % (TC_H / 8);
-        const ChainBlock& B = a.blk[b];
-        float x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = k8 * 8 + j;
-            const bool valid = n < (B.nmax ? B.nmax : TC_H) && k < (B.kmax ? B.kmax : TC_H);
-            x[j] = !valid ? 0.0f : B.transpose ? B.W[(size_t)(B.row0 + k) * B.ld + B.col0 + n] : B.W[(size_t)(B.row0 + n) * B.ld + B.col0 + k];
-        }
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
-        const int half = n >> 6, nl = n & 63;
-        const size_t off = (size_t)(nl >> 3) * (TC_H * 16) + (size_t)k8 * 128 + (nl & 7) * 16;
-        *reinterpret_cast<uint4*>(images + ((size_t)(b * NSI + 0) * 2 + half) * WIMG + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (NS == 3)
-            *reinterpret_cast<uint4*>(images + ((size_t)(b * NSI + 1) * 2 + half) * WIMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-    if (b == 0 && idx < 5 * TC_H) {
-        const int v = idx / TC_H, c = idx % TC_H;
-        vec[idx] = (a.vec_src[v] && c < a.vec_len[v]) ? a.vec_src[v][c] : (v == 3 ? 1.0f : 0.0f);
-    }
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
@@ -686,7 +669,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     const int n_in = op.in1 ? 2 : 1;
     const int n_blocks = n_in + op.n_layers - 1;
     CGNN_CHECK_ARG(op.n_layers == 1 || op.n_layers == 3, "tensor-core chain: 1 or 3 layers");
-    CGNN_CHECK_ARG(n_blocks <= MAX_BLOCKS && op.rows >= 1 && op.in0 && op.out && op.images && op.vec, "tensor-core chain: bad arguments");
+    CGNN_CHECK_ARG(n_blocks <= MAX_BLOCKS && op.rows >= 1 && op.in0 && op.out, "tensor-core chain: bad arguments");
     const bool gather = op.Ps != nullptr;
     const bool uses_k = gather || op.agg_out || op.du_recv || op.hid_agg[0] || op.hid_agg[1];
     int k = 1, kshift = 0;
@@ -701,22 +684,6 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     } else if (gather && op.n_layers == 1) {
         CGNN_CHECK_ARG(!op.mask_src && !op.residual, "tensor-core chain: a one-layer gather chain takes no mask / residual");
     }
-    if (!op.prepared) {
-        PrepArgs pa{};
-        pa.n_blocks = n_blocks;
-        for (int b = 0; b < n_blocks; ++b) pa.blk[b] = op.blk[b];
-        if (op.n_layers == 1) {
-            pa.vec_src[0] = op.bias[0];
-        } else {
-            pa.vec_src[0] = op.bias[0]; pa.vec_src[1] = op.bias[1]; pa.vec_src[2] = op.bias[2];
-        }
-        pa.vec_src[3] = op.gamma; pa.vec_src[4] = op.beta;
-        for (int v = 0; v < 5; ++v) pa.vec_len[v] = TC_H;
-        if (op.out_valid > 0) pa.vec_len[op.n_layers - 1] = op.out_valid;       // bias of a narrow last layer
-        dim3 pg((TC_H * (TC_H / 8) + 255) / 256, n_blocks);
-        tc_prep_kernel<NS><<<pg, 256, 0, stream>>>(pa, op.images, op.vec);
-        CGNN_LAUNCH_CHECK();
-    }
     TcParams p{};
     p.n_rows = op.rows; p.n_pair_tiles = (op.rows + 255) / 256;
     p.n_in = n_in; p.n_layers = op.n_layers; p.k = k; p.kshift = kshift;
@@ -726,7 +693,15 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     for (int l = 0; l < 2; ++l) { p.hid_mask[l] = op.hid_mask[l]; p.hid_out[l] = op.hid_out[l]; p.hid_agg[l] = op.hid_agg[l]; }
     p.du_rows = op.du_rows; p.du_recv = op.du_recv; p.ln_partials = static_cast<float*>(op.ln_ws);
     p.out = op.out;
-    p.w_images = op.images; p.vec = op.vec;
+    for (int b = 0; b < n_blocks; ++b) p.blk[b] = op.blk[b];
+    if (op.n_layers == 1) {
+        p.vec_src[0] = op.bias[0];
+    } else {
+        p.vec_src[0] = op.bias[0]; p.vec_src[1] = op.bias[1]; p.vec_src[2] = op.bias[2];
+    }
+    p.vec_src[3] = op.gamma; p.vec_src[4] = op.beta;
+    for (int v = 0; v < 5; ++v) p.vec_len[v] = TC_H;
+    if (op.out_valid > 0) p.vec_len[op.n_layers - 1] = op.out_valid;       // bias of a narrow last layer
     if (g_stamps != nullptr && g_stamp_next < g_stamp_launches) {
         p.stamps = g_stamps + (size_t)(g_stamp_next++) * 2 * g_stamp_tiles * 16;
         p.stamp_tiles = g_stamp_tiles;

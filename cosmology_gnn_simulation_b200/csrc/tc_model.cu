@@ -219,15 +219,21 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// 0: one-layer chains everywhere (each runs at the HBM rate) with the LayerNorm backward fused into the Y chain;
-// 1: the two fused 3-layer chains of fused_backward (fewer row-stream passes, but bound by the per-tile latency chain)
-static int bwd_mode() {
-    static int mode = -1;
-    if (mode < 0) {
+// How one MLP's backward over `rows` rows is composed:
+//   0  one-layer chains (each runs at the HBM rate) with the LayerNorm backward fused into the Y chain -- the choice for
+//      long row streams (edges), where the fused chains' serial per-tile latency costs more than the row-stream passes they save;
+//   1  the two fused 3-layer chains of fused_backward -- the choice when every epilogue group has at most one tile (node-sized
+//      streams): nothing pipelines across tiles there, so the per-tile latency is paid either way and 2 launches replace 6.
+// CGNN_BWD_FUSED=0/1 forces one of them (measurements).
+static int bwd_mode(int64_t rows) {
+    static int forced = -2;
+    if (forced == -2) {
         const char* e = getenv("CGNN_BWD_FUSED");
-        mode = e ? atoi(e) : 0;
+        forced = e ? atoi(e) : -1;
     }
-    return mode;
+    if (forced >= 0) return forced;
+    const int64_t pair_tiles = (rows + 255) / 256, clusters = num_sms() / 2;
+    return pair_tiles <= 2 * clusters ? 1 : 0;
 }
 
 // Backward of one 3-layer MLP (+ LayerNorm) over a row range as TWO fused chains plus the weight gradients:
@@ -245,7 +251,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
                           int accumulate, cudaStream_t s) {
     int rc;
     const int n_in = r.in1 ? 2 : 1;
-    if (bwd_mode() == 0) {
+    if (bwd_mode(rows) == 0) {
         // A1 = relu(layer 1), A2 = relu(A1 W2^T + b2)
         r.ns = ns; r.rows = rows; r.n_layers = 1; r.images = sc.images; r.vec = sc.vec;
         r.relu_out = 1; r.out = A1;
