@@ -349,6 +349,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             const int64_t grow = valid ? row0 + r : p.n_rows - 1;           // clamped: loads of padded rows stay in bounds
             const int64_t recv = grow >> p.kshift;
             const size_t rowoff = (size_t)grow * TC_H, recvoff = (size_t)recv * TC_H;
+            // the sender index is fetched now so that the address of the gathered P_s row is ready when its epilogue starts
+            const int32_t snd = p.gather ? __ldg(p.senders + grow) : 0;
             CGNN_STAMP(0);
             // ---- input phases: stream chunks, split, write the A operand -------------------------------------
             for (int ip = 0; ip < p.n_in; ++ip) {
@@ -385,7 +387,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             for (int l = 0; l + 1 < N_LAYERS; ++l) {
                 const bool gather = p.gather && l == 0;
                 // row streams of this layer, thread = row: a = P_s[sender] | mask source, b = P_r[receiver]
-                const float* pa = !HS ? nullptr : gather ? p.Ps + (size_t)__ldg(p.senders + grow) * TC_H : (p.hid_mask[l] ? p.hid_mask[l] + rowoff : nullptr);
+                const float* pa = !HS ? nullptr : gather ? p.Ps + (size_t)snd * TC_H : (p.hid_mask[l] ? p.hid_mask[l] + rowoff : nullptr);
                 const float* pb = HS && gather ? p.Pr + recvoff : nullptr;
                 const bool masked = !gather && pa != nullptr;
                 float* hout = p.hid_out[l] ? p.hid_out[l] + rowoff : nullptr;
@@ -454,7 +456,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             constexpr bool lnb = LNB;
             // row streams, thread = row:  a = P_s[sender] | dU rows | mask source,  b = P_r[receiver] | dU per receiver | residual
             const float* pa = !SA     ? nullptr
-                              : fgather ? p.Ps + (size_t)__ldg(p.senders + grow) * TC_H
+                              : fgather ? p.Ps + (size_t)snd * TC_H
                               : lnb   ? (p.du_rows ? p.du_rows + rowoff : nullptr)
                                       : (p.mask_src ? p.mask_src + rowoff : nullptr);
             const float* pb = !SB     ? nullptr
