@@ -819,8 +819,6 @@ void set_debug_stamps(unsigned long long* buf, int tiles, int launches) {
     g_stamps = buf; g_stamp_tiles = tiles; g_stamp_launches = launches; g_stamp_next = 0;
 }
 
-int64_t chain_image_bytes() { return (int64_t)MAX_BLOCKS * 2 * 2 * WIMG; }
-int64_t chain_vec_bytes() { return align_up(5 * TC_H * 4, 256); }
 int run_chain(const ChainOp& op, cudaStream_t stream) {
     return op.ns == 3 ? run_chain_t<3>(op, stream) : run_chain_t<1>(op, stream);
 }

@@ -58,16 +58,12 @@ struct ChainOp {
     const float* residual;        // result += residual                   (nullable)
     float* agg_out;               // [rows / k][128] = per-receiver sum of the result before the residual (nullable)
     float* out;                   // [rows][128]
-    uint8_t* images; float* vec;  // workspace (chain_image_bytes(), chain_vec_bytes())
-    int prepared;                 // images / vec already hold this chain's weight images (skip the prep launch)
     // hidden layers of a 3-layer chain (index 0, 1): mask instead of ReLU, extra output, per-receiver sum of the activation
     const float* hid_mask[2]; float* hid_out[2]; float* hid_agg[2];
     // LayerNorm backward instead of forward after the last layer: out = dY of (Y, dU), dU = du_rows[row] + du_recv[row / k];
     // d gamma / d beta (=|+=) their column sums (fixed-order reduction through ln_ws, ln_bwd_workspace_bytes())
     int ln_bwd; const float* du_rows; const float* du_recv; float* dgamma; float* dbeta; int accumulate; void* ln_ws;
 };
-int64_t chain_image_bytes();
-int64_t chain_vec_bytes();
 int run_chain(const ChainOp& op, cudaStream_t stream);
 
 // dW[n][col0 + c] (=|+=) sum_rows X[row][n] * A[row][c];  db[n] (=|+=) sum_rows X[row][n]   (deterministic)

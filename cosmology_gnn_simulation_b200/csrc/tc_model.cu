@@ -29,19 +29,17 @@ bool tc_shape_ok(const MlpDev& m, int in_mult) {
 int64_t rows_bytes(int64_t rows) { return align_up(rows * TC_H * 4, 256); }
 
 struct Scratch {
-    uint8_t* images; float* vec; void* wg; void* lnb;
+    void* wg; void* lnb;
     void carve(Carver& cv) {
-        images = cv.take<uint8_t>(chain_image_bytes());
-        vec = cv.take<float>(chain_vec_bytes() / 4);
         wg = cv.take<uint8_t>(wgrad_workspace_bytes());
         lnb = cv.take<uint8_t>(ln_bwd_workspace_bytes());
     }
-    static int64_t bytes() { return chain_image_bytes() + chain_vec_bytes() + wgrad_workspace_bytes() + ln_bwd_workspace_bytes(); }
+    static int64_t bytes() { return wgrad_workspace_bytes() + ln_bwd_workspace_bytes(); }
 };
 
 ChainOp base_op(int ns, const Scratch& sc, int64_t rows) {
     ChainOp op{};
-    op.ns = ns; op.rows = rows; op.n_layers = 1; op.images = sc.images; op.vec = sc.vec;
+    op.ns = ns; op.rows = rows; op.n_layers = 1;
     return op;
 }
 
@@ -253,7 +251,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
     const int n_in = r.in1 ? 2 : 1;
     if (bwd_mode(rows) == 0) {
         // A1 = relu(layer 1), A2 = relu(A1 W2^T + b2)
-        r.ns = ns; r.rows = rows; r.n_layers = 1; r.images = sc.images; r.vec = sc.vec;
+        r.ns = ns; r.rows = rows; r.n_layers = 1;
         r.relu_out = 1; r.out = A1;
         if ((rc = run_chain(r, s))) return rc;
         {
@@ -289,7 +287,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
         }
         return CGNN_OK;
     }
-    r.ns = ns; r.rows = rows; r.n_layers = 3; r.images = sc.images; r.vec = sc.vec;
+    r.ns = ns; r.rows = rows; r.n_layers = 3;
     r.blk[n_in] = {m.W[1], TC_H, 0, 0, 0};
     r.blk[n_in + 1] = {m.W[2], TC_H, 0, 0, 0, m.out_dim, 0};
     r.bias[1] = m.b[1]; r.bias[2] = m.b[2];

@@ -33,8 +33,10 @@ def extend_positions_torch(positions, box_size):
 
 
 def _wrap_displacement_(disp, box_size):
-    disp[disp < -1 * box_size / 2] += box_size
-    disp[disp > box_size / 2] -= box_size
+    # the reference's two masked in-place updates (data_utils.py:44-45, 104-105), as selects: same values, but no
+    # boolean-mask indexing (which synchronises with the host to size its result)
+    disp = torch.where(disp < -1 * box_size / 2, disp + box_size, disp)
+    disp = torch.where(disp > box_size / 2, disp - box_size, disp)
     return disp
 
 

@@ -81,11 +81,24 @@ class _Plan:
         self.dec_acc, self.dec_temp = dec_acc, dec_temp
         self.groups = groups                  # [(MlpParams, first index into the flat parameter list)]
         self.edge_ckpt_every = edge_ckpt_every
+        self.grad_enabled = torch.is_grad_enabled()      # sampled where the module is called (autograd runs Function.forward in no-grad mode)
+
+
+_STREAM_PLANS = {}
 
 
 def _edge_stream_plan(n_steps: int, bytes_per_copy: int, device) -> int:
     """Checkpoint spacing s for the edge latent stream in message="edge" training: keep e^t for
-    t % s == 0 and recompute the rest segment by segment in backward."""
+    t % s == 0 and recompute the rest segment by segment in backward.  Decided once per (steps, stream size,
+    device): cudaMemGetInfo costs ~15 ms of host time per call, far too much for every step."""
+    key = (n_steps, bytes_per_copy, str(device))
+    s = _STREAM_PLANS.get(key)
+    if s is None:
+        s = _STREAM_PLANS[key] = _edge_stream_plan_uncached(n_steps, bytes_per_copy, device)
+    return s
+
+
+def _edge_stream_plan_uncached(n_steps: int, bytes_per_copy: int, device) -> int:
     free, _ = torch.cuda.mem_get_info(device)
     budget = int(free * 0.6)
     for s in range(1, n_steps + 1):
@@ -105,7 +118,8 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         p, M, k, prec = plan, plan.n_steps, plan.k, plan.precision
         n, L = x.shape[0], plan.enc_node.out_dim
         e_count = edge_attr.shape[0]
-        train = any(ctx.needs_input_grad[3:])
+        # (needs_input_grad reflects requires_grad only: under torch.no_grad() nothing will be differentiated)
+        train = plan.grad_enabled and any(ctx.needs_input_grad[3:])
         edge_mode = p.message == "edge"
 
         halo = p.halo

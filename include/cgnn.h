@@ -60,7 +60,7 @@ typedef enum {
     CGNN_PREC_BF16X3 = 1,      /* tcgen05 tensor cores, bf16 hi/lo split operands (3 MMAs), FP32 accum/storage */
     CGNN_PREC_BF16 = 2         /* tcgen05, single bf16 pass (fastest; ~1e-2, outside the parity bar) */
     /* The tensor-core modes cover the processor phases (cgnn_mp_edge_* / cgnn_mp_node_*) for
-     * latent = hidden = 128 with 2 hidden layers and k dividing 128; other shapes return
+     * latent = hidden = 128 with 2 hidden layers and k a power of two <= 32; other shapes return
      * CGNN_ERR_UNSUPPORTED.  The row-wise encoder / decoder entry points use the tensor cores for 3-layer
      * MLPs with hidden = 128 and in, out <= 128 (zero padded), and run their FP32 kernels for any other
      * shape or when an input gradient narrower than 128 columns is requested. */
