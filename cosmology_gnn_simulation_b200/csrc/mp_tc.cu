@@ -27,6 +27,8 @@
 //     the number of live values at each step (15 shuffles per 16 columns at k = 16), fixed order, deterministic.
 //
 // Reference semantics: InteractionNetwork.forward + residuals, graph_network.py:83-101,177-183, and its autograd.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace cgnn {
@@ -84,14 +86,14 @@ int g_stamp_tiles = 0, g_stamp_launches = 0, g_stamp_next = 0;
 // shared-memory layout (dynamic, 1024-byte aligned base)
 struct Smem {
     static constexpr int vec = 0;                                  // 5 * 128 floats
-    static constexpr int lnacc = vec + 5 * TC_H * 4;               // 8 warps * 2 * 128 floats (LayerNorm backward column sums)
-    static constexpr int bars = lnacc + 8 * 2 * TC_H * 4;          // barriers (512 bytes)
-    static constexpr int weights = bars + 512;                     // n_blocks * NSI * WIMG
+    static constexpr int bars = vec + 5 * TC_H * 4;                // barriers (512 bytes)
+    static constexpr int lnacc = bars + 512;                       // LayerNorm-backward variants only: 8 warps * 2 * 128 floats (column sums)
+    __host__ __device__ static constexpr int weights(bool lnb) { return lnacc + (lnb ? 8 * 2 * TC_H * 4 : 0); }   // n_blocks * NSI * WIMG
     // then (1024-aligned) n_ring * CW_BYTES input ring
 };
-static_assert(Smem::weights % 128 == 0, "weight images need 128-byte alignment");
-__host__ __device__ constexpr uint32_t ring_offset(int n_blocks, int nsi) {
-    return (uint32_t)((Smem::weights + n_blocks * nsi * WIMG + 1023) / 1024 * 1024);
+static_assert(Smem::weights(false) % 128 == 0 && Smem::weights(true) % 128 == 0, "weight images need 128-byte alignment");
+__host__ __device__ constexpr uint32_t ring_offset(int n_blocks, int nsi, bool lnb) {
+    return (uint32_t)((Smem::weights(lnb) + n_blocks * nsi * WIMG + 1023) / 1024 * 1024);
 }
 
 struct Bars {
@@ -175,13 +177,15 @@ __device__ __forceinline__ void receiver_store16(float* dst, int c, const float*
 // CFG: compile-time shape of the chain, so that every instantiation carries only the code and the registers (row-stream
 // buffers) it uses: C_L3 three layers (else one), C_LN / C_LNB LayerNorm forward / backward after the last layer,
 // C_SA / C_SB the final epilogue reads row stream a (P_s | dU rows | mask source) / b (P_r | dU per receiver |
-// residual), C_HS the hidden epilogues read row streams (gather or mask sources), C_AGG per-receiver sums.
-constexpr int C_L3 = 1, C_LN = 2, C_LNB = 4, C_SA = 8, C_SB = 16, C_HS = 32, C_AGG = 64;
+// residual), C_HS the hidden epilogues read row streams (gather or mask sources), C_AGG per-receiver sums, C_RIN the
+// residual is the chain's own input: its tile stays in the input ring until the output pass instead of being re-read.
+constexpr int C_L3 = 1, C_LN = 2, C_LNB = 4, C_SA = 8, C_SB = 16, C_HS = 32, C_AGG = 64, C_RIN = 128;
 template <int NS, int CFG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1, const TcParams p) {
     constexpr int NSI = NS == 3 ? 2 : 1;                    // weight / activation images per value (hi [, lo])
     constexpr bool L3 = (CFG & C_L3) != 0, SA = (CFG & C_SA) != 0, SB = (CFG & C_SB) != 0, HS = (CFG & C_HS) != 0, AGG = (CFG & C_AGG) != 0;
+    constexpr bool RIN = (CFG & C_RIN) != 0;
     constexpr int LN = (CFG & C_LNB) ? 2 : ((CFG & C_LN) ? 1 : 0);
     constexpr bool LNB = LN == 2;
     constexpr int N_LAYERS = L3 ? 3 : 1;
@@ -189,8 +193,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     Bars* bars = reinterpret_cast<Bars*>(smem + Smem::bars);
     float* sVec = reinterpret_cast<float*>(smem + Smem::vec);
     const int n_blocks = p.n_in + N_LAYERS - 1;             // MMA phases per tile
-    uint8_t* sW = smem + Smem::weights;
-    uint8_t* sRing = smem + ring_offset(n_blocks, NSI);
+    uint8_t* sW = smem + Smem::weights(LNB);
+    uint8_t* sRing = smem + ring_offset(n_blocks, NSI, LNB);
     const int NRING = p.n_ring;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -345,6 +349,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
         for (int64_t it = g; it < n_it; it += 2) {
             const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
             uint32_t seq = (uint32_t)it * (uint32_t)(NCW * p.n_in);
+            const uint32_t rin_seq0 = seq;          // RIN: ring position of this tile's first input chunk
             const bool valid = row0 + r < p.n_rows;
             const int64_t grow = valid ? row0 + r : p.n_rows - 1;           // clamped: loads of padded rows stay in bounds
             const int64_t recv = grow >> p.kshift;
@@ -371,8 +376,10 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         split2(v.x, v.y, hi[2 * j], lo[2 * j]);
                         split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
+                    if (!(RIN && ip == 0)) {             // (RIN: the chunk is released by the output pass, which reads it as the residual)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
+                    }
                     tmem_st_32x32b_x16(tAhi + q * 16, hi);
                     if (NS == 3) tmem_st_32x32b_x16(tAlo + q * 16, lo);
                 }
@@ -459,7 +466,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                               : fgather ? p.Ps + (size_t)snd * TC_H
                               : lnb   ? (p.du_rows ? p.du_rows + rowoff : nullptr)
                                       : (p.mask_src ? p.mask_src + rowoff : nullptr);
-            const float* pb = !SB     ? nullptr
+            const float* pb = !SB || RIN ? nullptr
                               : fgather ? p.Pr + recvoff
                               : lnb   ? (p.du_recv ? p.du_recv + recvoff : nullptr)
                                       : (p.residual ? p.residual + rowoff : nullptr);
@@ -602,7 +609,19 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = ca[j] > 0.0f ? v[j] : 0.0f;
                         }
-                        if (!fgather && !lnb && pb) {
+                        if (RIN) {
+                            // residual = this tile's input, still in its ring slots (this thread's own row, swizzled)
+                            const uint32_t rbuf = (rin_seq0 + (uint32_t)(cc >> 5)) % NRING;
+                            const uint8_t* src = sRing + rbuf * CW_BYTES;
+                            float o[16];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 e4 = *reinterpret_cast<const float4*>(src + swz128(r, ((cc & 31) >> 2) + j));
+                                o[4 * j] = v[4 * j] + e4.x; o[4 * j + 1] = v[4 * j + 1] + e4.y;
+                                o[4 * j + 2] = v[4 * j + 2] + e4.z; o[4 * j + 3] = v[4 * j + 3] + e4.w;
+                            }
+                            if (valid) st16(outp + cc, o);
+                        } else if (!fgather && !lnb && pb) {
                             // residual: the sum goes out from the stream's own registers, v stays free for the per-receiver sum
 #pragma unroll
                             for (int j = 0; j < 16; ++j) cb[j] += v[j];
@@ -620,6 +639,11 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         }
                     }
                 }
+            }
+            if (RIN) {                                   // the tile's input slots go back to the producer
+                __syncwarp();
+                if (lane == 0)
+                    for (int q = 0; q < NCW; ++q) mbar_arrive_local(&bars->in_empty[(rin_seq0 + (uint32_t)q) % NRING]);
             }
             CGNN_STAMP(13);
             // D and A of this slot are free again: the next tile of this group starts with its input phase
@@ -713,7 +737,11 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     if ((rc = make_row_map32(&m0, op.in0, op.rows))) return rc;
     if ((rc = make_row_map32(&m1, op.in1 ? op.in1 : op.in0, op.rows))) return rc;
     // the shared memory the weights leave goes to the input ring
-    const size_t ring_off = ring_offset(n_blocks, NSI);
+    const size_t ring_off = ring_offset(n_blocks, NSI, op.ln_bwd != 0);
+    // the residual is the chain's own (first) input and the ring can hold both groups' tiles: no re-read
+    static const bool rin_allowed = getenv("CGNN_NO_RIN") == nullptr;       // measurements: force the re-read path
+    const bool rin = rin_allowed && !op.ln_bwd && op.residual != nullptr && op.residual == op.in0 && !(gather && op.n_layers == 1) &&
+                     ring_off + (size_t)(2 * NCW * n_in) * CW_BYTES <= SMEM_MAX;
     CGNN_CHECK_ARG(ring_off + 2 * CW_BYTES <= SMEM_MAX, "tensor-core chain: shared memory need %zu exceeds 227 KB", ring_off + 2 * CW_BYTES);
     p.n_ring = (int)((SMEM_MAX - ring_off) / CW_BYTES);
     if (p.n_ring > MAXRING) p.n_ring = MAXRING;
@@ -724,7 +752,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     const bool fin_b = (gather && op.n_layers == 1) || (op.ln_bwd ? op.du_recv != nullptr : op.residual != nullptr);
     const bool any_agg = op.agg_out || op.hid_agg[0] || op.hid_agg[1];
     const int cfg = (op.n_layers == 3 ? C_L3 : 0) | (op.ln_bwd ? C_LNB : (op.gamma ? C_LN : 0)) | (fin_a ? C_SA : 0) | (fin_b ? C_SB : 0) |
-                    (any_hidden ? C_HS : 0) | (any_agg ? C_AGG : 0);
+                    (any_hidden ? C_HS : 0) | (any_agg ? C_AGG : 0) | (rin ? C_RIN : 0);
     void (*kern)(CUtensorMap, CUtensorMap, TcParams) = nullptr;
     int slot = -1;
 #define CGNN_CHAIN_CFG(i, c) else if (cfg == (c)) { kern = tc_chain_fwd<NS, (c)>; slot = (i); }
@@ -739,6 +767,9 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     CGNN_CHAIN_CFG(7, C_L3 | C_LN | C_SB)                             // node phase forward
     CGNN_CHAIN_CFG(8, C_L3 | C_LN | C_SB | C_HS)                      // edge phase forward without the per-receiver sum
     CGNN_CHAIN_CFG(9, C_L3 | C_LN | C_SB | C_HS | C_AGG)              // edge phase forward
+    CGNN_CHAIN_CFG(21, C_L3 | C_LN | C_SB | C_HS | C_AGG | C_RIN)     // edge phase forward, residual from the input ring
+    CGNN_CHAIN_CFG(22, C_L3 | C_LN | C_SB | C_HS | C_RIN)
+    CGNN_CHAIN_CFG(23, C_L3 | C_LN | C_SB | C_RIN)                    // node phase forward, residual from the input ring
     CGNN_CHAIN_CFG(10, C_L3 | C_LNB | C_SA | C_SB | C_HS)             // edge backward, recompute + LayerNorm backward
     CGNN_CHAIN_CFG(11, C_L3 | C_LNB | C_SA)                           // node backward, recompute + LayerNorm backward
     CGNN_CHAIN_CFG(12, C_L3 | C_SB | C_HS | C_AGG)                    // edge backward, dgrad chain
