@@ -264,16 +264,16 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     if (warp == 8) {
         // ============================ producer: weights, input chunks ============================================
         if (lane == 0) {
-            uint32_t seq = 0;
+            uint32_t buf = 0, use = 0;                 // ring slot of the next chunk and how often it has been used
             for (int64_t it = 0; it < n_it; ++it) {
                 const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
                 for (int ip = 0; ip < p.n_in; ++ip)
-                    for (int q = 0; q < NCW; ++q, ++seq) {
-                        const uint32_t buf = seq % NRING, use = seq / NRING;
+                    for (int q = 0; q < NCW; ++q) {
                         mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 100 + buf);
                         uint64_t* full = &bars->in_full[it & 1][buf];
                         mbar_expect_tx(full, CW_BYTES);
                         tma_load_2d(sRing + buf * CW_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CW, (int)row0, full);
+                        if (++buf == (uint32_t)NRING) { buf = 0; ++use; }
                     }
             }
         }
@@ -346,16 +346,32 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
         if (stamping && (it >> 1) < p.stamp_tiles) p.stamps[((size_t)g * p.stamp_tiles + (it >> 1)) * 16 + (slot)] = clock64(); \
     } while (0)
 
+        // ring slot of this group's next tile's first chunk: advanced by the chunks of two tiles (its own and the other group's) per
+        // iteration, wrapped by subtraction -- no division in the loops
+        const uint32_t uring = (uint32_t)NRING, tile_chunks = (uint32_t)(NCW * p.n_in);
+        uint32_t ring0 = (uint32_t)g * tile_chunks % uring;
+        // sender index of the first tile's row; the next tile's is fetched one tile ahead so its latency never shows
+        int32_t snd_next = 0;
+        if (p.gather && g < n_it) {
+            const int64_t first = ((cluster_id + (int64_t)g * n_clusters) * 2 + rank) * 128 + r;
+            snd_next = __ldg(p.senders + (first < p.n_rows ? first : p.n_rows - 1));
+        }
         for (int64_t it = g; it < n_it; it += 2) {
             const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
-            uint32_t seq = (uint32_t)it * (uint32_t)(NCW * p.n_in);
-            const uint32_t rin_seq0 = seq;          // RIN: ring position of this tile's first input chunk
+            uint32_t buf = ring0;                   // ring slot of the next input chunk of this tile
+            const uint32_t rin0 = ring0;            // RIN: slot of this tile's first input chunk
+            ring0 += 2 * tile_chunks;
+            while (ring0 >= uring) ring0 -= uring;
             const bool valid = row0 + r < p.n_rows;
             const int64_t grow = valid ? row0 + r : p.n_rows - 1;           // clamped: loads of padded rows stay in bounds
             const int64_t recv = grow >> p.kshift;
             const size_t rowoff = (size_t)grow * TC_H, recvoff = (size_t)recv * TC_H;
             // the sender index is fetched now so that the address of the gathered P_s row is ready when its epilogue starts
-            const int32_t snd = p.gather ? __ldg(p.senders + grow) : 0;
+            const int32_t snd = snd_next;
+            if (p.gather && it + 2 < n_it) {
+                const int64_t nxt = ((cluster_id + (it + 2) * n_clusters) * 2 + rank) * 128 + r;
+                snd_next = __ldg(p.senders + (nxt < p.n_rows ? nxt : p.n_rows - 1));
+            }
             CGNN_STAMP(0);
             // ---- input phases: stream chunks, split, write the A operand -------------------------------------
             for (int ip = 0; ip < p.n_in; ++ip) {
@@ -364,8 +380,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     pm ^= 1u;
                     tc_fence_after_sync();
                 }
-                for (int q = 0; q < NCW; ++q, ++seq) {
-                    const uint32_t buf = seq % NRING;
+                for (int q = 0; q < NCW; ++q, buf = buf + 1 == uring ? 0 : buf + 1) {
                     mbar_wait_or_trap(&bars->in_full[g][buf], (in_par >> buf) & 1u, 150 + buf);
                     in_par ^= 1u << buf;
                     const uint8_t* src = sRing + buf * CW_BYTES;
@@ -611,7 +626,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         }
                         if (RIN) {
                             // residual = this tile's input, still in its ring slots (this thread's own row, swizzled)
-                            const uint32_t rbuf = (rin_seq0 + (uint32_t)(cc >> 5)) % NRING;
+                            uint32_t rbuf = rin0 + (uint32_t)(cc >> 5);
+                            if (rbuf >= uring) rbuf -= uring;
                             const uint8_t* src = sRing + rbuf * CW_BYTES;
                             float o[16];
 #pragma unroll
@@ -643,7 +659,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             if (RIN) {                                   // the tile's input slots go back to the producer
                 __syncwarp();
                 if (lane == 0)
-                    for (int q = 0; q < NCW; ++q) mbar_arrive_local(&bars->in_empty[(rin_seq0 + (uint32_t)q) % NRING]);
+                    for (uint32_t q = 0, b = rin0; q < (uint32_t)NCW; ++q, b = b + 1 == uring ? 0 : b + 1) mbar_arrive_local(&bars->in_empty[b]);
             }
             CGNN_STAMP(13);
             // D and A of this slot are free again: the next tile of this group starts with its input phase
