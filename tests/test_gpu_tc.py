@@ -61,7 +61,7 @@ def test_tc_node_phase_forward(precision, n):
 
 
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
-@pytest.mark.parametrize("n,k", [(300, 16), (64, 8), (1000, 32), (5000, 16), (130, 4), (20000, 16)])
+@pytest.mark.parametrize("n,k", [(300, 16), (64, 8), (1000, 32), (5000, 16), (130, 4), (20000, 16), (1, 32), (7, 1), (33, 2)])
 @pytest.mark.parametrize("with_agg", [True, False])
 def test_tc_edge_phase_forward(precision, n, k, with_agg):
     from cosmology_gnn_simulation_b200 import ops
@@ -118,6 +118,51 @@ def test_tc_rejects_unsupported_shapes():
     s = torch.zeros(800, dtype=torch.int32, device=d)
     with pytest.raises(RuntimeError, match="tensor-core edge phase supports"):
         ops.mp_edge_fwd(p, h, e, s, 8, torch.empty_like(e), None, "bf16x3")
+
+
+def test_tc_rejects_in_degrees_the_butterfly_sum_cannot_take():
+    """Per-receiver sums are warp-shuffle butterflies over the k lanes of a receiver: k must be a power of two <= 32."""
+    from cosmology_gnn_simulation_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    p, *_ = _mlp_params(3 * L, gen)
+    d = _dev()
+    n, k = 40, 12
+    h = torch.randn(n, L, generator=gen).to(d)
+    e = torch.randn(n * k, L, generator=gen).to(d)
+    s = torch.zeros(n * k, dtype=torch.int32, device=d)
+    with pytest.raises(RuntimeError, match="power of two"):
+        ops.mp_edge_fwd(p, h, e, s, k, torch.empty_like(e), None, "bf16x3")
+
+
+def test_chain_stage_stamps_debug_hook():
+    """cgnn_debug_stamps: block 0 records increasing clock64 stamps for the stages of its tiles; off again afterwards."""
+    import ctypes
+    from cosmology_gnn_simulation_b200 import ops
+    from cosmology_gnn_simulation_b200._lib import lib
+    gen = torch.Generator().manual_seed(5)
+    p, *_ = _mlp_params(3 * L, gen)
+    d = _dev()
+    n, k = 40000, 16
+    h = torch.randn(n, L, generator=gen).to(d)
+    e = torch.randn(n * k, L, generator=gen).to(d)
+    s = torch.randint(0, n, (n * k,), generator=gen, dtype=torch.int32).to(d)
+    out = torch.empty_like(e)
+    tiles, launches = 4, 3
+    buf = torch.zeros(launches * 2 * tiles * 16, dtype=torch.int64, device=d)
+    lib().cgnn_debug_stamps(ctypes.c_void_p(buf.data_ptr()), tiles, launches)
+    try:
+        ops.mp_edge_fwd(p, h, e, s, k, out, None, "bf16x3")         # P_s chain, P_r chain, fused edge chain
+        torch.cuda.synchronize()
+    finally:
+        lib().cgnn_debug_stamps(None, 0, 0)
+    st = buf.cpu().view(launches, 2, tiles, 16)
+    edge = st[2, 0]                                                   # third launch, epilogue group 0
+    assert (edge[:, 0] > 0).all() and (edge[:, 13] > edge[:, 0]).all()
+    assert (edge[1:, 0] > edge[:-1, 0]).all()                         # tiles of a group run one after the other
+    snapshot = buf.clone()
+    ops.mp_edge_fwd(p, h, e, s, k, out, None, "bf16x3")
+    torch.cuda.synchronize()
+    assert torch.equal(buf, snapshot)                                 # recording is off
 
 
 # ------------------------------------------------------------------------------------------------
