@@ -65,6 +65,8 @@ SIGNATURES = {
                                  c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_scatter_to_senders": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                         c_void_p, c_void_p]),
+    "cgnn_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float,
+                               c_int32, c_float, c_void_p]),
     "cgnn_loss_workspace_bytes": (c_int64, [c_int64, c_int32]),
     "cgnn_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                   c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -195,6 +195,17 @@ int cgnn_loss_fwd_bwd(const float* acc, const float* temp, const float* y_acc, c
                       float w_acc, float w_temp, float w_mom, float* losses, float* d_acc,
                       float* d_temp, void* workspace, int64_t workspace_bytes, cgnn_stream stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step -- train.py:183-187 (torch.optim.Adam(lr, weight_decay) + ExponentialLR), :263-265.
+ * One fused pass over a flat FP32 parameter buffer and its gradient / moment buffers (all n floats, 16-byte
+ * aligned):  g = grads * grad_scale + weight_decay * p;  m, v <- Adam moments;  p -= lr / (1 - beta1^step) *
+ * m / (sqrt(v) / sqrt(1 - beta2^step) + eps).  `lr` is the scheduler's current rate (lr0 * gamma^epoch),
+ * `step` counts from 1, `grad_scale` folds an all-reduce average (1 / world) into the same pass.
+ */
+int cgnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                   cgnn_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
