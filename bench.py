@@ -179,10 +179,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, message, precision, gpus, sharding="slab"):
+def workload_config(name, message, precision, gpus, sharding="slab", scaling="weak"):
     n, k, L, M, kind = WORKLOADS[name]
     if gpus == 1:
         par = "single GPU"
+    elif sharding == "slab" and scaling == "strong":
+        par = (f"slab{gpus}, strong: the workload's ONE box of {n} particles cut into {gpus} equal-count x-slabs; per MP step one "
+               f"halo exchange of boundary latents (NCCL P2P), 5-float loss all-reduce, gradient all-reduce(SUM)")
+        n = n // gpus
     elif sharding == "slab":
         par = (f"slab{gpus}: ONE box of {gpus}x{n} particles cut into {gpus} equal-count x-slabs; per MP step one halo "
                f"exchange of boundary latents (NCCL P2P), 5-float loss all-reduce, gradient all-reduce(SUM)")
@@ -219,7 +223,11 @@ def run_gpu(args):
     slab = world > 1 and args.sharding == "slab"
     # slab: every rank holds the same box of world * n particles and owns one x-slab of it (weak scaling);
     # replica: every rank has its own box of n particles
-    box = synthetic.make_box(n * world, kind, seed=0) if slab else synthetic.make_box(n, kind, seed=rank)
+    strong = slab and args.scaling == "strong"        # strong: ONE box of n particles cut into `world` slabs (a box too large for one GPU)
+    n_box = n if strong else n * world
+    box = synthetic.make_box(n_box, kind, seed=0) if slab else synthetic.make_box(n, kind, seed=rank)
+    if strong:
+        n = n_box // world                            # particles per GPU, for the throughput count below
     md = box["metadata"]
     coords_host = box["Coordinates"].pin_memory()
     energy_host = box["InternalEnergy"].pin_memory()
@@ -353,10 +361,10 @@ def run_gpu(args):
     achieved = fl / (edge_ms * 1e-3) / 1e12 if edge_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16 operands, f32 accumulate/storage)", "bf16": "bf16"}[precision],
         "data": "synthetic",
-        "config": workload_config(args.workload, message, precision, world, args.sharding),
+        "config": workload_config(args.workload, message, precision, world, args.sharding, args.scaling),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
                 "includes": "H2D of the 6 frames, graph build (k-NN + features), forward, loss, backward, D2H of the 4 loss scalars"},
@@ -434,6 +442,8 @@ def main():
     ap.add_argument("--message", default="edge", choices=["sender", "edge"],
                     help="edge: the Interaction Network of the north star (default); sender: what PyG's default message() computes")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1, slab sharding: weak = one box of N x the workload's particles (default), strong = the workload's box itself cut into N slabs")
     ap.add_argument("--sharding", default="slab", choices=["slab", "replica"],
                     help="N > 1: slab = one box of N x particles cut into x-slabs with halo exchange (default); "
                          "replica = one independent box per GPU")
