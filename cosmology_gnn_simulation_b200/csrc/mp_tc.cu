@@ -71,6 +71,8 @@ struct TcParams {
     const float* du_recv;
     float* ln_partials;         // [gridDim.x * 8][2][128]: per-warp column sums of dU * xhat and dU
     float* out;                 // [n_rows][128]
+    uint32_t* bits_out;         // [n_rows][4]: bit c = (result column c > 0) -- the ReLU gate of the backward, 16 B per row (nullable)
+    const uint32_t* mask_bits;  // [n_rows][4]: result = bit c ? result : 0 -- the same gate read back (nullable)
     int n_ring;                 // input ring depth
     ChainBlock blk[MAX_BLOCKS]; // weight blocks in FP32 (torch layout): every CTA builds its BF16 images in shared memory itself
     const float* vec_src[5];    // bias of layer 1, 2, 3, gamma, beta (nullable -> zeros / ones for gamma)
@@ -491,6 +493,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             float a0[16], a1[16], a2[16], a3[16], b0[16], b1[16], b2[16], b3[16];
             if (pa) { ld16(pa, a0); ld16(pa + 16, a1); ld16(pa + 32, a2); ld16(pa + 48, a3); }
             if (pb) { ld16(pb, b0); ld16(pb + 16, b1); ld16(pb + 32, b2); ld16(pb + 48, b3); }
+            uint4 mbits = make_uint4(0u, 0u, 0u, 0u);
+            if (p.mask_bits != nullptr) mbits = __ldg(reinterpret_cast<const uint4*>(p.mask_bits) + grow);
             mbar_wait_or_trap(&bars->mma_done[g], pm, 180);
             pm ^= 1u;
             tc_fence_after_sync();
@@ -566,6 +570,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 tmem_ld_32x32b_x16(tD, va);
 #pragma unroll 1
                 for (int c = 0; c < TC_H; c += 64) {
+                    uint32_t gate0 = 0u, gate1 = 0u;         // ReLU gates of columns c .. c+31, c+32 .. c+63
 #pragma unroll
                     for (int hh = 0; hh < 4; ++hh) {
                         float* v = (hh & 1) == 0 ? va : vb;
@@ -624,6 +629,21 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = ca[j] > 0.0f ? v[j] : 0.0f;
                         }
+                        if (p.mask_bits != nullptr) {
+                            const uint32_t wsel = (cc >> 5) == 0 ? mbits.x : (cc >> 5) == 1 ? mbits.y : (cc >> 5) == 2 ? mbits.z : mbits.w;
+                            const uint32_t w16 = wsel >> (cc & 16);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = (w16 >> j) & 1u ? v[j] : 0.0f;
+                        }
+                        if (p.bits_out != nullptr) {
+                            uint32_t w16 = 0u;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) w16 |= (v[j] > 0.0f ? 1u : 0u) << j;
+                            if (hh == 0) gate0 = w16;
+                            else if (hh == 1) gate0 |= w16 << 16;
+                            else if (hh == 2) gate1 = w16;
+                            else gate1 |= w16 << 16;
+                        }
                         if (RIN) {
                             // residual = this tile's input, still in its ring slots (this thread's own row, swizzled)
                             uint32_t rbuf = rin0 + (uint32_t)(cc >> 5);
@@ -654,6 +674,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             if (pb) ld16(pb + cc + 64, cb);
                         }
                     }
+                    if (p.bits_out != nullptr && valid) *reinterpret_cast<uint2*>(p.bits_out + (size_t)grow * 4 + (c >> 5)) = make_uint2(gate0, gate1);
                 }
             }
             if (RIN) {                                   // the tile's input slots go back to the producer
@@ -734,7 +755,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     p.agg_out = op.agg_out; p.senders = op.senders; p.Ps = op.Ps; p.Pr = op.Pr;
     for (int l = 0; l < 2; ++l) { p.hid_mask[l] = op.hid_mask[l]; p.hid_out[l] = op.hid_out[l]; p.hid_agg[l] = op.hid_agg[l]; }
     p.du_rows = op.du_rows; p.du_recv = op.du_recv; p.ln_partials = static_cast<float*>(op.ln_ws);
-    p.out = op.out;
+    p.out = op.out; p.bits_out = op.bits_out; p.mask_bits = op.mask_bits;
     for (int b = 0; b < n_blocks; ++b) p.blk[b] = op.blk[b];
     if (op.n_layers == 1) {
         p.vec_src[0] = op.bias[0];

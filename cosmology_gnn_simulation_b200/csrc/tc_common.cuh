@@ -58,6 +58,8 @@ struct ChainOp {
     const float* residual;        // result += residual                   (nullable)
     float* agg_out;               // [rows / k][128] = per-receiver sum of the result before the residual (nullable)
     float* out;                   // [rows][128]
+    uint32_t* bits_out;           // [rows][4]: bit c = result column c > 0 (the ReLU gate, 16 B per row instead of a 512 B mask source; nullable)
+    const uint32_t* mask_bits;    // [rows][4]: result = bit c ? result : 0  (nullable; applied after relu_out / mask_src)
     // hidden layers of a 3-layer chain (index 0, 1): mask instead of ReLU, extra output, per-receiver sum of the activation
     const float* hid_mask[2]; float* hid_out[2]; float* hid_agg[2];
     // LayerNorm backward instead of forward after the last layer: out = dY of (Y, dU), dU = du_rows[row] + du_recv[row / k];

@@ -27,6 +27,7 @@ bool tc_shape_ok(const MlpDev& m, int in_mult) {
 }
 
 int64_t rows_bytes(int64_t rows) { return align_up(rows * TC_H * 4, 256); }
+int64_t gate_bytes(int64_t rows) { return align_up(rows * 16, 256); }      // ReLU gates: 128 bits per row
 
 struct Scratch {
     void* wg; void* lnb;
@@ -107,14 +108,14 @@ int64_t tc_node_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision) {
 int64_t tc_rows_workspace(const cgnn_mlp* mlp, int64_t rows, int precision, int backward) {
     (void)mlp; (void)precision;
     const int64_t chunk = rows < CHUNK_ROWS ? rows : CHUNK_ROWS;
-    return Scratch::bytes() + (backward ? 6 : 2) * rows_bytes(chunk);
+    return Scratch::bytes() + (backward ? 6 : 2) * rows_bytes(chunk) + (backward ? 2 * gate_bytes(chunk) : 0);
 }
 // k == 0: node phase
 int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int64_t n_nodes, int k, int precision) {
     (void)mlp; (void)precision;
-    if (k == 0) return Scratch::bytes() + 5 * rows_bytes(n);
+    if (k == 0) return Scratch::bytes() + 5 * rows_bytes(n) + 2 * gate_bytes(n);
     int64_t chunk = n * k < CHUNK_ROWS ? n * k : CHUNK_ROWS;
-    return Scratch::bytes() + 5 * rows_bytes(chunk) + 2 * rows_bytes(n) + 2 * rows_bytes(n_nodes);
+    return Scratch::bytes() + 5 * rows_bytes(chunk) + 2 * gate_bytes(chunk) + 2 * rows_bytes(n) + 2 * rows_bytes(n_nodes);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -244,7 +245,8 @@ static int bwd_mode(int64_t rows) {
 // `r` carries the input side of R (in0 / in1, their weight blocks, bias[0] or the gather); without a LayerNorm
 // (decoders) the caller has put dY, zero padded to 128 columns, into T.
 static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn_mlp_grad* g, int64_t rows, ChainOp r,
-                          float* A1, float* A2, float* T, float* G2, const float* du_rows, const float* du_recv, int k,
+                          float* A1, float* A2, float* T, float* G2, uint32_t* gate1, uint32_t* gate2,
+                          const float* du_rows, const float* du_recv, int k,
                           ChainBlock last, const float* residual, float* d_in, float* g1_out, float* g1_agg,
                           int accumulate, cudaStream_t s) {
     int rc;
@@ -252,11 +254,11 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
     if (bwd_mode(rows) == 0) {
         // A1 = relu(layer 1), A2 = relu(A1 W2^T + b2)
         r.ns = ns; r.rows = rows; r.n_layers = 1;
-        r.relu_out = 1; r.out = A1;
+        r.relu_out = 1; r.out = A1; r.bits_out = gate1;          // the ReLU gates go out as 16 B per row for the dgrad chains
         if ((rc = run_chain(r, s))) return rc;
         {
             ChainOp op = base_op(ns, sc, rows);
-            op.in0 = A1; op.blk[0] = {m.W[1], TC_H, 0, 0, 0}; op.bias[0] = m.b[1]; op.relu_out = 1; op.out = A2;
+            op.in0 = A1; op.blk[0] = {m.W[1], TC_H, 0, 0, 0}; op.bias[0] = m.b[1]; op.relu_out = 1; op.out = A2; op.bits_out = gate2;
             if ((rc = run_chain(op, s))) return rc;
         }
         if (m.gamma != nullptr) {   // dY = LayerNorm backward of (Y = A2 W3^T + b3, dU), in the chain's final epilogue
@@ -270,13 +272,13 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
         if ((rc = run_wgrad(ns, T, A2, rows, g->W[2], TC_H, 0, g->b[2], accumulate, sc.wg, s, m.out_dim, 0))) return rc;
         {   // G2 = (dY W3) * [A2 > 0]
             ChainOp op = base_op(ns, sc, rows);
-            op.in0 = T; op.blk[0] = {m.W[2], TC_H, 0, 0, 1, 0, m.out_dim}; op.mask_src = A2; op.out = G2;
+            op.in0 = T; op.blk[0] = {m.W[2], TC_H, 0, 0, 1, 0, m.out_dim}; op.mask_bits = gate2; op.out = G2;
             if ((rc = run_chain(op, s))) return rc;
         }
         if ((rc = run_wgrad(ns, G2, A1, rows, g->W[1], TC_H, 0, g->b[1], accumulate, sc.wg, s))) return rc;
         {   // G1 = (G2 W2) * [A1 > 0]   (+ per-receiver sum)
             ChainOp op = base_op(ns, sc, rows);
-            op.in0 = G2; op.blk[0] = {m.W[1], TC_H, 0, 0, 1}; op.mask_src = A1; op.out = g1_out;
+            op.in0 = G2; op.blk[0] = {m.W[1], TC_H, 0, 0, 1}; op.mask_bits = gate1; op.out = g1_out;
             op.k = k; op.agg_out = g1_agg;
             if ((rc = run_chain(op, s))) return rc;
         }
@@ -336,6 +338,7 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         const int64_t chunk = a.n < CHUNK_ROWS ? a.n : CHUNK_ROWS;
         float* Xp = cv.take<float>(chunk * TC_H); float* A1 = cv.take<float>(chunk * TC_H); float* A2 = cv.take<float>(chunk * TC_H);
         float* T = cv.take<float>(chunk * TC_H); float* G2 = cv.take<float>(chunk * TC_H); float* G1 = cv.take<float>(chunk * TC_H);
+        uint32_t* gate1 = cv.take<uint32_t>(chunk * 4); uint32_t* gate2 = cv.take<uint32_t>(chunk * 4);
         for (int64_t r0 = 0, c = 0; r0 < a.n; r0 += chunk, ++c) {
             const int64_t rows = a.n - r0 < chunk ? a.n - r0 : chunk;
             const int acc = c > 0;
@@ -352,7 +355,7 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             ChainOp r{};
             r.in0 = in; r.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim}; r.bias[0] = m.b[0];
             // dx = G1 W1 (in_dim == 128) comes out of the dgrad chain's last layer
-            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, dU, nullptr, 1, {m.W[0], m.in_dim, 0, 0, 1, m.in_dim, 0},
+            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, dU, nullptr, 1, {m.W[0], m.in_dim, 0, 0, 1, m.in_dim, 0},
                                      nullptr, a.dx ? a.dx + r0 * TC_H : nullptr, G1, nullptr, acc, s))) return rc;
             if ((rc = run_wgrad(ns, G1, in, rows, g->W[0], m.in_dim, 0, g->b[0], acc, sc.wg, s, 0, m.in_dim))) return rc;
         }
@@ -370,12 +373,13 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         const int64_t n = a.n;
         float* A1 = cv.take<float>(n * TC_H); float* A2 = cv.take<float>(n * TC_H); float* T = cv.take<float>(n * TC_H);
         float* G2 = cv.take<float>(n * TC_H); float* G1 = cv.take<float>(n * TC_H);
+        uint32_t* gate1 = cv.take<uint32_t>(n * 4); uint32_t* gate2 = cv.take<uint32_t>(n * 4);
         ChainOp r{};
         r.in0 = a.h; r.in1 = a.agg;
         r.blk[0] = {m.W[0], 2 * TC_H, 0, 0, 0}; r.blk[1] = {m.W[0], 2 * TC_H, 0, TC_H, 0};
         r.bias[0] = m.b[0];
         // dh = dh_next + G1 W1[:, 0:L] is the dgrad chain's last layer
-        if ((rc = fused_backward(ns, sc, m, g, n, r, A1, A2, T, G2, a.dout, nullptr, 1, {m.W[0], 2 * TC_H, 0, 0, 1}, a.dout, a.dh, G1,
+        if ((rc = fused_backward(ns, sc, m, g, n, r, A1, A2, T, G2, gate1, gate2, a.dout, nullptr, 1, {m.W[0], 2 * TC_H, 0, 0, 1}, a.dout, a.dh, G1,
                                  nullptr, 0, s))) return rc;
         // dW1 = G1^T [h | agg], db1
         if ((rc = run_wgrad(ns, G1, a.h, n, g->W[0], 2 * TC_H, 0, g->b[0], 0, sc.wg, s))) return rc;
@@ -401,6 +405,7 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         const int64_t chunk = E < CHUNK_ROWS ? E : CHUNK_ROWS;
         float* A1 = cv.take<float>(chunk * TC_H); float* A2 = cv.take<float>(chunk * TC_H); float* T = cv.take<float>(chunk * TC_H);
         float* G2 = cv.take<float>(chunk * TC_H); float* spare = cv.take<float>(chunk * TC_H); (void)spare;
+        uint32_t* gate1 = cv.take<uint32_t>(chunk * 4); uint32_t* gate2 = cv.take<uint32_t>(chunk * 4);
         float* Ps = cv.take<float>(nn * TC_H); float* Pr = cv.take<float>(n * TC_H);
         float* dPs = cv.take<float>(nn * TC_H); float* dPr = cv.take<float>(n * TC_H);
         if ((rc = project_nodes(ns, sc, m, a.h, n, nn, Ps, Pr, s))) return rc;
@@ -415,7 +420,7 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             ChainOp r{};
             r.in0 = e_in; r.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 0};
             r.k = a.k; r.senders = a.senders + r0; r.Ps = Ps; r.Pr = Pr + (r0 / k) * TC_H;
-            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, de_next, a.dagg + (r0 / k) * TC_H, a.k,
+            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, de_next, a.dagg + (r0 / k) * TC_H, a.k,
                                      {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}, de_next, a.de + r0 * TC_H, G1, dPr + (r0 / k) * TC_H, acc, s))) return rc;
             // dW1e = G1^T e, db1
             if ((rc = run_wgrad(ns, G1, e_in, rows, g->W[0], 3 * TC_H, 2 * TC_H, g->b[0], acc, sc.wg, s))) return rc;
