@@ -67,6 +67,25 @@ def flops_application(n, k, L, M, message):
     return fwd + 2.0 * (enc_n + M * proc_n + dec)
 
 
+def phase_work(n, k, L, M, message):
+    """Algorithmic FLOPs and HBM bytes of the forward and the backward of one training application (SURVEY §8d formulas,
+    FP32 latents b = 4, the fused design's traffic: only latents and indices touch HBM; recompute is not useful work)."""
+    e, b = n * k, 4
+    fn, fe = 17, 4
+    enc_n = 2.0 * n * (fn * L + L * L + L * L)
+    enc_e = 2.0 * e * (fe * L + L * L + L * L)
+    proc_e = flops_edge_fwd(n, k, L)
+    proc_n = 2.0 * n * (2 * L * L + L * L + L * L)
+    dec = 2.0 * n * (L * L + L * L + 3 * L) + 2.0 * n * (L * L + L * L + L)
+    fwd_flop = enc_n + enc_e + M * (proc_e + proc_n) + dec
+    bwd_flop = 2.0 * fwd_flop if message == "edge" else 2.0 * (enc_n + M * proc_n + dec)
+    enc_bytes = fn * 4 * n + fe * 4 * e + n * L * b + e * L * b
+    dec_bytes = n * L * b + 16 * n
+    fwd_bytes = enc_bytes + M * (2 * e * L * b + 2 * n * L * b + 4 * e) + dec_bytes
+    bwd_bytes = enc_bytes + dec_bytes + M * ((3 * e * L * b + 3 * n * L * b + 8 * e) if message == "edge" else (3 * n * L * b + 8 * e))
+    return {"forward": (fwd_flop, float(fwd_bytes)), "backward": (bwd_flop, float(bwd_bytes))}
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks (sampled DURING the timed region)
 # ------------------------------------------------------------------------------------------------
@@ -247,9 +266,18 @@ def run_gpu(args):
 
     graph = build_graph(coords_host, energy_host)        # resident inputs for the device-timed region
 
+    PHASE_EVENTS = {"on": False, "marks": []}         # (start, after forward + loss, after backward) CUDA events of eager steps
+
+    def _mark():
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
     def train_step(g):
         for p in model.parameters():
             p.grad = None
+        if PHASE_EVENTS["on"]:
+            return _train_step_marked(g)
         pred = model(g)
         if slab:
             ls = slab_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
@@ -259,6 +287,17 @@ def run_gpu(args):
             ls = combined_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
             ls["loss"].backward()
             bucket.all_reduce(average=True)
+        return ls
+
+    def _train_step_marked(g):
+        e0 = _mark()
+        pred = model(g)
+        ls = slab_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM) if slab else combined_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
+        e1 = _mark()
+        ls["loss"].backward()
+        e2 = _mark()
+        bucket.all_reduce(average=not slab)
+        PHASE_EVENTS["marks"].append((e0, e1, e2))
         return ls
 
     def barrier():
@@ -328,8 +367,12 @@ def run_gpu(args):
     # ---- the dominant kernel, bracketed by CUDA events: an eager replica of the timed region (launches inside a
     # replayed CUDA graph cannot be bracketed one by one) -----------------------------------------
     eager_ms = None
+    PHASE_EVENTS["on"] = True
     if graphed is not None:
         eager_ms, _, events, _ = timed_loop(train_step, True)
+    elif world == 1:
+        timed_loop(train_step, False)
+    PHASE_EVENTS["on"] = False
     edge_ms = sum(a.elapsed_time(b) for a, b in events) / max(len(events), 1)
 
     # ---- graph build alone (reported apart; not part of the model application) -----
@@ -385,6 +428,18 @@ def run_gpu(args):
                         "what": "cgnn_knn_periodic + cgnn_edge_features, device resident"},
         "loss_check": [float(v) for v in last],
     }
+    if PHASE_EVENTS["marks"]:
+        marks = PHASE_EVENTS["marks"][-args.steps:]
+        work = phase_work(n, k, L, M, message)
+        phases = {}
+        for name, (a, b_) in (("forward", (0, 1)), ("backward", (1, 2))):
+            ms = sum(m[a].elapsed_time(m[b_]) for m in marks) / len(marks)
+            fl, by = work[name]
+            phases[name] = {"ms": ms, "tflops": fl / (ms * 1e-3) / 1e12, "frac_tensor": fl / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                            "gbs": by / (ms * 1e-3) / 1e9, "frac_hbm": by / (ms * 1e-3) / 1e9 / peaks["hbm"]}
+        phases["what"] = ("eager steps of the same process, CUDA events around forward + loss and around backward; algorithmic FLOPs and "
+                          "HBM bytes of SURVEY 8d (FP32 latents, fused-design traffic) against the measured BF16 and copy peaks")
+        line["phases"] = phases
     if not args.no_cpu_baseline and world == 1:
         r = cpu_training_step_rate(k, L, M, steps=2, warmup=1, sample_n=min(n, 8192), message=message)
         line["cpu_baseline"] = {
