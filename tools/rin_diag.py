@@ -1,5 +1,10 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""Soak test of the edge forward whose residual comes from the input ring (C_RIN): repeats the same launch and reports every
+output element that differs from the first result (rows, tile, columns) -- a refilled ring slot shows up as another tile's e.
+  python tools/rin_diag.py [bf16x3|bf16] [launches]"""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import torch
 from cosmology_gnn_simulation_b200 import ops
 from cosmology_gnn_simulation_b200.ops import MlpParams
 L = 128

@@ -1,5 +1,9 @@
-import sys, time, torch
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""Where a rollout step spends its host and device time: preprocess (k-NN + features) and the model forward timed with and
+without synchronisation, plus a cProfile of the unsynchronised loop (found the 15 ms cudaMemGetInfo call per forward)."""
+import os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import torch
 from cosmology_gnn_simulation_b200 import synthetic, ops
 from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
 from cosmology_gnn_simulation_b200.data_utils import preprocess
