@@ -394,6 +394,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
                     }
                     if (!(RIN && ip == 0)) {             // (RIN: the chunk is released by the output pass, which reads it as the residual)
+                        consume16(hi);                   // the loads of every lane have returned before the slot is handed back
                         __syncwarp();
                         if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
                     }
@@ -657,6 +658,16 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                                 o[4 * j + 2] = v[4 * j + 2] + e4.z; o[4 * j + 3] = v[4 * j + 3] + e4.w;
                             }
                             if (valid) st16(outp + cc, o);
+                            if ((cc & 31) == 16) {
+                                // Both halves of the chunk are read: its ring slot goes back to the producer.  The arrival must come
+                                // after an instruction that CONSUMES the loaded values in every lane: shared-memory loads that are only
+                                // issued can still be queued behind the scattered global stores when lane 0's arrival becomes visible,
+                                // and the refill then lands under them (seen as rare wrong residuals).  Consuming o[] here does that
+                                // (consume16 reads the registers, the warp barrier then covers all lanes).
+                                consume16(reinterpret_cast<const uint32_t*>(o));
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_local(&bars->in_empty[rbuf]);
+                            }
                         } else if (!fgather && !lnb && pb) {
                             // residual: the sum goes out from the stream's own registers, v stays free for the per-receiver sum
 #pragma unroll
@@ -676,11 +687,6 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     }
                     if (p.bits_out != nullptr && valid) *reinterpret_cast<uint2*>(p.bits_out + (size_t)grow * 4 + (c >> 5)) = make_uint2(gate0, gate1);
                 }
-            }
-            if (RIN) {                                   // the tile's input slots go back to the producer
-                __syncwarp();
-                if (lane == 0)
-                    for (uint32_t q = 0, b = rin0; q < (uint32_t)NCW; ++q, b = b + 1 == uring ? 0 : b + 1) mbar_arrive_local(&bars->in_empty[b]);
             }
             CGNN_STAMP(13);
             // D and A of this slot are free again: the next tile of this group starts with its input phase

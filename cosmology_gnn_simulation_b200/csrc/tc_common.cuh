@@ -30,6 +30,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float* v) {
         : "memory");
 }
 
+// Orders a warp's shared-memory LOADS before a later mbarrier arrival that hands the buffer back to a TMA producer: an empty
+// volatile asm that READS the registers the loads feed (so every lane's loads have returned when it is passed); follow it by
+// __syncwarp() and the elected lane's arrival.  Without it the compiler may sink the arithmetic on the loaded values below the
+// arrival, the loads are then merely issued -- possibly queued behind scattered global accesses -- when the slot is refilled.
+__device__ __forceinline__ void consume16(const uint32_t* r) {
+    asm volatile("" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
 // byte offset of the 16-byte piece j (0..3) of row r inside a 64-byte-swizzled chunk buffer
 __device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
 

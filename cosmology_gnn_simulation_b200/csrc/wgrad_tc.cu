@@ -142,6 +142,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                         split2(v.x, v.y, hi[2 * j], lo[2 * j]);
                         split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
                     }
+                    consume16(hi);                       // every lane's loads have returned before the slot is handed back
                     __syncwarp();
                     if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
                     // columns 32q .. 32q+31 = mn groups 4q .. 4q+3; k = r
