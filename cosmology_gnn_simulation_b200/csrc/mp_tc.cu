@@ -156,6 +156,35 @@ __device__ __forceinline__ void receiver_sum16(float* v, int k, int lane) {
         }
     }
 }
+// Two 16-column blocks at once: the same butterfly on both, level by level, so that the two dependency chains (select ->
+// shuffle -> add, four levels at k = 16) overlap in a warp that has nobody else to hide its latencies behind.
+__device__ __forceinline__ void receiver_sum16x2(float* v, float* w, int k, int lane) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int m = k >> (s + 1);
+        if (m >= 1) {
+            const bool upper = (lane & m) != 0;
+            if (s < 4) {
+                const int half = 8 >> s;
+                float sv[8], sw[8];
+#pragma unroll
+                for (int j = 0; j < half; ++j) {
+                    sv[j] = __shfl_xor_sync(0xffffffffu, upper ? v[j] : v[j + half], m);
+                    sw[j] = __shfl_xor_sync(0xffffffffu, upper ? w[j] : w[j + half], m);
+                }
+#pragma unroll
+                for (int j = 0; j < half; ++j) {
+                    v[j] = (upper ? v[j + half] : v[j]) + sv[j];
+                    w[j] = (upper ? w[j + half] : w[j]) + sw[j];
+                }
+            } else {
+                const float a = __shfl_xor_sync(0xffffffffu, v[0], m), b = __shfl_xor_sync(0xffffffffu, w[0], m);
+                v[0] += a;
+                w[0] += b;
+            }
+        }
+    }
+}
 // stores the sums receiver_sum16 left in v for columns [c, c + 16) of receiver row `dst`
 __device__ __forceinline__ void receiver_store16(float* dst, int c, const float* v, int k, int lane) {
     if (k == 32) {
@@ -572,6 +601,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 #pragma unroll 1
                 for (int c = 0; c < TC_H; c += 64) {
                     uint32_t gate0 = 0u, gate1 = 0u;         // ReLU gates of columns c .. c+31, c+32 .. c+63
+                    float held[16];                          // the even 16-column block of a pair, waiting for the joint per-receiver sum
 #pragma unroll
                     for (int hh = 0; hh < 4; ++hh) {
                         float* v = (hh & 1) == 0 ? va : vb;
@@ -677,8 +707,17 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             st16(outp + cc, v);
                         }
                         if (aggp) {
-                            receiver_sum16(v, k, lane);
-                            if (valid) receiver_store16(aggp, cc, v, k, lane);
+                            // per-receiver sums, two 16-column blocks per butterfly: the even block waits for the odd one
+                            if ((hh & 1) == 0) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) held[j] = v[j];
+                            } else {
+                                receiver_sum16x2(held, v, k, lane);
+                                if (valid) {
+                                    receiver_store16(aggp, cc - 16, held, k, lane);
+                                    receiver_store16(aggp, cc, v, k, lane);
+                                }
+                            }
                         }
                         if (!lnb && cc + 64 < TC_H) {
                             if (pa) ld16(pa + cc + 64, ca);

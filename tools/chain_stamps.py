@@ -26,6 +26,8 @@ ap.add_argument("--k", type=int, default=16)
 ap.add_argument("--tiles", type=int, default=12)
 ap.add_argument("--precision", default="bf16x3")
 ap.add_argument("--bwd", action="store_true")
+ap.add_argument("--no-agg", action="store_true", help="forward without the per-receiver sum")
+ap.add_argument("--local-senders", action="store_true", help="sender = receiver: the gathered P_s row is shared by the k lanes of a receiver")
 a = ap.parse_args()
 L = 128
 d = torch.device("cuda", 0)
@@ -37,6 +39,8 @@ n, k = a.n, a.k
 h = torch.randn(n, L, device=d, generator=g)
 e = torch.randn(n * k, L, device=d, generator=g)
 senders = torch.randint(0, n, (n * k,), device=d, generator=g, dtype=torch.int32)
+if a.local_senders:
+    senders = torch.arange(n, device=d, dtype=torch.int32).repeat_interleave(k)
 e_out = torch.empty_like(e)
 agg = torch.empty_like(h)
 
@@ -51,7 +55,7 @@ def run():
         gs = torch.empty_like(e)
         ops.mp_edge_bwd(p, h, e, senders, rowptr, perm, k, de_next, dagg, de, dh, gs, a.precision)
     else:
-        ops.mp_edge_fwd(p, h, e, senders, k, e_out, agg, a.precision)
+        ops.mp_edge_fwd(p, h, e, senders, k, e_out, None if a.no_agg else agg, a.precision)
 
 
 run()                                   # warm-up (module load, workspaces)
