@@ -93,3 +93,21 @@ def test_preprocess_without_gpu_raises():
     with pytest.raises(RuntimeError, match="CUDA"):
         data_utils.preprocess(torch.from_numpy(g["coords"])[:5], torch.from_numpy(g["energy"])[:5],
                               {"temp_rate_std": 1.0}, dt=0.01, box_size=1.0)
+
+
+def test_bench_work_model_matches_survey_table():
+    """bench.py's algorithmic FLOP / HBM-byte model reproduces SURVEY §8d's table rows (config 2: 2.83 TFLOP and 14.9 GB per
+    application with FP32 latents; config 3: 352.8 TFLOP)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    w = bench.phase_work(32768, 16, 128, 10, "edge")
+    flop = w["forward"][0] + w["backward"][0]
+    assert abs(flop - bench.flops_application(32768, 16, 128, 10, "edge")) < 1e-6 * flop
+    assert abs(flop / 1e12 - 2.83) < 0.01
+    assert abs((w["forward"][1] + w["backward"][1]) / 1e9 - 14.9) < 0.1
+    assert abs(bench.flops_application(128 ** 3, 32, 128, 10, "edge") / 1e12 - 352.8) < 0.5
+    s = bench.phase_work(32768, 16, 128, 10, "sender")
+    assert abs((s["forward"][0] + s["backward"][0]) - bench.flops_application(32768, 16, 128, 10, "sender")) < 1e-6 * flop
