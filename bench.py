@@ -6,9 +6,9 @@ the encode / M x message-passing / decode Interaction Network on a synthetic per
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
     torchrun --nproc-per-node N ... bench.py --gpus N ...    # N ranks, one box replica each + gradient all-reduce
 
-Workload (default `config2`): BASELINE.json configs[1] -- 32^3 = 32768 particles, k=16, latent 128,
-10 MP steps, acceleration + temperature-rate + momentum loss.  `--workload config3` is configs[2]
-(128^3 particles, k=32).  One JSON line on stdout (rank 0).
+Workload (default `config3`): BASELINE.json configs[2], the configuration the metric is quoted on -- 128^3 =
+2 097 152 particles, k=32, latent 128, 10 MP steps, acceleration + temperature-rate + momentum loss, edge
+messages, on ONE B200.  `--workload config2` is configs[1] (32^3 particles, k=16).  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -35,8 +35,15 @@ WORKLOADS = {
     "tiny": (2048, 8, 32, 2, "uniform"),
 }
 W_ACC, W_TEMP, W_MOM = 1.0, 1.0, 0.1
-METRIC = "particle-steps/sec (fwd+bwd, 10 MP, L=128, k=32) at 1/2/4/8 B200; % roofline"
+METRIC = "particle-steps/sec (fwd+bwd, 10 MP, L=128, k=32) at 1/2/4/8 B200; % roofline"      # BASELINE.json, = config3's shape
 UNIT = "particle-steps/s"
+GRAPH_MAX_EDGES = 8 << 20         # above this a step's kernels are long enough that replaying a captured step buys nothing
+
+
+def metric_name(workload):
+    """BASELINE.json's metric string; for the other workloads the same wording with their own shape."""
+    n, k, L, M, kind = WORKLOADS[workload]
+    return f"particle-steps/sec (fwd+bwd, {M} MP, L={L}, k={k}) at 1/2/4/8 B200; % roofline"
 
 
 def measured_peaks():
@@ -141,7 +148,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference leg (oracle port of the reference algorithm; the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_training_step_rate(k, L, M, steps, warmup, sample_n=8192, seed=0, message="edge"):
+def cpu_training_step_rate(k, L, M, steps, warmup, sample_n=8192, seed=0, message="edge", keep=False):
     """Times the reference algorithm (gathers, cat, Linear, ReLU, LayerNorm, index_add_, autograd backward;
     `message` as the GPU arm) on the host cores with all threads.
     The particle count is a bounded sample of the workload (cost is linear in N at fixed k, L, M)."""
@@ -172,8 +179,12 @@ def cpu_training_step_rate(k, L, M, steps, warmup, sample_n=8192, seed=0, messag
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"rate": sample_n * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
-            "sample_n": sample_n, "knn_rate": sample_n / knn_s, "knn_s": knn_s}
+    out = {"rate": sample_n * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+           "sample_n": sample_n, "knn_rate": sample_n / knn_s, "knn_s": knn_s}
+    if keep:                                               # the sample and the oracle's result on it, for the parity block
+        out["sample"] = {"x": x, "ei": ei, "ea": ea, "ya": ya, "yt": yt, "params": params, "loss": ls["loss"].detach(),
+                         "acc": o["acceleration"].detach(), "temp": o["temp_rate"].detach()}
+    return out
 
 
 def run_reference(args):
@@ -187,7 +198,7 @@ def run_reference(args):
               f"(cost linear in N); graph build (KD-tree on 27N ghosts, 1 thread) timed apart: "
               f"{r['knn_rate']:.3g} particles/s")
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.workload), "value": r["rate"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, args.message, args.precision, args.gpus, args.sharding),
@@ -276,28 +287,16 @@ def run_gpu(args):
     def train_step(g):
         for p in model.parameters():
             p.grad = None
-        if PHASE_EVENTS["on"]:
-            return _train_step_marked(g)
-        pred = model(g)
-        if slab:
-            ls = slab_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
-            ls["loss"].backward()
-            bucket.all_reduce(average=False)          # every rank holds the partial gradient of ONE global loss
-        else:
-            ls = combined_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
-            ls["loss"].backward()
-            bucket.all_reduce(average=True)
-        return ls
-
-    def _train_step_marked(g):
-        e0 = _mark()
+        e0 = _mark() if PHASE_EVENTS["on"] else None
         pred = model(g)
         ls = slab_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM) if slab else combined_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
-        e1 = _mark()
+        e1 = _mark() if PHASE_EVENTS["on"] else None
         ls["loss"].backward()
-        e2 = _mark()
+        e2 = _mark() if PHASE_EVENTS["on"] else None
+        # slab: every rank holds the partial gradient of ONE global loss (SUM); replicas average
         bucket.all_reduce(average=not slab)
-        PHASE_EVENTS["marks"].append((e0, e1, e2))
+        if PHASE_EVENTS["on"]:
+            PHASE_EVENTS["marks"].append((e0, e1, e2))
         return ls
 
     def barrier():
@@ -305,25 +304,26 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # One GPU: the ~2000 launches of a step are captured once into a CUDA graph and replayed (graphed.py); the
-    # capture has to come before any eager step on the default stream.  N > 1 (NCCL point-to-point inside the
-    # step) stays eager.
+    # One GPU, small boxes: the ~2000 launches of a step are captured once into a CUDA graph and replayed (graphed.py);
+    # the capture has to come before any eager step on the default stream.  Large boxes (kernels of milliseconds) and
+    # N > 1 (NCCL point-to-point inside the step) run eagerly.
     graphed = None
     launches_per_graphed_step = 0
-    if world == 1 and not args.no_cuda_graph:
+    if world == 1 and not args.no_cuda_graph and n * k <= GRAPH_MAX_EDGES:
         from cosmology_gnn_simulation_b200.graphed import GraphedTrainStep
         graphed = GraphedTrainStep(model, lambda pred, g: combined_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM))
-        l0 = _lib.launch_count()
         graphed.capture(graph)
         launches_per_graphed_step = graphed.launches_per_step
-        del l0
     run_step = graphed if graphed is not None else train_step
 
-    def timed_loop(step_fn, collect_edge_events):
+    def timed_loop(step_fn, collect):
+        """`collect`: eager steps -- bracket every cgnn_mp_edge_fwd call and the forward / backward phases with CUDA events
+        (event records only; nothing is synchronised inside the loop)."""
         for _ in range(args.warmup):
             step_fn(graph)
         barrier()
-        ops.EDGE_FWD_EVENTS = [] if collect_edge_events else None
+        ops.EDGE_FWD_EVENTS = [] if collect else None
+        PHASE_EVENTS["on"], PHASE_EVENTS["marks"] = collect, []
         l0 = _lib.launch_count()
         marks = []
         with ClockSampler(local) as clk:
@@ -337,6 +337,7 @@ def run_gpu(args):
                 marks.append((s, e))
             barrier()
         ev, ops.EDGE_FWD_EVENTS = ops.EDGE_FWD_EVENTS, None
+        PHASE_EVENTS["on"] = False
         ms = cd.max_over_ranks(sum(s.elapsed_time(e) for s, e in marks), dev)
         return ms, _lib.launch_count() - l0, ev, clk
 
@@ -345,6 +346,36 @@ def run_gpu(args):
     if graphed is not None:
         launches = launches_per_graphed_step * args.steps
     value = world * n * args.steps / (total_ms * 1e-3)
+    phase_marks = PHASE_EVENTS["marks"]
+
+    # ---- the dominant kernel, bracketed by CUDA events.  Launches inside a replayed CUDA graph cannot be bracketed one
+    # by one, so a graphed run adds an eager replica of the timed region; an eager run measured them in the region itself
+    eager_ms = None
+    if graphed is not None:
+        eager_ms, _, events, _ = timed_loop(train_step, True)
+        phase_marks = PHASE_EVENTS["marks"]
+    edge_ms = sum(a.elapsed_time(b) for a, b in events) / max(len(events), 1)
+
+    # ---- graph build alone (reported apart; not part of the model application, SURVEY §8d) -----
+    pos_dev = graph.pos.contiguous()
+    n_pos = pos_dev.shape[0]
+    del graph
+    if not slab:
+        for _ in range(2):
+            ops.knn_periodic(pos_dev, md["box_size"], k)
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        reps = 5
+        for _ in range(reps):
+            nbr = ops.knn_periodic(pos_dev, md["box_size"], k)
+            feats = ops.edge_features(pos_dev, nbr, md["box_size"], want_edge_index=False)
+        e.record()
+        torch.cuda.synchronize(dev)
+        knn_ms = s.elapsed_time(e) / reps
+        del nbr, feats
+    else:
+        knn_ms = None
 
     # ---- end to end through the public API with host buffers (`e2e`) ---------------------------
     def e2e_step():
@@ -354,102 +385,187 @@ def run_gpu(args):
         ls = run_step(g)
         return torch.stack([ls["loss"].detach(), ls["acc_loss"], ls["temp_rate_loss"], ls["momentum_loss"]]).cpu()
 
-    for _ in range(min(args.warmup, 3)):
+    # (steps of seconds: a few are enough, the default run has to end within minutes)
+    e2e_steps = args.steps if total_ms / args.steps < 500.0 else min(args.steps, 4)
+    for _ in range(min(args.warmup, 3) if e2e_steps == args.steps else 1):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         last = e2e_step()
     barrier()
     e2e_s = cd.max_over_ranks(time.perf_counter() - t0, dev)
-    e2e_value = world * n * args.steps / e2e_s
+    e2e_value = world * n * e2e_steps / e2e_s
 
-    # ---- the dominant kernel, bracketed by CUDA events: an eager replica of the timed region (launches inside a
-    # replayed CUDA graph cannot be bracketed one by one) -----------------------------------------
-    eager_ms = None
-    PHASE_EVENTS["on"] = True
-    if graphed is not None:
-        eager_ms, _, events, _ = timed_loop(train_step, True)
-    elif world == 1:
-        timed_loop(train_step, False)
-    PHASE_EVENTS["on"] = False
-    edge_ms = sum(a.elapsed_time(b) for a, b in events) / max(len(events), 1)
-
-    # ---- graph build alone (reported apart; not part of the model application, SURVEY §8d) -----
-    pos_dev = graph.pos.contiguous()
-    for _ in range(2):
-        ops.knn_periodic(pos_dev, md["box_size"], k)
-    torch.cuda.synchronize(dev)
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    reps = 5
-    for _ in range(reps):
-        nbr = ops.knn_periodic(pos_dev, md["box_size"], k)
-        ops.edge_features(pos_dev, nbr, md["box_size"])
-    e.record()
-    torch.cuda.synchronize(dev)
-    knn_ms = s.elapsed_time(e) / reps
+    # ---- N > 1: the sharded step against the single-GPU step on a small box (the world-2 pytest cannot run on the
+    # driver's one-GPU test lease, so the check travels with the bench line) -----------------------------------
+    parity = slab_parity(rank, world, dev, k, L, M, message, precision) if slab else None
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks = measured_peaks()
     fl = flops_edge_fwd(n, k, L)
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "edge_fwd_traffic.json")     # dram bytes of the same launch from `ncu --set full`
     if os.path.exists(tpath):
         with open(tpath) as f:
-            t = json.load(f)
-        if t.get("workload") == args.workload and t.get("precision") == precision:
-            traffic = t.get("dram_bytes_per_launch")
+            tt = json.load(f)
+        for t in (tt if isinstance(tt, list) else [tt]):
+            if t.get("workload") == args.workload and t.get("precision") == precision:
+                traffic = t.get("dram_bytes_per_launch")
+                traffic_src = "profiles/edge_fwd_traffic.json: " + t.get("source", "ncu --set full capture of this kernel at this workload (not measured in this run)")
     achieved = fl / (edge_ms * 1e-3) / 1e12 if edge_ms > 0 else 0.0
+    step_ms = (eager_ms if eager_ms is not None else total_ms) / args.steps
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16 operands, f32 accumulate/storage)", "bf16": "bf16"}[precision],
         "data": "synthetic",
         "config": workload_config(args.workload, message, precision, world, args.sharding, args.scaling),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
+                "steps": e2e_steps,
                 "includes": "H2D of the 6 frames, graph build (k-NN + features), forward, loss, backward, D2H of the 4 loss scalars"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "cgnn_mp_edge_fwd (processor edge phase, forward)",
                      "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                      "executed_flop_per_launch": (2.0 * n * k * 3 * L * L + 2.0 * n * 2 * L * L) * (3 if precision == "bf16x3" else 1)
                      if precision != "fp32" else fl,
                      "flop_per_launch": fl, "ms_per_launch": edge_ms, "launches_timed": len(events),
                      "peak_source": peaks["source"] + " (bf16 dense, sustained)",
-                     "share_of_step": edge_ms * M / ((eager_ms if eager_ms is not None else total_ms) / args.steps),
+                     "share_of_step": edge_ms * len(events) / max(args.steps, 1) / step_ms,
                      "timed": "eager replica of the timed region, same process" if eager_ms is not None else "the timed region"},
         "cuda_graph": graphed is not None,
         "eager_ms_per_step": None if eager_ms is None else eager_ms / args.steps,
         "model_tflops": flops_application(n, k, L, M, message) / (total_ms / args.steps * 1e-3) / 1e12,
-        "graph_build": {"ms": knn_ms, "particles_per_s": n / (knn_ms * 1e-3),
-                        "what": "cgnn_knn_periodic + cgnn_edge_features, device resident"},
+        "graph_build": None if knn_ms is None else {"ms": knn_ms, "particles_per_s": n_pos / (knn_ms * 1e-3),
+                                                    "what": "cgnn_knn_periodic + cgnn_edge_features, device resident"},
         "loss_check": [float(v) for v in last],
     }
-    if PHASE_EVENTS["marks"]:
-        marks = PHASE_EVENTS["marks"][-args.steps:]
+    if message == "edge" and precision != "fp32":
+        from cosmology_gnn_simulation_b200 import graph_network as gn
+        plans = [v for kk, v in gn._STREAM_PLANS.items()]
+        if plans:
+            from cosmology_gnn_simulation_b200 import ckpt_plan
+            nb = plans[-1]
+            line["edge_stream"] = {"buffers": nb, "bytes_per_copy": n * k * L * 4,
+                                   "recomputed_edge_phases_per_step": ckpt_plan.recomputed_phases(ckpt_plan.schedule(M, nb)),
+                                   "what": "copies of the FP32 edge latent stream kept for the backward (ckpt_plan.py); the rest is recomputed"}
+    if parity is not None:
+        line["parity"] = parity
+    if phase_marks:
+        marks = phase_marks[-args.steps:]
         work = phase_work(n, k, L, M, message)
         phases = {}
         for name, (a, b_) in (("forward", (0, 1)), ("backward", (1, 2))):
             ms = sum(m[a].elapsed_time(m[b_]) for m in marks) / len(marks)
-            fl, by = work[name]
-            phases[name] = {"ms": ms, "tflops": fl / (ms * 1e-3) / 1e12, "frac_tensor": fl / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            fl_, by = work[name]
+            phases[name] = {"ms": ms, "tflops": fl_ / (ms * 1e-3) / 1e12, "frac_tensor": fl_ / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
                             "gbs": by / (ms * 1e-3) / 1e9, "frac_hbm": by / (ms * 1e-3) / 1e9 / peaks["hbm"]}
         phases["what"] = ("eager steps of the same process, CUDA events around forward + loss and around backward; algorithmic FLOPs and "
                           "HBM bytes of SURVEY 8d (FP32 latents, fused-design traffic) against the measured BF16 and copy peaks")
         line["phases"] = phases
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_training_step_rate(k, L, M, steps=2, warmup=1, sample_n=min(n, 8192), message=message)
-        line["cpu_baseline"] = {
-            "value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-            "sample": f"oracle port (message='{message}'), {r['sample_n']} of {n} particles per step, "
-                      f"k={k}, L={L}, M={M}, fwd+loss+bwd, 1 warm-up + 2 timed steps; k-NN oracle "
-                      f"(KD-tree on 27N ghosts, 1 thread) {r['knn_rate']:.3g} particles/s"}
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_baseline_leg(k, L, M, n, message, precision, dev)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline_leg(k, L, M, n, message, precision, dev):
+    """The oracle port timed on the host cores on a bounded sample of the workload -- and, as the checker it is, the CUDA
+    path run on that very sample (same graph, features, targets, weights): loss and outputs side by side."""
+    from cosmology_gnn_simulation_b200.graph import Data
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    r = cpu_training_step_rate(k, L, M, steps=2, warmup=1, sample_n=min(n, 8192), message=message, keep=True)
+    s = r.pop("sample")
+    model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision)
+    model.load_state_dict({k_: v.detach() for k_, v in s["params"].items()})
+    model = model.to(dev)
+    g = Data(x=s["x"].to(dev), edge_index=s["ei"].to(dev), edge_attr=s["ea"].to(dev), y_acc=s["ya"].to(dev), y_temp_rate=s["yt"].to(dev))
+    pred = model(g)
+    ls = combined_loss(pred, g, 0.01, W_ACC, W_TEMP, W_MOM)
+    ls["loss"].backward()
+
+    def rel(a, b):
+        return float((a.detach().double().cpu() - b.detach().double()).norm() / b.detach().double().norm())
+    grad_err = max(rel(prm.grad, s["params"][name].grad) for name, prm in model.named_parameters()
+                   if prm.grad is not None and s["params"][name].grad is not None)
+    return {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": f"oracle port (message='{message}'), {r['sample_n']} of {n} particles per step, "
+                      f"k={k}, L={L}, M={M}, fwd+loss+bwd, 1 warm-up + 2 timed steps; k-NN oracle "
+                      f"(KD-tree on 27N ghosts, 1 thread) {r['knn_rate']:.3g} particles/s",
+            "parity_on_sample": {"loss_cuda": float(ls["loss"]), "loss_oracle_fp32": float(s["loss"]),
+                                 "loss_rel": abs(float(ls["loss"]) - float(s["loss"])) / abs(float(s["loss"])),
+                                 "acceleration_rel_l2": rel(pred["acceleration"], s["acc"]),
+                                 "temp_rate_rel_l2": rel(pred["temp_rate"], s["temp"]),
+                                 "worst_gradient_rel_l2": grad_err,
+                                 "what": "this repo's CUDA path on the oracle's sample (same graph, inputs, weights) against the "
+                                         "oracle's float32 result; gradients carry the ReLU-gate noise of two fp32-class "
+                                         "implementations (DESIGN.md section 2)"}}
+
+
+def slab_parity(rank, world, dev, k, L, M, message, precision, n_small=8192):
+    """Runs one training application of a small box slab-sharded over all ranks and again on rank 0 alone; returns the
+    relative differences of loss, outputs and parameter gradients (rank 0; None elsewhere)."""
+    import torch.distributed as dist
+    from cosmology_gnn_simulation_b200 import distributed as cd, synthetic
+    from cosmology_gnn_simulation_b200.data_utils import preprocess, preprocess_slab
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    from cosmology_gnn_simulation_b200.slab import slab_loss
+    n_small -= n_small % world
+    box = synthetic.make_box(n_small, "uniform", seed=123)
+    md = box["metadata"]
+    args_ = (box["Coordinates"][:5], box["InternalEnergy"][:5], md, box["Coordinates"][5:6], box["InternalEnergy"][5:6])
+    kw = dict(noise_std=0.0, num_neighbors=k, dt=md["dt"], box_size=md["box_size"], device=dev)
+    torch.manual_seed(1234)
+    model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision).to(dev)
+    g = preprocess_slab(*[a.clone() if torch.is_tensor(a) else a for a in args_], rank=rank, world=world, **kw)
+    torch.manual_seed(1234)                             # the lazy first layers draw their weights here: same on every rank
+    pred = model(g)
+    ls = slab_loss(pred, g, md["dt"], W_ACC, W_TEMP, W_MOM)
+    ls["loss"].backward()
+    cd.GradientBucket(model.parameters()).all_reduce(average=False)
+    own = torch.cat([pred["acceleration"].detach(), pred["temp_rate"].detach()], dim=1).contiguous()
+    parts = [torch.empty_like(own) for _ in range(world)]
+    dist.all_gather(parts, own)
+    torch.cuda.synchronize(dev)
+    if rank != 0:
+        dist.barrier()
+        return None
+    out_sorted = torch.cat(parts, dim=0)
+    out_slab = torch.empty_like(out_sorted)
+    out_slab[g.order] = out_sorted                       # back to the input order
+    single = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision)
+    single.load_state_dict(model.state_dict())
+    single = single.to(dev)
+    g1 = preprocess(*[a.clone() if torch.is_tensor(a) else a for a in args_], **kw)
+    pred1 = single(g1)
+    ls1 = combined_loss(pred1, g1, md["dt"], W_ACC, W_TEMP, W_MOM)
+    ls1["loss"].backward()
+    torch.cuda.synchronize(dev)
+
+    def rel(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm())
+    out1 = torch.cat([pred1["acceleration"].detach(), pred1["temp_rate"].detach()], dim=1)
+    grads = [(rel(p.grad, q.grad), nm) for (nm, p), q in zip(model.named_parameters(), single.parameters())
+             if p.grad is not None and q.grad is not None]
+    worst = max(grads)
+    res = {"box": f"{n_small} particles, k={k}, L={L}, M={M}, message={message}, precision={precision}: {world}-rank slab step vs the "
+                  f"same box on rank 0 alone",
+           "loss_rel": abs(float(ls["loss"]) - float(ls1["loss"])) / abs(float(ls1["loss"])),
+           "outputs_rel_l2": rel(out_slab, out1), "worst_gradient_rel_l2": worst[0], "worst_gradient": worst[1],
+           "gradients_compared": len(grads),
+           "note": "sums over a receiver's k edges and over rows are taken in the same order on both sides; the sender scatter "
+                   "adds halo contributions in peer order, so gradients agree to rounding, not bitwise"}
+    dist.barrier()
+    return res
 
 
 def run_rollout(args):
@@ -493,7 +609,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cgnn", choices=["cgnn", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--message", default="edge", choices=["sender", "edge"],
                     help="edge: the Interaction Network of the north star (default); sender: what PyG's default message() computes")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])

@@ -2,6 +2,7 @@
 first kernel call raises, loudly."""
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
@@ -67,6 +68,8 @@ SIGNATURES = {
                                         c_void_p, c_void_p]),
     "cgnn_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float,
                                c_int32, c_float, c_void_p]),
+    "cgnn_adam_step_masked": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                                      c_float, c_int32, c_float, c_void_p]),
     "cgnn_loss_workspace_bytes": (c_int64, [c_int64, c_int32]),
     "cgnn_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                   c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -120,7 +123,12 @@ def require_cuda(t: torch.Tensor, name: str, dtype=None):
 
 
 class Workspace:
-    """Grow-only scratch buffers, one per (device, tag); the C ABI never allocates."""
+    """Grow-only scratch buffers, one per (device, tag); the C ABI never allocates.
+
+    A CUDA-graph capture records the raw addresses of the buffers it was handed, so a capture must own its buffers:
+    `with workspace.scope() as held:` switches to a private set for the duration of the block (graphed.py keeps
+    `held` alive next to the captured graph); buffers of the shared set are then free to grow or move without
+    touching a captured step."""
 
     def __init__(self):
         self._bufs = {}
@@ -129,9 +137,20 @@ class Workspace:
         key = (str(device), tag)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError(f"cgnn: workspace '{tag}' would have to grow inside a CUDA-graph capture "
+                                   "(warm the step up at its final size before capturing)")
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self._bufs[key] = buf
         return buf
+
+    @contextlib.contextmanager
+    def scope(self):
+        outer, self._bufs = self._bufs, {}
+        try:
+            yield self._bufs
+        finally:
+            self._bufs = outer
 
 
 workspace = Workspace()

@@ -35,7 +35,6 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
 int64_t tc_edge_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision);
 int64_t tc_node_fwd_workspace(const cgnn_mlp* mlp, int64_t n, int precision);
 int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s);
-int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp);
 int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int64_t n_nodes, int k, int precision);
 int64_t tc_rows_workspace(const cgnn_mlp* mlp, int64_t rows, int precision, int backward);
 
@@ -97,8 +96,7 @@ extern "C" int cgnn_mlp_rows_fwd(const cgnn_mlp* mlp, const float* x, int64_t ro
 
 extern "C" int64_t cgnn_mlp_bwd_workspace_bytes(const cgnn_mlp* mlp) {
     if (mlp_validate(mlp, "cgnn_mlp_bwd_workspace_bytes")) return -1;
-    int64_t a = simt_mlp_bwd_workspace(mlp), b = tc_mlp_bwd_workspace(mlp);
-    return a > b ? a : b;
+    return simt_mlp_bwd_workspace(mlp);
 }
 
 extern "C" int cgnn_mlp_rows_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const float* x, int64_t rows,
@@ -132,7 +130,7 @@ extern "C" int cgnn_mp_edge_fwd(const cgnn_mlp* mlp, const float* h, const float
     int rc = mlp_validate(mlp, "cgnn_mp_edge_fwd");
     if (rc) return rc;
     if ((rc = check_latent(mlp, 3, "cgnn_mp_edge_fwd"))) return rc;
-    CGNN_CHECK_ARG(h && e_in && senders && e_out && n >= 1 && n_nodes >= n, "cgnn_mp_edge_fwd: bad arguments");
+    CGNN_CHECK_ARG(h && e_in && senders && (e_out || agg_edge) && n >= 1 && n_nodes >= n, "cgnn_mp_edge_fwd: bad arguments");
     CGNN_CHECK_ARG(k >= 1 && k <= 64, "cgnn_mp_edge_fwd: need 1 <= k <= 64");
     MlpTask a{};
     a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.n_nodes = n_nodes; a.k = k; a.L = mlp->out_dim;
@@ -194,9 +192,9 @@ extern "C" int cgnn_mp_edge_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, 
     int rc = mlp_validate(mlp, "cgnn_mp_edge_bwd");
     if (rc) return rc;
     if ((rc = check_latent(mlp, 3, "cgnn_mp_edge_bwd"))) return rc;
-    CGNN_CHECK_ARG(grad && h && e_in && senders && t_rowptr && t_perm && dagg && de && dh && gs && n >= 1 && n_nodes >= n,
+    CGNN_CHECK_ARG(grad && h && e_in && senders && t_rowptr && t_perm && dagg && de && dh && n >= 1 && n_nodes >= n,
                    "cgnn_mp_edge_bwd: bad arguments");
-    CGNN_CHECK_ARG(k >= 1 && k <= 64, "cgnn_mp_edge_bwd: need 1 <= k <= 64");
+    CGNN_CHECK_ARG(k >= 1 && k <= 32, "cgnn_mp_edge_bwd: need 1 <= k <= 32 (got %d)", k);      // the FP32 backward tile holds 32 rows
     MlpTask a{};
     a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.n_nodes = n_nodes; a.k = k; a.L = mlp->out_dim;
     a.h = h; a.e_in = e_in; a.senders = senders; a.de_next = de_next; a.dagg = dagg;
@@ -207,6 +205,7 @@ extern "C" int cgnn_mp_edge_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, 
         if (rc != CGNN_ERR_UNSUPPORTED) return rc;          // the tensor-core path also did the sender scatter
     }
     // FP32 kernels: gs[e] = dIn[:, :L] per edge, then the deterministic scatter over the transpose
+    CGNN_CHECK_ARG(gs != nullptr, "cgnn_mp_edge_bwd: the FP32 kernels need the per-edge scratch `gs` [E][latent]");
     if ((rc = simt_mlp_bwd(a, grad, workspace, workspace_bytes, (cudaStream_t)stream))) return rc;
     return simt_scatter_to_senders(gs, 0, t_rowptr, t_perm, n_nodes, k, mlp->out_dim, dh, (cudaStream_t)stream);
 }

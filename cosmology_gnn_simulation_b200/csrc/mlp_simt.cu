@@ -240,7 +240,7 @@ mlp_fwd_kernel(MlpTask a, int64_t n_tiles) {
             if (a.mode == MODE_ROWS) {
                 a.out[g * N + c] = v;
             } else if (a.mode == MODE_EDGE) {
-                a.out[g * N + c] = a.e_in[g * N + c] + v;       // e' = e + u_e   (graph_network.py:182)
+                if (a.out != nullptr) a.out[g * N + c] = a.e_in[g * N + c] + v;       // e' = e + u_e   (graph_network.py:182)
                 cur[row * AS + c] = v;                          // keep u_e for the segmented sum
             } else {
                 a.out[g * N + c] = a.h[g * N + c] + v;          // h' = h + u_n   (graph_network.py:181)

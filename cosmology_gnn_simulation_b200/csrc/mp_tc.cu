@@ -518,6 +518,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                               : lnb   ? (p.du_recv ? p.du_recv + recvoff : nullptr)
                                       : (p.residual ? p.residual + rowoff : nullptr);
             float* outp = p.out + rowoff;
+            const bool vout = valid && p.out != nullptr;            // the last processor step of a forward has no use for e'
             float* aggp = AGG && p.agg_out ? p.agg_out + recvoff : nullptr;
             // four 16-column chunk buffers per stream, each reloaded four chunks (64 columns) ahead
             float a0[16], a1[16], a2[16], a3[16], b0[16], b1[16], b2[16], b3[16];
@@ -687,7 +688,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                                 o[4 * j] = v[4 * j] + e4.x; o[4 * j + 1] = v[4 * j + 1] + e4.y;
                                 o[4 * j + 2] = v[4 * j + 2] + e4.z; o[4 * j + 3] = v[4 * j + 3] + e4.w;
                             }
-                            if (valid) st16(outp + cc, o);
+                            if (vout) st16(outp + cc, o);
                             if ((cc & 31) == 16) {
                                 // Both halves of the chunk are read: its ring slot goes back to the producer.  The arrival must come
                                 // after an instruction that CONSUMES the loaded values in every lane: shared-memory loads that are only
@@ -702,8 +703,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             // residual: the sum goes out from the stream's own registers, v stays free for the per-receiver sum
 #pragma unroll
                             for (int j = 0; j < 16; ++j) cb[j] += v[j];
-                            if (valid) st16(outp + cc, cb);
-                        } else if (valid) {
+                            if (vout) st16(outp + cc, cb);
+                        } else if (vout) {
                             st16(outp + cc, v);
                         }
                         if (aggp) {
@@ -777,7 +778,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     const int n_in = op.in1 ? 2 : 1;
     const int n_blocks = n_in + op.n_layers - 1;
     CGNN_CHECK_ARG(op.n_layers == 1 || op.n_layers == 3, "tensor-core chain: 1 or 3 layers");
-    CGNN_CHECK_ARG(n_blocks <= MAX_BLOCKS && op.rows >= 1 && op.in0 && op.out, "tensor-core chain: bad arguments");
+    CGNN_CHECK_ARG(n_blocks <= MAX_BLOCKS && op.rows >= 1 && op.in0 && (op.out || op.agg_out), "tensor-core chain: bad arguments");
     const bool gather = op.Ps != nullptr;
     const bool uses_k = gather || op.agg_out || op.du_recv || op.hid_agg[0] || op.hid_agg[1];
     int k = 1, kshift = 0;

@@ -86,6 +86,32 @@ int slice_rows(const float* src, int w, int64_t rows, float* dst, cudaStream_t s
     return CGNN_OK;
 }
 
+// dPs[j] += sum of G1[e - r0] over the out-edges e of sender j with r0 <= e < r1, in perm order (= ascending edge id, so
+// chunk after chunk in ascending r0 adds every row's terms in exactly the order of a one-shot pass: deterministic and
+// independent of the chunk size).  A warp-sized group of threads per node, thread <-> 4 columns.
+__global__ void scatter_chunk_kernel(const float4* __restrict__ G1, int r0, int r1, const int32_t* __restrict__ rowptr,
+                                     const int32_t* __restrict__ perm, int64_t n, float4* __restrict__ dPs) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n * (TC_H / 4)) return;
+    const int64_t j = idx / (TC_H / 4);
+    const int c = (int)(idx - j * (TC_H / 4));
+    const int a = rowptr[j], b = rowptr[j + 1];
+    int lo = a, hi = b;
+    while (lo < hi) {                          // first out-edge of j inside the chunk (rows are ~k long)
+        const int mid = (lo + hi) >> 1;
+        if (perm[mid] < r0) lo = mid + 1; else hi = mid;
+    }
+    if (lo == b || perm[lo] >= r1) return;
+    float4 s = dPs[idx];
+    for (int p = lo; p < b; ++p) {
+        const int e = perm[p];
+        if (e >= r1) break;
+        const float4 v = G1[(int64_t)(e - r0) * (TC_H / 4) + c];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    dPs[idx] = s;
+}
+
 // encoder / decoder MLPs: 3 layers, hidden 128, in <= 128, out <= 128 (LayerNorm only with out == 128)
 bool tc_rows_ok(const MlpDev& m) {
     return m.n_layers == 3 && m.hidden == TC_H && m.in_dim >= 1 && m.in_dim <= TC_H && m.out_dim >= 1 && m.out_dim <= TC_H &&
@@ -404,16 +430,17 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         Scratch sc; sc.carve(cv);
         const int64_t chunk = E < CHUNK_ROWS ? E : CHUNK_ROWS;
         float* A1 = cv.take<float>(chunk * TC_H); float* A2 = cv.take<float>(chunk * TC_H); float* T = cv.take<float>(chunk * TC_H);
-        float* G2 = cv.take<float>(chunk * TC_H); float* spare = cv.take<float>(chunk * TC_H); (void)spare;
+        float* G2 = cv.take<float>(chunk * TC_H); float* G1 = cv.take<float>(chunk * TC_H);
         uint32_t* gate1 = cv.take<uint32_t>(chunk * 4); uint32_t* gate2 = cv.take<uint32_t>(chunk * 4);
         float* Ps = cv.take<float>(nn * TC_H); float* Pr = cv.take<float>(n * TC_H);
         float* dPs = cv.take<float>(nn * TC_H); float* dPr = cv.take<float>(n * TC_H);
         if ((rc = project_nodes(ns, sc, m, a.h, n, nn, Ps, Pr, s))) return rc;
+        // per-node sums of G1 by sender: accumulated chunk by chunk over the sender-sorted transpose (no E-sized buffer)
+        CGNN_CUDA(cudaMemsetAsync(dPs, 0, (size_t)nn * TC_H * 4, s));
         for (int64_t r0 = 0, c = 0; r0 < E; r0 += chunk, ++c) {
             const int64_t rows = E - r0 < chunk ? E - r0 : chunk;       // chunk is a multiple of 256 and of k unless it is the whole graph
             const float* e_in = a.e_in + r0 * TC_H;
             const float* de_next = a.de_next ? a.de_next + r0 * TC_H : nullptr;
-            float* G1 = a.gs + r0 * TC_H;
             const int acc = c > 0;
             // recompute with e W1e^T + Ps[sender] + Pr[receiver] as layer 1; dU = de_next + dagg[receiver];
             // de = de_next + G1 W1e is the dgrad chain's last layer, the per-receiver sum of G1 is d P_r
@@ -424,10 +451,11 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
                                      {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}, de_next, a.de + r0 * TC_H, G1, dPr + (r0 / k) * TC_H, acc, s))) return rc;
             // dW1e = G1^T e, db1
             if ((rc = run_wgrad(ns, G1, e_in, rows, g->W[0], 3 * TC_H, 2 * TC_H, g->b[0], acc, sc.wg, s))) return rc;
+            scatter_chunk_kernel<<<(unsigned)((nn * (TC_H / 4) + 255) / 256), 256, 0, s>>>(
+                reinterpret_cast<const float4*>(G1), (int)r0, (int)(r0 + rows), a.t_rowptr, a.t_perm, nn, reinterpret_cast<float4*>(dPs));
+            CGNN_LAUNCH_CHECK();
         }
-        // per-node sums of G1: by sender (transpose CSR, deterministic) and by receiver (dPr, from the chunks)
-        CGNN_CUDA(cudaMemsetAsync(dPs, 0, (size_t)nn * TC_H * 4, s));
-        if ((rc = simt_scatter_to_senders(a.gs, 0, a.t_rowptr, a.t_perm, nn, a.k, TC_H, dPs, s))) return rc;
+        // (the per-receiver sums dPr came out of the chunks' G1 chains)
         if ((rc = run_wgrad(ns, dPs, a.h, nn, g->W[0], 3 * TC_H, 0, nullptr, 0, sc.wg, s))) return rc;
         if ((rc = run_wgrad(ns, dPr, a.h, n, g->W[0], 3 * TC_H, TC_H, nullptr, 0, sc.wg, s))) return rc;
         if (nn == n) {   // dh += dPs W1s + dPr W1r
@@ -448,7 +476,5 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
     }
     return CGNN_ERR_UNSUPPORTED;
 }
-
-int64_t tc_mlp_bwd_workspace(const cgnn_mlp* mlp) { (void)mlp; return 0; }
 
 }  // namespace cgnn

@@ -25,7 +25,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ckpt_plan, ops
 from .ops import MlpParams
 
 __all__ = ["EncodeProcessDecode", "build_mlp"]
@@ -73,41 +73,47 @@ class _Plan:
     """Static description of one forward call, shared by forward and backward."""
 
     def __init__(self, n_steps, message, precision, k, enc_node, enc_edge, proc_node, proc_edge, dec_acc,
-                 dec_temp, groups, edge_ckpt_every, halo=None):
+                 dec_temp, groups, edge_buffers, halo=None):
         self.halo = halo                      # slab.HaloPlan of a sharded box, or None
         self.n_steps, self.message, self.precision, self.k = n_steps, message, precision, k
         self.enc_node, self.enc_edge = enc_node, enc_edge
         self.proc_node, self.proc_edge = proc_node, proc_edge
         self.dec_acc, self.dec_temp = dec_acc, dec_temp
         self.groups = groups                  # [(MlpParams, first index into the flat parameter list)]
-        self.edge_ckpt_every = edge_ckpt_every
+        self.edge_buffers = edge_buffers      # forced number of edge-stream buffers (0: from the free memory)
         self.grad_enabled = torch.is_grad_enabled()      # sampled where the module is called (autograd runs Function.forward in no-grad mode)
 
 
 _STREAM_PLANS = {}
 
 
-def _edge_stream_plan(n_steps: int, bytes_per_copy: int, device) -> int:
-    """Checkpoint spacing s for the edge latent stream in message="edge" training: keep e^t for
-    t % s == 0 and recompute the rest segment by segment in backward.  Decided once per (steps, stream size,
-    device): cudaMemGetInfo costs ~15 ms of host time per call, far too much for every step."""
-    key = (n_steps, bytes_per_copy, str(device))
-    s = _STREAM_PLANS.get(key)
-    if s is None:
-        s = _STREAM_PLANS[key] = _edge_stream_plan_uncached(n_steps, bytes_per_copy, device)
-    return s
-
-
-def _edge_stream_plan_uncached(n_steps: int, bytes_per_copy: int, device) -> int:
+def _edge_stream_buffers(plan: _Plan, n: int, n_loc: int, e_count: int, L: int, device) -> int:
+    """How many copies of the edge latent stream (E x L x 4 bytes each) message="edge" training may keep next to the
+    gradient stream; ckpt_plan.schedule() turns that into the checkpoint / recompute schedule of the backward.
+    Decided once per (steps, sizes, device): cudaMemGetInfo costs ~15 ms of host time per call, far too much for
+    every step.  The workspaces of the backward are sized first so that the measurement sees them."""
+    M = plan.n_steps
+    if plan.edge_buffers:
+        return min(int(plan.edge_buffers), M)
+    key = (M, n, n_loc, e_count, L, plan.precision, str(device))
+    nbuf = _STREAM_PLANS.get(key)
+    if nbuf is not None:
+        return nbuf
+    copy = e_count * L * 4
+    ops.presize_workspaces(plan.proc_edge[0], plan.enc_edge, n, n_loc, plan.k, e_count, plan.precision, device)
+    if copy >= (1 << 30):
+        torch.cuda.empty_cache()          # large streams: hand cached fragments back before measuring
     free, _ = torch.cuda.mem_get_info(device)
-    budget = int(free * 0.6)
-    for s in range(1, n_steps + 1):
-        copies = (n_steps + s - 1) // s + (s - 1) + 3          # checkpoints + segment + (de, de', gs)
-        if copies * bytes_per_copy <= budget:
-            return s
-    raise RuntimeError(
-        f"cgnn: the edge latent stream does not fit: {bytes_per_copy / 2**30:.1f} GiB per copy, "
-        f"{free / 2**30:.1f} GiB free; shard the box over more GPUs or use message='sender'")
+    free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    # still to come: h^t and agg^t for every step, the node-sized gradients / partial products, the transpose, slack
+    other = (2 * M + 12) * n_loc * L * 4 + 12 * e_count + (1 << 30) + free // 50
+    nbuf = min(M, (free - other) // copy - 1)                  # - 1: the gradient stream de
+    if nbuf < 1:
+        raise RuntimeError(
+            f"cgnn: the edge latent stream does not fit: {copy / 2**30:.1f} GiB per copy, two copies needed, "
+            f"{free / 2**30:.1f} GiB free; shard the box over more GPUs or use message='sender'")
+    _STREAM_PLANS[key] = int(nbuf)
+    return int(nbuf)
 
 
 class _EncodeProcessDecodeFn(torch.autograd.Function):
@@ -118,6 +124,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         p, M, k, prec = plan, plan.n_steps, plan.k, plan.precision
         n, L = x.shape[0], plan.enc_node.out_dim
         e_count = edge_attr.shape[0]
+        dev = x.device
         # (needs_input_grad reflects requires_grad only: under torch.no_grad() nothing will be differentiated)
         train = plan.grad_enabled and any(ctx.needs_input_grad[3:])
         edge_mode = p.message == "edge"
@@ -128,49 +135,85 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         def with_halo(h_own_rows):
             if halo is None:
                 return h_own_rows
-            full = torch.empty((n_loc, L), dtype=torch.float32, device=x.device)
+            full = torch.empty((n_loc, L), dtype=torch.float32, device=dev)
             full[:n] = h_own_rows
             halo.exchange(full)
             return full
 
         h = with_halo(ops.mlp_rows_fwd(p.enc_node, x, prec))
-        e = ops.mlp_rows_fwd(p.enc_edge, edge_attr, prec)
-        hs, aggs, e_ckpt = [h], [], {}
-        keep_e = train and edge_mode
-        s = plan.edge_ckpt_every if keep_e else 0
-        if keep_e and s == 0:
-            s = _edge_stream_plan(M, e_count * L * 4, x.device)
-        if keep_e:
-            e_ckpt[0] = e
-        for t in range(M):
-            agg = torch.empty((n, L), dtype=torch.float32, device=x.device)
-            # e^t is overwritten in place unless it is a checkpoint the backward will need
-            e_next = torch.empty_like(e) if (keep_e and t % s == 0) else e
-            if edge_mode:
-                ops.mp_edge_fwd(p.proc_edge[t], h, e, senders, k, e_next, agg, prec)
-            else:
-                ops.mp_edge_fwd(p.proc_edge[t], h, e, senders, k, e_next, None, prec)
-                ops.aggregate_senders(h, senders, k, agg)
+        hs, aggs = [h], []
+
+        def node_phase(t, h, agg):
             # inference updates h in place: a node tile only reads its own rows of h
             h_next = torch.empty_like(h) if train else h
             ops.mp_node_fwd(p.proc_node[t], h[:n], agg, h_next[:n], prec)
             if halo is not None:
                 halo.exchange(h_next)                       # the one collective of a message-passing step
-            h, e = h_next, e_next
             if train:
-                hs.append(h)
+                hs.append(h_next)
                 aggs.append(agg)
-            if keep_e and (t + 1) % s == 0 and t + 1 < M:
-                e_ckpt[t + 1] = e
+            return h_next
+
+        bufs, acts, pos = None, None, 0
+        if not edge_mode:
+            # What the reference computes (PyG's default message): the receivers sum SENDER latents.  The edge
+            # latents never reach h, the decoders or any gradient, so the edge stream is not computed at all.
+            for t in range(M):
+                agg = torch.empty((n, L), dtype=torch.float32, device=dev)
+                ops.aggregate_senders(h, senders, k, agg)
+                h = node_phase(t, h, agg)
+        elif not train:
+            e = ops.mlp_rows_fwd(p.enc_edge, edge_attr, prec)
+            for t in range(M):
+                agg = torch.empty((n, L), dtype=torch.float32, device=dev)
+                ops.mp_edge_fwd(p.proc_edge[t], h, e, senders, k, e if t + 1 < M else None, agg, prec)   # e^M is never read
+                h = node_phase(t, h, agg)
+            del e
+        else:
+            nbuf = _edge_stream_buffers(p, n, n_loc, e_count, L, dev)
+            acts = ckpt_plan.schedule(M, nbuf)
+            bufs = [None] * nbuf
+            last = None
+            for pos, act in enumerate(acts):
+                if act[0] == "bwd":
+                    last = act[2]
+                    break
+                _EncodeProcessDecodeFn._advance(p, act, bufs, edge_attr, senders, hs, e_count, L, first=True,
+                                                node_phase=node_phase)
+            agg = torch.empty((n, L), dtype=torch.float32, device=dev)
+            ops.mp_edge_fwd(p.proc_edge[M - 1], hs[M - 1], bufs[last], senders, k, None, agg, prec)     # e^M is never read
+            node_phase(M - 1, hs[M - 1], agg)
+            h = hs[M]
         acc = ops.mlp_rows_fwd(p.dec_acc, h[:n], prec)
         temp = ops.mlp_rows_fwd(p.dec_temp, h[:n], prec)
 
         if train:
             ctx.plan, ctx.senders, ctx.transpose_fn = plan, senders, transpose_fn
             ctx.x, ctx.edge_attr = x, edge_attr
-            ctx.hs, ctx.aggs, ctx.e_ckpt, ctx.s = hs, aggs, e_ckpt, s
+            ctx.hs, ctx.aggs, ctx.bufs, ctx.acts, ctx.pos = hs, aggs, bufs, acts, pos
             ctx.n_params = len(params)
         return acc, temp
+
+    @staticmethod
+    def _advance(p, act, bufs, edge_attr, senders, hs, e_count, L, first, node_phase=None):
+        """One "enc" / "adv" action of the checkpoint schedule on the stream buffers."""
+        prec, k = p.precision, p.k
+        if act[0] == "enc":
+            b = act[1]
+            if bufs[b] is None:
+                bufs[b] = torch.empty((e_count, L), dtype=torch.float32, device=edge_attr.device)
+            ops.mlp_rows_fwd(p.enc_edge, edge_attr, prec, out=bufs[b])
+            return
+        _, t, src, dst = act
+        if bufs[dst] is None:
+            bufs[dst] = torch.empty((e_count, L), dtype=torch.float32, device=edge_attr.device)
+        if first:                                           # the real forward of step t
+            h = hs[t]
+            agg = torch.empty((h.shape[0] if p.halo is None else p.halo.n_own, L), dtype=torch.float32, device=h.device)
+            ops.mp_edge_fwd(p.proc_edge[t], h, bufs[src], senders, k, bufs[dst], agg, prec)
+            node_phase(t, h, agg)
+        else:                                               # recompute of the edge phase alone
+            ops.mp_edge_fwd(p.proc_edge[t], hs[t], bufs[src], senders, k, bufs[dst], None, prec)
 
     @staticmethod
     def backward(ctx, d_acc, d_temp):
@@ -202,8 +245,10 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         else:
             dh = torch.zeros((n_loc, L), dtype=torch.float32, device=dh_a.device)
             dh[:n] = dh_a.add_(dh_t)
+        del dh_a, dh_t
         de = None
         rowptr, perm = ctx.transpose_fn()
+        fp32 = prec == "fp32"
 
         def step_backward(t, e_t, dh, de):
             if halo is not None:
@@ -214,8 +259,10 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
             dagg = torch.empty((n, L), dtype=torch.float32, device=dh.device)
             put(p.proc_node[t], ops.mp_node_bwd(p.proc_node[t], hs[t][:n], aggs[t], dh[:n], dh_new[:n], dagg, prec))
             if edge_mode:
-                de_new = torch.empty_like(e_t)
-                gs = torch.empty_like(e_t)
+                # the gradient stream is updated in place (de^t over de^{t+1}); only the FP32 kernels need the per-edge
+                # scratch gs, the tensor-core path accumulates the sender sums chunk by chunk in its workspace
+                de_new = de if de is not None else torch.empty_like(e_t)
+                gs = torch.empty_like(e_t) if fp32 else None
                 put(p.proc_edge[t], ops.mp_edge_bwd(p.proc_edge[t], hs[t], e_t, senders, rowptr, perm, k, de, dagg,
                                                     de_new, dh_new, gs, prec))
                 return dh_new, de_new
@@ -223,20 +270,18 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
             return dh_new, None
 
         if edge_mode:
-            s = ctx.s
-            t = M - 1
-            while t >= 0:
-                a = (t // s) * s
-                seg = {a: ctx.e_ckpt[a]}
-                for u in range(a, t):                         # recompute e^{a+1..t}
-                    nxt = torch.empty_like(seg[u])
-                    ops.mp_edge_fwd(p.proc_edge[u], hs[u], seg[u], senders, k, nxt, None, prec)
-                    seg[u + 1] = nxt
-                for u in range(t, a - 1, -1):
-                    dh, de = step_backward(u, seg[u], dh, de)
-                    seg.pop(u + 1, None)
-                ctx.e_ckpt.pop(a, None)
-                t = a - 1
+            bufs, acts = ctx.bufs, ctx.acts
+            e_count = ctx.edge_attr.shape[0]
+            for act in acts[ctx.pos:]:
+                if act[0] == "bwd":
+                    _, t, b = act
+                    dh, de = step_backward(t, bufs[b], dh, de)
+                    hs[t + 1] = None                         # h^{t+1} and agg^t have had their last reader
+                    aggs[t] = None
+                else:
+                    _EncodeProcessDecodeFn._advance(p, act, bufs, ctx.edge_attr, senders, hs, e_count, L, first=False)
+            for i in range(len(bufs)):
+                bufs[i] = None
         else:
             for t in range(M - 1, -1, -1):
                 dh, de = step_backward(t, None, dh, None)
@@ -250,7 +295,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         if edge_mode:
             g_ee, dea = ops.mlp_rows_bwd(p.enc_edge, ctx.edge_attr, de, need_dea, prec)
             put(p.enc_edge, g_ee)
-        ctx.hs = ctx.aggs = ctx.e_ckpt = None
+        ctx.hs = ctx.aggs = ctx.bufs = None
         return (None, None, None, dx, dea, *grads)
 
 
@@ -265,7 +310,7 @@ class EncodeProcessDecode(nn.Module):
 
     def __init__(self, latent_size: int, mlp_hidden_size: int, mlp_num_hidden_layers: int,
                  num_message_passing_steps: int, output_size: int, *, num_neighbors: Optional[int] = None,
-                 message: str = "sender", precision: str = "fp32", edge_ckpt_every: int = 0):
+                 message: str = "sender", precision: str = "fp32", edge_buffers: int = 0):
         super().__init__()
         if message not in ("sender", "edge"):
             raise ValueError("message must be 'sender' or 'edge'")
@@ -279,7 +324,7 @@ class EncodeProcessDecode(nn.Module):
         self.num_neighbors = num_neighbors
         self.message = message
         self.precision = precision
-        self.edge_ckpt_every = edge_ckpt_every
+        self.edge_buffers = edge_buffers        # message='edge' training: copies of the edge stream to keep (0: from the free memory)
 
         def mlp_ln():
             return nn.Sequential(build_mlp(mlp_hidden_size, mlp_num_hidden_layers, latent_size),
@@ -300,9 +345,9 @@ class EncodeProcessDecode(nn.Module):
         L = self._latent_size
         _materialize(self.encoder.node_model[0], node_in, like)
         _materialize(self.encoder.edge_model[0], edge_in, like)
-        for blk in self.processor:
-            _materialize(blk.node_model[0], 2 * L, like)
+        for blk in self.processor:                          # the reference's first forward reaches edge_model first (graph_network.py:90,96)
             _materialize(blk.edge_model[0], 3 * L, like)
+            _materialize(blk.node_model[0], 2 * L, like)
         _materialize(self.decoder_acc, L, like)
         _materialize(self.decoder_temp_rate, L, like)
 
@@ -366,7 +411,7 @@ class EncodeProcessDecode(nn.Module):
         n = x.shape[0]
         senders, k, transpose = self._graph_tables(input_graph, n)
         plan = _Plan(self._num_message_passing_steps, self.message, self.precision, k, enc_node, enc_edge,
-                     proc_node, proc_edge, dec_acc, dec_temp, groups, self.edge_ckpt_every,
+                     proc_node, proc_edge, dec_acc, dec_temp, groups, self.edge_buffers,
                      halo=getattr(input_graph, "halo", None))
         acc, temp = _EncodeProcessDecodeFn.apply(plan, senders, transpose, x, edge_attr, *flat)
         return {"acceleration": acc, "temp_rate": temp}

@@ -164,9 +164,14 @@ def _bwd_ws(mlp_c: CgnnMlp, device):
 # ------------------------------------------------------------------------------------------------
 # K3/K6 rows, K4/K5 message passing
 # ------------------------------------------------------------------------------------------------
-def mlp_rows_fwd(p: MlpParams, x: torch.Tensor, precision: str = "fp32") -> torch.Tensor:
+def mlp_rows_fwd(p: MlpParams, x: torch.Tensor, precision: str = "fp32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
     require_cuda(x, "x", torch.float32)
-    out = torch.empty((x.shape[0], p.out_dim), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((x.shape[0], p.out_dim), dtype=torch.float32, device=x.device)
+    else:
+        require_cuda(out, "out", torch.float32)
+        if tuple(out.shape) != (x.shape[0], p.out_dim):
+            raise ValueError(f"out must be {(x.shape[0], p.out_dim)}, got {tuple(out.shape)}")
     m = p.c_struct()
     with torch.cuda.device(x.device):
         ws = _rows_ws(m, x.shape[0], precision, 0, x.device)
@@ -231,6 +236,20 @@ def mp_node_fwd(p: MlpParams, h, agg, h_out, precision: str = "fp32"):
               "cgnn_mp_node_fwd")
 
 
+def presize_workspaces(edge_mlp: MlpParams, enc_edge: MlpParams, n: int, n_nodes: int, k: int, n_edges: int, precision: str,
+                        device) -> None:
+    """Grows the shared scratch buffers to what one training application of this size will ask for (edge phase
+    forward / backward, edge encoder forward / backward), so that a memory plan made afterwards sees them."""
+    em, ee = edge_mlp.c_struct(), enc_edge.c_struct()
+    with torch.cuda.device(device):
+        nb = lib().cgnn_mp_edge_fwd_workspace_bytes(byref(em), n_nodes, PREC[precision])
+        if nb > 0:
+            workspace.get(device, "edge_fwd", nb)
+        _mp_bwd_ws(em, n, k, precision, device, n_nodes=n_nodes)
+        _rows_ws(ee, n_edges, precision, 1, device)
+        _rows_ws(ee, n_edges, precision, 0, device)
+
+
 def _mp_bwd_ws(mlp_c: CgnnMlp, n: int, k: int, precision: str, device, n_nodes=None):
     nbytes = lib().cgnn_mp_bwd_workspace_bytes(byref(mlp_c), n, n if n_nodes is None else n_nodes, k, PREC[precision])
     if nbytes < 0:
@@ -252,7 +271,8 @@ def mp_node_bwd(p: MlpParams, h, agg, dh_next, dh, dagg, precision: str = "fp32"
 def mp_edge_bwd(p: MlpParams, h, e_in, senders, rowptr, perm, k: int, de_next, dagg, de, dh, gs,
                 precision: str = "fp32"):
     """Edge-phase backward including the deterministic scatter of the sender gradients into `dh`
-    (`rowptr`, `perm`: sender-sorted transpose from `csr_transpose`); `gs` [E,L] is scratch."""
+    (`rowptr`, `perm`: sender-sorted transpose from `csr_transpose`).  `de` may be `de_next` (in place); `gs` [E,L] is
+    the scratch of the FP32 kernels (None for the tensor-core precisions)."""
     m = p.c_struct()
     g, grads = p.new_grads()
     n_recv = e_in.shape[0] // k

@@ -3,8 +3,17 @@
 `FusedAdam` does what the reference's `torch.optim.Adam(simulator.parameters(), lr, weight_decay)` +
 `ExponentialLR(optimizer, gamma)` do (train.py:183-187, 263-265, 316), in ONE kernel launch per step for the whole
 model: the parameters are re-pointed at views of one flat FP32 buffer (so a single pass covers all ~110 tensors),
-the gradients are gathered into a flat buffer with one multi-tensor copy — the same buffer the gradient all-reduce
-of `distributed.GradientBucket` uses — and `cgnn_adam_step` (csrc/optim.cu) updates parameters and both moments.
+the gradients are gathered into a flat buffer with one multi-tensor copy and `cgnn_adam_step_masked`
+(csrc/optim.cu) updates parameters and both moments.
+
+* Parameters whose `.grad` is None (the dead edge stream of `message="sender"`) are skipped entirely -- no weight
+  decay, no moment update -- as `torch.optim.Adam` does.
+* `step_overlapped` is the multi-GPU form: the flat gradient is all-reduced in buckets and the update of bucket i
+  runs while bucket i+1 is still in flight (the collective is the only one of the training path).
+* `state_dict()` / `load_state_dict()` use `torch.optim.Adam`'s layout (per-parameter `step`, `exp_avg`,
+  `exp_avg_sq`), so either optimizer resumes from the other's checkpoint; `save_training_state` /
+  `load_training_state` add what the reference's checkpoints lack for a true resume (train.py:329-351 saves the
+  model weights only): optimizer, scheduler, epoch and the RNG streams `preprocess` draws its noise from.
 """
 from __future__ import annotations
 
@@ -34,7 +43,8 @@ class FusedAdam:
         self.sizes = [p.numel() for p in self.params]
         n = sum(self.sizes)
         self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        # parameters become views of the flat buffer (values preserved); state_dict / load_state_dict keep working
+        # parameters become views of the flat buffer (values preserved); state_dict / load_state_dict keep working.
+        # Build the optimizer BEFORE capturing a GraphedTrainStep (a captured step notices moved parameters and recaptures).
         off = 0
         with torch.no_grad():
             for p, sz in zip(self.params, self.sizes):
@@ -45,6 +55,8 @@ class FusedAdam:
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.live = torch.ones(n, dtype=torch.float32, device=dev)         # 0 where a parameter has no gradient
+        self._live_key = None
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self.params:
@@ -54,15 +66,26 @@ class FusedAdam:
                 p.grad.zero_()
 
     def gather_grads(self) -> torch.Tensor:
-        """Copies every `.grad` into the flat gradient buffer (zeros where a parameter got no gradient: the dead edge
-        stream in message='sender' mode) and returns it — the buffer to all-reduce when training on several GPUs."""
+        """Copies every `.grad` into the flat gradient buffer and returns it -- the buffer to all-reduce when
+        training on several GPUs.  Parameters without a gradient are masked out of the update."""
         views = list(torch.split(self.grad, self.sizes))
+        has = tuple(p.grad is not None for p in self.params)
+        if has != self._live_key:                        # (re)build the mask only when the set of live parameters changes
+            for v, h in zip(torch.split(self.live, self.sizes), has):
+                v.fill_(1.0 if h else 0.0)
+            self._live_key = has
         live = [(v, p.grad.reshape(-1)) for v, p in zip(views, self.params) if p.grad is not None]
-        if len(live) != len(self.params):
-            self.grad.zero_()
         if live:
             torch._foreach_copy_([a for a, _ in live], [b for _, b in live])
         return self.grad
+
+    def _launch(self, lo: int, hi: int, grad_scale: float) -> None:
+        sl = slice(lo, hi)
+        mask = None if all(self._live_key or (True,)) else self.live[sl]
+        with torch.cuda.device(self.flat.device):
+            check(lib().cgnn_adam_step_masked(ptr(self.flat[sl]), ptr(self.grad[sl]), ptr(self.exp_avg[sl]), ptr(self.exp_avg_sq[sl]),
+                                              ptr(mask), hi - lo, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                              self.step_count, float(grad_scale), stream_ptr(self.flat.device)), "cgnn_adam_step")
 
     def step(self, grad_scale: float = 1.0, gathered: bool = False) -> None:
         """One Adam update with the current `lr`.  `gathered=True`: the flat gradient buffer already holds the
@@ -70,10 +93,57 @@ class FusedAdam:
         if not gathered:
             self.gather_grads()
         self.step_count += 1
-        with torch.cuda.device(self.flat.device):
-            check(lib().cgnn_adam_step(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.flat.numel(),
-                                       self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
-                                       float(grad_scale), stream_ptr(self.flat.device)), "cgnn_adam_step")
+        self._launch(0, self.flat.numel(), grad_scale)
+
+    def step_overlapped(self, group=None, n_buckets: int = 4, average: bool = False) -> None:
+        """Multi-GPU step: gathers the gradients, all-reduces (SUM) the flat buffer in `n_buckets` slices issued back to
+        back on the communication stream, and updates each slice as soon as ITS reduction has landed -- the update of
+        bucket i overlaps the reduction of bucket i+1.  `average` folds 1/world into the update (replica training);
+        slab training sums (every rank holds a partial gradient of one global loss)."""
+        import torch.distributed as dist
+        self.gather_grads()
+        self.step_count += 1
+        n = self.flat.numel()
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            self._launch(0, n, 1.0)
+            return
+        per = -(-n // max(1, n_buckets))
+        per = -(-per // 4) * 4                            # slices stay 16-byte aligned
+        bounds = list(range(0, n, per)) + [n]
+        works = [dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True)
+                 for a, b in zip(bounds[:-1], bounds[1:])]
+        scale = 1.0 / world if average else 1.0
+        for (a, b), w in zip(zip(bounds[:-1], bounds[1:]), works):
+            w.wait()                                      # the current stream waits for this bucket only
+            self._launch(a, b, scale)
+
+    # -- checkpoint / resume (torch.optim.Adam layout) ---------------------------------------------------------------
+    def state_dict(self) -> dict:
+        state = {}
+        if self.step_count > 0:
+            for i, (m, v, p) in enumerate(zip(torch.split(self.exp_avg, self.sizes), torch.split(self.exp_avg_sq, self.sizes), self.params)):
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": m.view_as(p).clone(), "exp_avg_sq": v.view_as(p).clone()}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        group = sd["param_groups"][0]
+        if len(group["params"]) != len(self.params):
+            raise ValueError(f"optimizer state has {len(group['params'])} parameters, the model {len(self.params)}")
+        self.lr = float(group["lr"])
+        self.betas = (float(group["betas"][0]), float(group["betas"][1]))
+        self.eps, self.weight_decay = float(group["eps"]), float(group["weight_decay"])
+        steps = [int(float(st["step"])) for st in sd["state"].values()]
+        self.step_count = max(steps) if steps else 0
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for i, (m, v) in enumerate(zip(torch.split(self.exp_avg, self.sizes), torch.split(self.exp_avg_sq, self.sizes))):
+            st = sd["state"].get(i)
+            if st is not None:
+                m.copy_(st["exp_avg"].reshape(-1))
+                v.copy_(st["exp_avg_sq"].reshape(-1))
 
 
 class ExponentialLR:
@@ -90,3 +160,35 @@ class ExponentialLR:
 
     def get_last_lr(self):
         return [self.optimizer.lr]
+
+    def state_dict(self) -> dict:
+        return {"gamma": self.gamma, "base_lrs": [self.base_lr], "last_epoch": self.last_epoch, "_last_lr": [self.optimizer.lr]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.gamma, self.base_lr, self.last_epoch = float(sd["gamma"]), float(sd["base_lrs"][0]), int(sd["last_epoch"])
+        self.optimizer.lr = self.base_lr * self.gamma ** self.last_epoch
+
+
+def save_training_state(path: str, model: torch.nn.Module, optimizer, scheduler=None, epoch: int = 0, extra: Optional[dict] = None) -> None:
+    """Everything a bit-exact resume needs.  The reference saves `simulator.state_dict()` only (train.py:329-351), so a
+    restarted run loses the Adam moments, restarts the learning-rate schedule and redraws the noise."""
+    state = {"model": model.state_dict(), "optimizer": optimizer.state_dict(),
+             "scheduler": None if scheduler is None else scheduler.state_dict(), "epoch": int(epoch),
+             "rng_cpu": torch.get_rng_state(),
+             "rng_cuda": torch.cuda.get_rng_state_all() if torch.cuda.is_available() else None,
+             "extra": extra or {}}
+    torch.save(state, path)
+
+
+def load_training_state(path: str, model: torch.nn.Module, optimizer, scheduler=None, map_location=None) -> dict:
+    """Restores what `save_training_state` wrote; returns {'epoch', 'extra'}.  The model's lazy layers must be
+    materialised (one forward) and the optimizer built over them first."""
+    state = torch.load(path, map_location=map_location, weights_only=False)
+    model.load_state_dict(state["model"])
+    optimizer.load_state_dict(state["optimizer"])
+    if scheduler is not None and state.get("scheduler") is not None:
+        scheduler.load_state_dict(state["scheduler"])
+    torch.set_rng_state(state["rng_cpu"].cpu() if torch.is_tensor(state["rng_cpu"]) else state["rng_cpu"])
+    if state.get("rng_cuda") is not None and torch.cuda.is_available():
+        torch.cuda.set_rng_state_all([s.cpu() for s in state["rng_cuda"]])
+    return {"epoch": state["epoch"], "extra": state.get("extra", {})}

@@ -137,7 +137,8 @@ int cgnn_mlp_rows_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const floa
 /* ---------------------------------------------------------------------------------------------
  * K4  one message-passing step, forward -- InteractionNetwork.forward + the residuals,
  *     graph_network.py:83-101,177-183.
- *  edge phase:  u_e = LN(MLP_e([h[s_e] | h[r_e] | e]));  e_out = e + u_e;
+ *  edge phase:  u_e = LN(MLP_e([h[s_e] | h[r_e] | e]));  e_out = e + u_e  (e_out may alias e_in: in place; NULL
+ *               skips the store -- the last step's e' is never read, graph_network.py:177-183);
  *               agg_edge[i] = sum over the k in-edges of i of u_e (rank order), or NULL to skip
  *  sender aggregation (reference-actual message): agg[i] = sum_r h[senders[i*k+r]]
  *  node phase:  u_n = LN(MLP_n([h | agg]));  h_out = h + u_n
@@ -164,8 +165,10 @@ int cgnn_mp_node_fwd(const cgnn_mlp* node_mlp, const float* h, const float* agg,
  *  edge phase (message = edge): given de_next = dL/de^{t+1} (NULL = zero) and dagg:
  *      dU = de_next + dagg[receiver];  de = de_next + dIn[:, 2L:];
  *      dh[receiver] += sum_rank dIn[:, L:2L];  dh[sender] += dIn[:, :L] summed over the sender-sorted
- *      transpose (t_rowptr, t_perm from cgnn_csr_transpose; fixed order, no atomics).  gs[E][L] is
- *      scratch for the per-edge sender gradient.
+ *      transpose (t_rowptr, t_perm from cgnn_csr_transpose; fixed order, no atomics).  `de` may alias
+ *      `de_next` (the gradient stream is updated in place).  gs[E][L] is scratch for the per-edge sender
+ *      gradient of the FP32 kernels; the tensor-core precisions accumulate it chunk by chunk inside their
+ *      workspace and take gs = NULL (no E-sized scratch: what lets 2 M particles, k = 32 fit one GPU).
  *  cgnn_scatter_to_senders: dh[j] += sum over edges e with sender j (perm order) of src[e] (stride L)
  *      or of src[e / k] (src_is_per_receiver: message = sender, where src = dagg).
  */
@@ -205,6 +208,13 @@ int cgnn_loss_fwd_bwd(const float* acc, const float* temp, const float* y_acc, c
 int cgnn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                    cgnn_stream stream);
+/* The same with a mask `live[n]` (NULL = all live): entries whose mask is 0 are left untouched -- parameter, both
+ * moments, no weight decay -- as torch.optim.Adam does for parameters whose .grad is None (the dead edge stream
+ * of the reference's actual message semantics).  Works on any 16-byte aligned slice of the flat buffers, which is
+ * what lets the step of one gradient bucket run while the next bucket is still being all-reduced. */
+int cgnn_adam_step_masked(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* live,
+                          int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                          float grad_scale, cgnn_stream stream);
 
 #ifdef __cplusplus
 }

@@ -118,21 +118,30 @@ def mlp_ln(params, prefix: str, z, n_hidden: int):
 
 def forward(params: Dict[str, torch.Tensor], x: torch.Tensor, edge_index: torch.Tensor,
             edge_attr: torch.Tensor, n_hidden: int, n_steps: int, message: str = "sender",
-            return_latents: bool = False):
-    """`EncodeProcessDecode.forward` (graph_network.py:154-164)."""
+            return_latents: bool = False, checkpoint_steps: bool = False):
+    """`EncodeProcessDecode.forward` (graph_network.py:154-164).  `checkpoint_steps` re-runs every processor
+    step in backward instead of keeping its activations (same arithmetic, same gradients): what lets the float64
+    oracle of a 32 768-particle box fit the host memory."""
     assert message in ("sender", "edge")
     src, dst = edge_index[0], edge_index[1]
     h = mlp_ln(params, "encoder.node_model", x, n_hidden)            # :54
     e = mlp_ln(params, "encoder.edge_model", edge_attr, n_hidden)    # :57
-    for t in range(n_steps):
+
+    def step(t, h, e):
         edge_in = torch.cat([h[src], h[dst], e], dim=-1)             # :89  sender, receiver, edge
         u_e = mlp_ln(params, f"processor.{t}.edge_model", edge_in, n_hidden)  # :90
         msg = h[src] if message == "sender" else u_e                 # :92 (see module docstring)
         agg = torch.zeros_like(h).index_add_(0, dst, msg)
         node_in = torch.cat([h, agg], dim=-1)                        # :94
         u_n = mlp_ln(params, f"processor.{t}.node_model", node_in, n_hidden)  # :96
-        h = h + u_n                                                  # :181
-        e = e + u_e                                                  # :182
+        return h + u_n, e + u_e                                      # :181, :182
+
+    for t in range(n_steps):
+        if checkpoint_steps:
+            from torch.utils.checkpoint import checkpoint
+            h, e = checkpoint(step, t, h, e, use_reentrant=False)
+        else:
+            h, e = step(t, h, e)
     acc = mlp(params, "decoder_acc", h, n_hidden)                    # :158
     temp_rate = mlp(params, "decoder_temp_rate", h, n_hidden)        # :159
     out = {"acceleration": acc, "temp_rate": temp_rate}

@@ -24,7 +24,7 @@ def test_graphed_step_equals_eager(message, precision):
         graphs.append(preprocess(box["Coordinates"][:5], box["InternalEnergy"][:5], md, box["Coordinates"][5:6],
                                  box["InternalEnergy"][5:6], num_neighbors=k, dt=md["dt"], box_size=md["box_size"], device=dev))
     torch.manual_seed(0)
-    model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision, edge_ckpt_every=1).to(dev)
+    model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision).to(dev)
     model(graphs[0])                                   # materialise the lazy layers (no backward yet)
     eager = copy.deepcopy(model)
 

@@ -111,3 +111,31 @@ def test_bench_work_model_matches_survey_table():
     assert abs(bench.flops_application(128 ** 3, 32, 128, 10, "edge") / 1e12 - 352.8) < 0.5
     s = bench.phase_work(32768, 16, 128, 10, "sender")
     assert abs((s["forward"][0] + s["backward"][0]) - bench.flops_application(32768, 16, 128, 10, "sender")) < 1e-6 * flop
+
+
+def test_edge_stream_schedule_is_valid_and_minimal():
+    """ckpt_plan.schedule: every step's backward sees e^t, buffers stay within the budget, nothing is recomputed when all
+    copies fit, and the recompute count matches the dynamic programme's optimum for the sizes the configs use."""
+    from cosmology_gnn_simulation_b200 import ckpt_plan
+    for M in (1, 2, 5, 10, 15):
+        for nbuf in (1, 2, 3, 4, M, M + 3):
+            acts = ckpt_plan.schedule(M, nbuf)
+            held, done, first = {}, [], ckpt_plan.split_forward(acts)
+            for i, a in enumerate(acts):
+                if a[0] == "enc":
+                    held[a[1]] = 0
+                elif a[0] == "adv":
+                    _, t, src, dst = a
+                    assert held[src] == t and dst < nbuf
+                    held[dst] = t + 1
+                else:
+                    _, t, b = a
+                    assert i >= first and held.pop(b) == t
+                    done.append(t)
+            assert done == list(range(M - 1, -1, -1))
+            # the forward sweep visits every step below M-1 exactly once, in order
+            assert [a[1] for a in acts[:first] if a[0] == "adv"] == list(range(M - 1))
+            if nbuf >= M:
+                assert ckpt_plan.recomputed_phases(acts) == 0.0
+    assert ckpt_plan.recomputed_phases(ckpt_plan.schedule(10, 2)) == 12.5
+    assert ckpt_plan.recomputed_phases(ckpt_plan.schedule(10, 3)) == 7.0
