@@ -444,6 +444,7 @@ def run_gpu(args):
         "graph_build": None if knn_ms is None else {"ms": knn_ms, "particles_per_s": n_pos / (knn_ms * 1e-3),
                                                     "what": "cgnn_knn_periodic + cgnn_edge_features, device resident"},
         "loss_check": [float(v) for v in last],
+        "peak_memory_gib": torch.cuda.max_memory_allocated(dev) / 2**30,
     }
     if message == "edge" and precision != "fp32":
         from cosmology_gnn_simulation_b200 import graph_network as gn
@@ -500,8 +501,8 @@ def cpu_baseline_leg(k, L, M, n, message, precision, dev):
             "sample": f"oracle port (message='{message}'), {r['sample_n']} of {n} particles per step, "
                       f"k={k}, L={L}, M={M}, fwd+loss+bwd, 1 warm-up + 2 timed steps; k-NN oracle "
                       f"(KD-tree on 27N ghosts, 1 thread) {r['knn_rate']:.3g} particles/s",
-            "parity_on_sample": {"loss_cuda": float(ls["loss"]), "loss_oracle_fp32": float(s["loss"]),
-                                 "loss_rel": abs(float(ls["loss"]) - float(s["loss"])) / abs(float(s["loss"])),
+            "parity_on_sample": {"loss_cuda": float(ls["loss"].detach()), "loss_oracle_fp32": float(s["loss"]),
+                                 "loss_rel": abs(float(ls["loss"].detach()) - float(s["loss"])) / abs(float(s["loss"])),
                                  "acceleration_rel_l2": rel(pred["acceleration"], s["acc"]),
                                  "temp_rate_rel_l2": rel(pred["temp_rate"], s["temp"]),
                                  "worst_gradient_rel_l2": grad_err,

@@ -43,6 +43,8 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p]),
     "cgnn_edge_features": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
+    "cgnn_preprocess_features": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_float,
+                                         POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cgnn_csr_transpose_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "cgnn_csr_transpose": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "cgnn_edge_index_to_senders": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),

@@ -4,7 +4,8 @@
 What changed underneath: the 27N ghost extension + `torch_cluster.knn` KD-tree (data_utils.py:148-149,
 CPU, single thread) is replaced by the sm_100a cell-list kernel (`csrc/knn.cu`), and the index
 remap / edge-feature gathers (data_utils.py:150-164) by one kernel (`csrc/graph.cu`).  The
-feature/target arithmetic is kept as torch ops in the reference's order so it stays bit-compatible.
+feature/target arithmetic (wrap, minimum-image velocities, normalisation, flattening, targets) is one kernel
+(`csrc/features.cu`) that performs the reference's float32 operations one by one, bit-identically.
 
 The returned graph lives on the CUDA device (a later `.to(device)` is a no-op).  There is no CPU
 fallback: without a CUDA device `preprocess` raises.
@@ -74,54 +75,83 @@ def _cuda_device(device):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _scalar(metadata, key) -> float:
+    """A metadata statistic as the float32 the reference's `torch.tensor(metadata[key], dtype=float32)` holds
+    (scalars or 1-element lists, generate_metadata.py:32-43)."""
+    v = metadata[key]
+    while isinstance(v, (list, tuple)):
+        if len(v) != 1:
+            raise ValueError(f"metadata[{key!r}] must be a scalar or a 1-element list")
+        v = v[0]
+    return float(torch.tensor(float(v), dtype=torch.float32))
+
+
+def _noise(position_seq_nw, temperature_seq_nw, metadata, noise_std, dt, box_size):
+    """The two random-walk noises (data_utils.py:36-70), drawn from the generator of the INPUT's device in the
+    reference's order.  With noise_std == 0 the noise is identically zero but the reference still draws: the
+    generator is advanced by the same two draws and no noise array is produced (None, None)."""
+    if noise_std == 0:
+        # the same `randn_like` calls on tensors of the same shape AND memory layout as the reference's velocity / rate
+        # sequences (a generator fills a permuted tensor differently from a contiguous one)
+        torch.randn_like(position_seq_nw[:, 1:] - position_seq_nw[:, :-1], dtype=torch.float32)
+        torch.randn_like(temperature_seq_nw[:, 1:] - temperature_seq_nw[:, :-1], dtype=torch.float32)
+        return None, None
+    rate_std = torch.tensor(metadata["temp_rate_std"], dtype=torch.float32, device=position_seq_nw.device)
+    pos_noise = generate_position_noise(position_seq_nw, noise_std, box_size, dt)
+    temp_noise = generate_temperature_noise(temperature_seq_nw, noise_std, rate_std, dt)
+    return pos_noise, temp_noise
+
+
 def _features_and_targets(position_seq, temperature_seq, metadata, target_position, target_temperature, noise_std, dt,
-                          box_size):
-    """Node features and normalised targets of one sample, in the reference's order of operations
-    (data_utils.py:86-145,166-214).  Returns (recent_pos [N,3], x [N,F], y_acc | None, y_temp | None)."""
-    def md(key):
-        return torch.tensor(metadata[key], dtype=torch.float32, device=position_seq.device)
-
-    pos = position_seq.float().permute(1, 0, 2)                                  # [N,W,3]
+                          box_size, dev):
+    """Node features and normalised targets of one sample (data_utils.py:86-145,166-214) by ONE kernel launch
+    (`cgnn_preprocess_features`, csrc/features.cu): bit-identical to the reference's CPU arithmetic.
+    Returns device tensors (recent_pos [N,3], x [N,F], y_acc [N,3] | None, y_temp [N,1] | None)."""
+    from ctypes import c_float
+    from ._lib import check, lib, ptr, stream_ptr
+    pos = position_seq.float()                                                   # [W,N,3], time-major
+    w, n = pos.shape[0], pos.shape[1]
     temp = temperature_seq.float()
-    if temp.shape[0] == pos.shape[1] and temp.shape[1] == pos.shape[0]:
-        temp = temp.permute(1, 0, 2)                                             # [N,W,1]
+    if temp.shape[0] == w and temp.shape[1] == n:                                # the reference permutes exactly in this case (:87-88)
+        temp_wn = temp.reshape(w, n)
+    else:                                                                        # already [N,W,1]
+        temp_wn = temp.reshape(n, w).t()
+    pos_noise, temp_noise = _noise(pos.permute(1, 0, 2), temp_wn.t().unsqueeze(-1), metadata, float(noise_std), dt, box_size)
 
-    pos_noise = generate_position_noise(pos, noise_std, box_size, dt)
-    pos = torch.remainder(pos + pos_noise, box_size)
-    temp_noise = generate_temperature_noise(temp, noise_std, md("temp_rate_std"), dt)
-    temp = temp + temp_noise
+    def to_dev(t):
+        return None if t is None else t.to(dev, non_blocking=True).contiguous()
 
-    recent_pos = pos[:, -1]
-    velocity = _wrap_displacement_(pos[:, 1:] - pos[:, :-1], box_size) / dt
-    recent_temp = temp[:, -1]
-    n = recent_pos.shape[0]
-
-    vel_feat = ((velocity - md("vel_mean")) / md("vel_std")).reshape(n, -1)
-    temp_feat = ((temp - md("temp_mean")) / md("temp_std")).reshape(n, -1)
-    x = torch.cat((vel_feat, temp_feat), dim=-1).float()
-
-    y_acc = None
+    tp = tt = None
     if target_position is not None:
         tp = target_position.float()
         if tp.dim() == 3:
             tp = tp.permute(1, 0, 2).squeeze(1)
         elif tp.dim() == 2 and tp.shape[0] != n:
             tp = tp.reshape(-1, 3)
-        tp += pos_noise[:, -1]                       # in place, like the reference (data_utils.py:182)
-        next_vel = _wrap_displacement_(tp - recent_pos, box_size) / dt
-        y_acc = (((next_vel - velocity[:, -1]) / dt - md("acc_mean")) / md("acc_std")).float()
-
-    y_temp = None
     if target_temperature is not None:
         tt = target_temperature.float()
         if tt.dim() == 3:
             tt = tt.permute(1, 0, 2).squeeze(1)
-        elif tt.dim() == 2 and tt.shape[1] != 1:
-            tt = tt.reshape(-1, 1)
-        if tt.shape != recent_temp.shape and tt.numel() == recent_temp.numel():
-            tt = tt.reshape(recent_temp.shape)
-        tt += temp_noise[:, -1]                      # in place (data_utils.py:206)
-        y_temp = (((tt - recent_temp) / dt - md("temp_rate_mean")) / md("temp_rate_std")).float()
+        tt = tt.reshape(n, 1) if tt.numel() == n else tt
+    pos_d, temp_d, pn_d, tn_d, tp_d, tt_d = (to_dev(t) for t in (pos, temp_wn, pos_noise, temp_noise, tp, tt))
+    f = 3 * (w - 1) + w
+    recent_pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    x = torch.empty((n, f), dtype=torch.float32, device=dev)
+    y_acc = torch.empty((n, 3), dtype=torch.float32, device=dev) if tp is not None else None
+    y_temp = torch.empty((n, 1), dtype=torch.float32, device=dev) if tt is not None else None
+    stats = (c_float * 8)(*[_scalar(metadata, k) for k in ("vel_mean", "vel_std", "temp_mean", "temp_std", "acc_mean", "acc_std",
+                                                           "temp_rate_mean", "temp_rate_std")])
+    with torch.cuda.device(dev):
+        check(lib().cgnn_preprocess_features(ptr(pos_d), ptr(temp_d), ptr(pn_d), ptr(tn_d), ptr(tp_d), ptr(tt_d), n, w, float(box_size),
+                                             float(dt), stats, ptr(recent_pos), ptr(x), ptr(y_acc), ptr(y_temp), stream_ptr(dev)),
+              "cgnn_preprocess_features")
+    if pos_noise is not None:
+        # the reference adds the last noise frame to the caller's target tensors in place (data_utils.py:182,206);
+        # done after the launch, so a target that already lives on the device is read un-noised by the kernel
+        if tp is not None:
+            tp += pos_noise[:, -1].to(tp.device)
+        if tt is not None:
+            tt += temp_noise[:, -1].to(tt.device)
     return recent_pos, x, y_acc, y_temp
 
 
@@ -138,22 +168,19 @@ def preprocess(position_seq, temperature_seq, metadata, target_position=None, ta
     box_size = float(box_size)
     dev = _cuda_device(device if device is not None else (position_seq.device if position_seq.is_cuda else None))
     recent_pos, x, y_acc, y_temp = _features_and_targets(position_seq, temperature_seq, metadata, target_position,
-                                                         target_temperature, noise_std, dt, box_size)
+                                                         target_temperature, noise_std, dt, box_size, dev)
     n = recent_pos.shape[0]
 
     # ---- graph: cell-list k-NN + edge features on the GPU --------------------------------------
-    pos_dev = recent_pos.contiguous().to(dev, non_blocking=True)
+    pos_dev = recent_pos
     if n * 27 < num_neighbors:
         raise ValueError(f"num_neighbors={num_neighbors} exceeds the 27*N={27 * n} periodic candidates")
     nbr_ext = ops.knn_periodic(pos_dev, box_size, int(num_neighbors))
     senders, edge_index, edge_attr = ops.edge_features(pos_dev, nbr_ext, box_size, disp=edge_disp)
     assert edge_index.shape[1] == n * num_neighbors
 
-    def mv(t):
-        return None if t is None else t.contiguous().to(dev, non_blocking=True)
-
     graph = Data(
-        x=mv(x), edge_index=edge_index, edge_attr=edge_attr, y_acc=mv(y_acc), y_temp_rate=mv(y_temp),
+        x=x, edge_index=edge_index, edge_attr=edge_attr, y_acc=y_acc, y_temp_rate=y_temp,
         pos=pos_dev, dt=torch.tensor([dt], dtype=torch.float32, device=dev),
         box_size=torch.tensor([box_size], dtype=torch.float32, device=dev),
     )
@@ -176,11 +203,11 @@ def preprocess_slab(position_seq, temperature_seq, metadata, target_position=Non
     box_size = float(box_size)
     dev = _cuda_device(device if device is not None else (position_seq.device if position_seq.is_cuda else None))
     recent_pos, x, y_acc, y_temp = _features_and_targets(position_seq, temperature_seq, metadata, target_position,
-                                                         target_temperature, noise_std, dt, box_size)
+                                                         target_temperature, noise_std, dt, box_size, dev)
     n = recent_pos.shape[0]
     if n * 27 < num_neighbors:
         raise ValueError(f"num_neighbors={num_neighbors} exceeds the 27*N={27 * n} periodic candidates")
-    pos_dev = recent_pos.contiguous().to(dev, non_blocking=True)
+    pos_dev = recent_pos
     order = torch.sort(pos_dev[:, 0], stable=True)[1]                 # identical on every rank (same data)
     pos_sorted = pos_dev[order].contiguous()
     bounds = _slab.slab_bounds(n, world)

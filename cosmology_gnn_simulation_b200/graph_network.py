@@ -20,6 +20,7 @@ CPU or PyTorch fallback: CPU inputs raise.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -93,8 +94,9 @@ def _edge_stream_buffers(plan: _Plan, n: int, n_loc: int, e_count: int, L: int, 
     Decided once per (steps, sizes, device): cudaMemGetInfo costs ~15 ms of host time per call, far too much for
     every step.  The workspaces of the backward are sized first so that the measurement sees them."""
     M = plan.n_steps
-    if plan.edge_buffers:
-        return min(int(plan.edge_buffers), M)
+    forced = plan.edge_buffers or int(os.environ.get("CGNN_EDGE_BUFFERS", "0"))
+    if forced:
+        return min(int(forced), M)
     key = (M, n, n_loc, e_count, L, plan.precision, str(device))
     nbuf = _STREAM_PLANS.get(key)
     if nbuf is not None:
@@ -304,14 +306,18 @@ class EncodeProcessDecode(nn.Module):
 
     Constructor arguments as the reference; the keyword-only extras select kernel behaviour:
       num_neighbors  optional hint (k is otherwise read from the graph: E / N)
-      message        "sender" (reference-actual, default) | "edge" (intended Interaction Network)
-      precision      "fp32" (FP32 SIMT, <= 1e-5 parity) | "bf16x3" | "bf16" (tcgen05 tensor cores)
+      message        "sender" (reference-actual, default) | "edge" (intended Interaction Network); env CGNN_MESSAGE
+      precision      "fp32" (FP32 SIMT, <= 1e-5 parity, default) | "bf16x3" | "bf16" (tcgen05 tensor cores); env CGNN_PRECISION
+      edge_buffers   message="edge" training: copies of the edge stream kept for the backward (0 = from the free memory)
     """
 
     def __init__(self, latent_size: int, mlp_hidden_size: int, mlp_num_hidden_layers: int,
                  num_message_passing_steps: int, output_size: int, *, num_neighbors: Optional[int] = None,
-                 message: str = "sender", precision: str = "fp32", edge_buffers: int = 0):
+                 message: Optional[str] = None, precision: Optional[str] = None, edge_buffers: int = 0):
         super().__init__()
+        # the reference's scripts construct the model with its five arguments only: the environment chooses for them
+        message = message if message is not None else os.environ.get("CGNN_MESSAGE", "sender")
+        precision = precision if precision is not None else os.environ.get("CGNN_PRECISION", "fp32")
         if message not in ("sender", "edge"):
             raise ValueError("message must be 'sender' or 'edge'")
         if precision not in ops.PREC:

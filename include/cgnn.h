@@ -108,6 +108,19 @@ int cgnn_edge_features_range(const float* pos, const int32_t* nbr_ext, int64_t n
                              int32_t disp_mode, int64_t q0, int64_t nq, int32_t* senders, int64_t* edge_index,
                              float* edge_attr, cgnn_stream stream);
 
+/* Node features and normalised targets of one sample in one launch -- data_utils.py:86-145,166-214: wrap the W frames
+ * into the box (torch.remainder), minimum-image frame differences / dt, normalise, flatten (velocities time-major then
+ * xyz, then the W temperatures) into x[N][3(W-1)+W]; recent_pos[N][3] = the wrapped last frame (the k-NN input);
+ * optional targets -> y_acc[N][3], y_temp[N].  Single IEEE float32 operations in the reference's order: bit-identical
+ * to the reference's CPU tensor arithmetic.  pos_seq[W][N][3], temp_seq[W][N] time-major; pos_noise[N][W][3] /
+ * temp_noise[N][W] are the random-walk noise of data_utils.py:36-70 (NULL = none; the draws stay with the caller's
+ * torch generator); stats[8] = vel_mean, vel_std, temp_mean, temp_std, acc_mean, acc_std, temp_rate_mean,
+ * temp_rate_std (host array, the metadata JSON of generate_metadata.py:32-43 rounded to float32). */
+int cgnn_preprocess_features(const float* pos_seq, const float* temp_seq, const float* pos_noise, const float* temp_noise,
+                             const float* target_pos, const float* target_temp, int64_t n, int32_t window, float box,
+                             float dt, const float* stats, float* recent_pos, float* x, float* y_acc, float* y_temp,
+                             cgnn_stream stream);
+
 /* Sender-sorted transpose of the receiver-sorted graph (needed for the deterministic d/dh[sender]):
  * rowptr[N+1], perm[E] = edge ids grouped by sender, ascending inside each group. */
 int64_t cgnn_csr_transpose_workspace_bytes(int64_t n, int64_t n_edges);

