@@ -444,14 +444,16 @@ def run_gpu(args):
         "graph_build": None if knn_ms is None else {"ms": knn_ms, "particles_per_s": n_pos / (knn_ms * 1e-3),
                                                     "what": "cgnn_knn_periodic + cgnn_edge_features, device resident"},
         "loss_check": [float(v) for v in last],
-        "peak_memory_gib": torch.cuda.max_memory_allocated(dev) / 2**30,
+        "peak_memory_gib": {"allocated": torch.cuda.max_memory_allocated(dev) / 2**30, "reserved": torch.cuda.max_memory_reserved(dev) / 2**30,
+                            "device": torch.cuda.mem_get_info(dev)[1] / 2**30},
     }
     if message == "edge" and precision != "fp32":
         from cosmology_gnn_simulation_b200 import graph_network as gn
         plans = [v for kk, v in gn._STREAM_PLANS.items()]
-        if plans:
+        forced = int(os.environ.get("CGNN_EDGE_BUFFERS", "0"))
+        if plans or forced:
             from cosmology_gnn_simulation_b200 import ckpt_plan
-            nb = plans[-1]
+            nb = min(forced, M) if forced else plans[-1]
             line["edge_stream"] = {"buffers": nb, "bytes_per_copy": n * k * L * 4,
                                    "recomputed_edge_phases_per_step": ckpt_plan.recomputed_phases(ckpt_plan.schedule(M, nb)),
                                    "what": "copies of the FP32 edge latent stream kept for the backward (ckpt_plan.py); the rest is recomputed"}

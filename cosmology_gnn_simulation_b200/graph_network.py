@@ -105,10 +105,11 @@ def _edge_stream_buffers(plan: _Plan, n: int, n_loc: int, e_count: int, L: int, 
     ops.presize_workspaces(plan.proc_edge[0], plan.enc_edge, n, n_loc, plan.k, e_count, plan.precision, device)
     if copy >= (1 << 30):
         torch.cuda.empty_cache()          # large streams: hand cached fragments back before measuring
-    free, _ = torch.cuda.mem_get_info(device)
+    free, total = torch.cuda.mem_get_info(device)
     free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
-    # still to come: h^t and agg^t for every step, the node-sized gradients / partial products, the transpose, slack
-    other = (2 * M + 12) * n_loc * L * 4 + 12 * e_count + (1 << 30) + free // 50
+    # still to come besides the stream copies: h^t (M+1) and agg^t (M) for every step, six node-sized temporaries of the
+    # backward, the sender-sorted transpose, 1 GiB of small tensors -- and 3 % of the device is left untouched
+    other = (2 * M + 7) * n_loc * L * 4 + 6 * e_count + (1 << 30) + (total * 3) // 100
     nbuf = min(M, (free - other) // copy - 1)                  # - 1: the gradient stream de
     if nbuf < 1:
         raise RuntimeError(

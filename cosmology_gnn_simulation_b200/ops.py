@@ -86,6 +86,8 @@ def senders_from_edge_index(edge_index: torch.Tensor, n: int) -> torch.Tensor:
     return senders
 
 
+# (every MLP entry point shares ONE scratch buffer, tag "mlp": calls are ordered on the stream and none keeps its
+#  workspace beyond its own kernels, so the buffer only has to be as large as the largest request)
 # ------------------------------------------------------------------------------------------------
 # MLP descriptors
 # ------------------------------------------------------------------------------------------------
@@ -151,14 +153,14 @@ def _rows_ws(mlp_c: CgnnMlp, rows: int, precision: str, backward: int, device):
     nbytes = lib().cgnn_mlp_rows_workspace_bytes(byref(mlp_c), rows, PREC[precision], backward)
     if nbytes < 0:
         check(-1, "cgnn_mlp_rows_workspace_bytes")
-    return workspace.get(device, "mlp_bwd" if backward else "rows_fwd", nbytes)
+    return workspace.get(device, "mlp", nbytes)
 
 
 def _bwd_ws(mlp_c: CgnnMlp, device):
     nbytes = lib().cgnn_mlp_bwd_workspace_bytes(byref(mlp_c))
     if nbytes < 0:
         check(-1, "cgnn_mlp_bwd_workspace_bytes")
-    return workspace.get(device, "mlp_bwd", nbytes)
+    return workspace.get(device, "mlp", nbytes)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -209,7 +211,7 @@ def mp_edge_fwd(p: MlpParams, h, e_in, senders, k: int, e_out, agg_edge, precisi
         nbytes = lib().cgnn_mp_edge_fwd_workspace_bytes(byref(m), h.shape[0], PREC[precision])
         if nbytes < 0:
             check(-1, "cgnn_mp_edge_fwd_workspace_bytes")
-        ws = workspace.get(h.device, "edge_fwd", nbytes) if nbytes > 0 else None
+        ws = workspace.get(h.device, "mlp", nbytes) if nbytes > 0 else None
         check(lib().cgnn_mp_edge_fwd(byref(m), ptr(h), ptr(e_in), ptr(senders), n_recv, h.shape[0], k, ptr(e_out),
                                      ptr(agg_edge), ptr(ws), 0 if ws is None else ws.numel(), PREC[precision],
                                      stream_ptr(h.device)), "cgnn_mp_edge_fwd")
@@ -230,7 +232,7 @@ def mp_node_fwd(p: MlpParams, h, agg, h_out, precision: str = "fp32"):
         nbytes = lib().cgnn_mp_node_fwd_workspace_bytes(byref(m), h.shape[0], PREC[precision])
         if nbytes < 0:
             check(-1, "cgnn_mp_node_fwd_workspace_bytes")
-        ws = workspace.get(h.device, "node_fwd", nbytes) if nbytes > 0 else None
+        ws = workspace.get(h.device, "mlp", nbytes) if nbytes > 0 else None
         check(lib().cgnn_mp_node_fwd(byref(m), ptr(h), ptr(agg), h.shape[0], ptr(h_out), ptr(ws),
                                      0 if ws is None else ws.numel(), PREC[precision], stream_ptr(h.device)),
               "cgnn_mp_node_fwd")
@@ -244,7 +246,7 @@ def presize_workspaces(edge_mlp: MlpParams, enc_edge: MlpParams, n: int, n_nodes
     with torch.cuda.device(device):
         nb = lib().cgnn_mp_edge_fwd_workspace_bytes(byref(em), n_nodes, PREC[precision])
         if nb > 0:
-            workspace.get(device, "edge_fwd", nb)
+            workspace.get(device, "mlp", nb)
         _mp_bwd_ws(em, n, k, precision, device, n_nodes=n_nodes)
         _rows_ws(ee, n_edges, precision, 1, device)
         _rows_ws(ee, n_edges, precision, 0, device)
@@ -254,7 +256,7 @@ def _mp_bwd_ws(mlp_c: CgnnMlp, n: int, k: int, precision: str, device, n_nodes=N
     nbytes = lib().cgnn_mp_bwd_workspace_bytes(byref(mlp_c), n, n if n_nodes is None else n_nodes, k, PREC[precision])
     if nbytes < 0:
         check(-1, "cgnn_mp_bwd_workspace_bytes")
-    return workspace.get(device, "mlp_bwd", nbytes)
+    return workspace.get(device, "mlp", nbytes)
 
 
 def mp_node_bwd(p: MlpParams, h, agg, dh_next, dh, dagg, precision: str = "fp32"):

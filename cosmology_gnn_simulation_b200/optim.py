@@ -39,8 +39,8 @@ class FusedAdam:
             if p.dtype != torch.float32 or p.device != dev:
                 raise TypeError("FusedAdam: parameters must be float32 on one CUDA device")
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
-        self.step_count = 0
         self.sizes = [p.numel() for p in self.params]
+        self.steps = [0] * len(self.params)               # per parameter, like torch.optim.Adam: a step without gradient does not count
         n = sum(self.sizes)
         self.flat = torch.empty(n, dtype=torch.float32, device=dev)
         # parameters become views of the flat buffer (values preserved); state_dict / load_state_dict keep working.
@@ -55,8 +55,8 @@ class FusedAdam:
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.live = torch.ones(n, dtype=torch.float32, device=dev)         # 0 where a parameter has no gradient
-        self._live_key = None
+        self._has = tuple(True for _ in self.params)      # which parameters had a gradient at the last gather
+        self._masks = {}                                  # tuple of parameter indices -> flat 0/1 mask selecting them
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self.params:
@@ -69,31 +69,55 @@ class FusedAdam:
         """Copies every `.grad` into the flat gradient buffer and returns it -- the buffer to all-reduce when
         training on several GPUs.  Parameters without a gradient are masked out of the update."""
         views = list(torch.split(self.grad, self.sizes))
-        has = tuple(p.grad is not None for p in self.params)
-        if has != self._live_key:                        # (re)build the mask only when the set of live parameters changes
-            for v, h in zip(torch.split(self.live, self.sizes), has):
-                v.fill_(1.0 if h else 0.0)
-            self._live_key = has
+        self._has = tuple(p.grad is not None for p in self.params)
         live = [(v, p.grad.reshape(-1)) for v, p in zip(views, self.params) if p.grad is not None]
         if live:
             torch._foreach_copy_([a for a, _ in live], [b for _, b in live])
         return self.grad
 
-    def _launch(self, lo: int, hi: int, grad_scale: float) -> None:
+    @property
+    def step_count(self) -> int:
+        return max(self.steps) if self.steps else 0
+
+    def _mask(self, idxs) -> torch.Tensor:
+        m = self._masks.get(idxs)
+        if m is None:
+            m = torch.zeros_like(self.flat)
+            for i, v in enumerate(torch.split(m, self.sizes)):
+                if i in set(idxs):
+                    v.fill_(1.0)
+            self._masks[idxs] = m
+        return m
+
+    def _advance(self):
+        """Counts this step for every parameter that has a gradient; returns [(step, mask | None)] -- one launch per
+        distinct step count (one, without a mask, unless some parameter has ever been skipped)."""
+        for i, h in enumerate(self._has):
+            if h:
+                self.steps[i] += 1
+        groups = {}
+        for i, h in enumerate(self._has):
+            if h:
+                groups.setdefault(self.steps[i], []).append(i)
+        if len(groups) == 1 and all(self._has):
+            return [(next(iter(groups)), None)]
+        return [(st, self._mask(tuple(idxs))) for st, idxs in sorted(groups.items())]
+
+    def _launch(self, lo: int, hi: int, grad_scale: float, step: int, mask: Optional[torch.Tensor]) -> None:
         sl = slice(lo, hi)
-        mask = None if all(self._live_key or (True,)) else self.live[sl]
         with torch.cuda.device(self.flat.device):
             check(lib().cgnn_adam_step_masked(ptr(self.flat[sl]), ptr(self.grad[sl]), ptr(self.exp_avg[sl]), ptr(self.exp_avg_sq[sl]),
-                                              ptr(mask), hi - lo, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                              self.step_count, float(grad_scale), stream_ptr(self.flat.device)), "cgnn_adam_step")
+                                              ptr(None if mask is None else mask[sl]), hi - lo, self.lr, self.betas[0], self.betas[1],
+                                              self.eps, self.weight_decay, step, float(grad_scale), stream_ptr(self.flat.device)),
+                  "cgnn_adam_step")
 
     def step(self, grad_scale: float = 1.0, gathered: bool = False) -> None:
         """One Adam update with the current `lr`.  `gathered=True`: the flat gradient buffer already holds the
         (all-reduced) gradients from `gather_grads()`."""
         if not gathered:
             self.gather_grads()
-        self.step_count += 1
-        self._launch(0, self.flat.numel(), grad_scale)
+        for st, mask in self._advance():
+            self._launch(0, self.flat.numel(), grad_scale, st, mask)
 
     def step_overlapped(self, group=None, n_buckets: int = 4, average: bool = False) -> None:
         """Multi-GPU step: gathers the gradients, all-reduces (SUM) the flat buffer in `n_buckets` slices issued back to
@@ -102,11 +126,12 @@ class FusedAdam:
         slab training sums (every rank holds a partial gradient of one global loss)."""
         import torch.distributed as dist
         self.gather_grads()
-        self.step_count += 1
+        launches = self._advance()
         n = self.flat.numel()
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world == 1:
-            self._launch(0, n, 1.0)
+            for st, mask in launches:
+                self._launch(0, n, 1.0, st, mask)
             return
         per = -(-n // max(1, n_buckets))
         per = -(-per // 4) * 4                            # slices stay 16-byte aligned
@@ -116,14 +141,15 @@ class FusedAdam:
         scale = 1.0 / world if average else 1.0
         for (a, b), w in zip(zip(bounds[:-1], bounds[1:]), works):
             w.wait()                                      # the current stream waits for this bucket only
-            self._launch(a, b, scale)
+            for st, mask in launches:
+                self._launch(a, b, scale, st, mask)
 
     # -- checkpoint / resume (torch.optim.Adam layout) ---------------------------------------------------------------
     def state_dict(self) -> dict:
         state = {}
-        if self.step_count > 0:
-            for i, (m, v, p) in enumerate(zip(torch.split(self.exp_avg, self.sizes), torch.split(self.exp_avg_sq, self.sizes), self.params)):
-                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": m.view_as(p).clone(), "exp_avg_sq": v.view_as(p).clone()}
+        for i, (m, v, p) in enumerate(zip(torch.split(self.exp_avg, self.sizes), torch.split(self.exp_avg_sq, self.sizes), self.params)):
+            if self.steps[i] > 0:                        # torch.optim.Adam creates a parameter's state at its first step
+                state[i] = {"step": torch.tensor(float(self.steps[i])), "exp_avg": m.view_as(p).clone(), "exp_avg_sq": v.view_as(p).clone()}
         group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
                  "params": list(range(len(self.params)))}
         return {"state": state, "param_groups": [group]}
@@ -135,8 +161,7 @@ class FusedAdam:
         self.lr = float(group["lr"])
         self.betas = (float(group["betas"][0]), float(group["betas"][1]))
         self.eps, self.weight_decay = float(group["eps"]), float(group["weight_decay"])
-        steps = [int(float(st["step"])) for st in sd["state"].values()]
-        self.step_count = max(steps) if steps else 0
+        self.steps = [int(float(sd["state"][i]["step"])) if i in sd["state"] else 0 for i in range(len(self.params))]
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         for i, (m, v) in enumerate(zip(torch.split(self.exp_avg, self.sizes), torch.split(self.exp_avg_sq, self.sizes))):

@@ -125,3 +125,49 @@ def test_slab_world2_equals_single_gpu(tmp_path, message, precision):
     full = _run_full(box, params, k, L, M, message, precision, dev)
     tol, gtol = (2e-5, 1e-3) if precision == "fp32" else (1e-3, 1e-2)
     _compare(full, slabs, n, tol, gtol)
+
+
+def _rollout_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from cosmology_gnn_simulation_b200 import distributed as cd
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.rollout import rollout_slab
+    cd.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    n, k, L, M, w = 4000, 16, 128, 2, 5
+    box, params = _setup(n, k, L, M, seed=7)
+    md = box["metadata"]
+    model = EncodeProcessDecode(L, L, 2, M, 3, precision="bf16x3")
+    model.load_state_dict(params)
+    model = model.to(dev)
+    data = {"Coordinates": box["Coordinates"][:w], "InternalEnergy": box["InternalEnergy"][:w]}
+    res = rollout_slab(model, data, md, 0.0, md["dt"], md["box_size"], window_size=w, num_neighbors=k, n_steps=4, rank=rank, world=world)
+    torch.save({k_: v.cpu() for k_, v in res.items()}, f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_rollout_world2_equals_single_gpu(tmp_path):
+    """Config-4 shape in miniature: a rollout whose box is re-partitioned into x-slabs every step (particles change owner
+    as they move) against the single-GPU rollout of the same box (render_rollout.py:39-85)."""
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.rollout import rollout
+    world = 2
+    out = str(tmp_path / "roll")
+    mp.spawn(_rollout_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    r0, r1 = torch.load(f"{out}.0"), torch.load(f"{out}.1")
+    assert torch.equal(r0["Coordinates"], r1["Coordinates"])             # every rank holds the same complete trajectory
+    n, k, L, M, w = 4000, 16, 128, 2, 5
+    box, params = _setup(n, k, L, M, seed=7)
+    md = box["metadata"]
+    model = EncodeProcessDecode(L, L, 2, M, 3, precision="bf16x3")
+    model.load_state_dict(params)
+    model = model.to(torch.device("cuda", 0))
+    data = {"Coordinates": box["Coordinates"][:w], "InternalEnergy": box["InternalEnergy"][:w]}
+    ref = rollout(model, data, md, 0.0, md["dt"], md["box_size"], window_size=w, num_neighbors=k, n_steps=4)
+    d = (ref["Coordinates"].cpu() - r0["Coordinates"]).abs()
+    d = torch.minimum(d, md["box_size"] - d)
+    assert float(d.max()) < 1e-4 * md["box_size"]
+    assert rel_l2(r0["InternalEnergy"], ref["InternalEnergy"].cpu()) < 1e-4
