@@ -37,7 +37,11 @@ namespace {
 using namespace ptx;
 
 constexpr int TC_THREADS = 384;           // 8 epilogue warps (2 groups of 4) + a control warpgroup: producer warp, MMA warp, 2 idle
-constexpr int EPI_REGS = 232, CTL_REGS = 40;   // setmaxnreg: the control warpgroup hands its registers to the epilogue warps
+constexpr int TC_THREADS_SPLIT = 640;     // column-split chains: 16 epilogue warps (2 groups of 8: two warps share a lane quarter, 64 columns each)
+// setmaxnreg: the control warpgroup hands its registers to the epilogue warps.  The pool is what the CTA was LAUNCHED with
+// (registers per thread at launch x threads): 168 x 384 -> 40 / 232;  96 x 640 -> 24 / 112 (40 / 112 would ask for more than
+// the pool holds and the epilogue warps would wait for registers forever).
+constexpr int EPI_REGS = 232, CTL_REGS = 40, EPI_REGS_SPLIT = 104, CTL_REGS_SPLIT = 40;
 constexpr int CW = 32;                    // columns per streamed input chunk (128-byte rows, SWIZZLE_128B)
 constexpr int NCW = TC_H / CW;            // 4 chunks per 128-column tile
 constexpr int CW_BYTES = 128 * CW * 4;    // 16384
@@ -210,13 +214,21 @@ __device__ __forceinline__ void receiver_store16(float* dst, int c, const float*
 // C_SA / C_SB the final epilogue reads row stream a (P_s | dU rows | mask source) / b (P_r | dU per receiver |
 // residual), C_HS the hidden epilogues read row streams (gather or mask sources), C_AGG per-receiver sums, C_RIN the
 // residual is the chain's own input: its tile stays in the input ring until the output pass instead of being re-read.
-constexpr int C_L3 = 1, C_LN = 2, C_LNB = 4, C_SA = 8, C_SB = 16, C_HS = 32, C_AGG = 64, C_RIN = 128;
+// C_GIN: the gather P_s[sender] + P_r[receiver] INITIALISES the layer-1 accumulator (written to TMEM in the input phase, the
+// MMAs then accumulate onto it) instead of being added in an epilogue.  C_SPLIT: 16 epilogue warps -- the two warps that
+// share a TMEM lane quarter take 64 columns each (LayerNorm moments combined through two spare TMEM columns).
+constexpr int C_L3 = 1, C_LN = 2, C_LNB = 4, C_SA = 8, C_SB = 16, C_HS = 32, C_AGG = 64, C_RIN = 128, C_GIN = 256, C_SPLIT = 512;
 template <int NS, int CFG>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__((CFG & C_SPLIT) ? TC_THREADS_SPLIT : TC_THREADS, 1)
 tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1, const TcParams p) {
     constexpr int NSI = NS == 3 ? 2 : 1;                    // weight / activation images per value (hi [, lo])
     constexpr bool L3 = (CFG & C_L3) != 0, SA = (CFG & C_SA) != 0, SB = (CFG & C_SB) != 0, HS = (CFG & C_HS) != 0, AGG = (CFG & C_AGG) != 0;
-    constexpr bool RIN = (CFG & C_RIN) != 0;
+    constexpr bool RIN = (CFG & C_RIN) != 0, GIN = (CFG & C_GIN) != 0, SPLIT = (CFG & C_SPLIT) != 0;
+    constexpr int NEPI = SPLIT ? 16 : 8;                    // epilogue warps
+    constexpr int GW = NEPI / 2;                            // warps per epilogue group (= per tile in flight)
+    constexpr int NTHR = (NEPI + 4) * 32;
+    constexpr int NC = SPLIT ? 64 : TC_H;                   // accumulator columns per epilogue thread
+    static_assert(!SPLIT || !(CFG & (C_LNB | C_HS | C_SA)), "the column split covers the forward chains only");
     constexpr int LN = (CFG & C_LNB) ? 2 : ((CFG & C_LN) ? 1 : 0);
     constexpr bool LNB = LN == 2;
     constexpr int N_LAYERS = L3 ? 3 : 1;
@@ -238,19 +250,19 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
         for (int i = 0; i < MAXRING; ++i) {
             mbar_init(&bars->in_full[0][i], 1);
             mbar_init(&bars->in_full[1][i], 1);
-            mbar_init(&bars->in_empty[i], 4);
+            mbar_init(&bars->in_empty[i], GW);              // every warp of the group hands a slot back (owner or not)
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->a_ready[s], 8); mbar_init(&bars->mma_done[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->a_ready[s], 2 * GW); mbar_init(&bars->mma_done[s], 1); }
         fence_mbar_init();
     }
-    for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
+    for (int i = tid; i < 5 * TC_H; i += NTHR) {
         const int v = i / TC_H, c = i % TC_H;
         sVec[i] = (p.vec_src[v] != nullptr && c < p.vec_len[v]) ? __ldg(p.vec_src[v] + c) : (v == 3 ? 1.0f : 0.0f);
     }
     // This CTA's half (64 output rows) of every weight block as K-major BF16 image(s):  B[n][k] = W[(row0 + n) * ld + col0 + k]
     // (transposed: W[(row0 + k) * ld + col0 + n]), element (n, k) at (n / 8) * 2048 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2.
     // 16-byte pieces (n, k8); 14 MB of L2 reads per launch instead of a separate preparation kernel.
-    for (int piece = tid; piece < n_blocks * 64 * (TC_H / 8); piece += TC_THREADS) {
+    for (int piece = tid; piece < n_blocks * 64 * (TC_H / 8); piece += NTHR) {
         const int b = piece / (64 * (TC_H / 8)), rem = piece % (64 * (TC_H / 8));
         const int nl = rem / (TC_H / 8), k8 = rem % (TC_H / 8);
         const int n = (int)rank * 64 + nl;
@@ -278,9 +290,9 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     }
     fence_proxy_async_smem();                                // the MMAs (async proxy, both CTAs of the pair) read these images
     if (LNB)
-        for (int i = tid; i < 8 * 2 * TC_H; i += TC_THREADS) reinterpret_cast<float*>(smem + Smem::lnacc)[i] = 0.0f;
-    if (warp == 9) tmem_alloc<2>(&bars->tmem_base, 512);
-    if (warp == 8 && lane == 0) {
+        for (int i = tid; i < 8 * 2 * TC_H; i += NTHR) reinterpret_cast<float*>(smem + Smem::lnacc)[i] = 0.0f;
+    if (warp == NEPI + 1) tmem_alloc<2>(&bars->tmem_base, 512);
+    if (warp == NEPI && lane == 0) {
         prefetch_tmap(&tm_in0);
         prefetch_tmap(&tm_in1);
     }
@@ -290,9 +302,9 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     tc_fence_after_sync();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp >= 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTL_REGS));
-    if (warp == 8) {
+    if (warp >= NEPI) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SPLIT ? CTL_REGS_SPLIT : CTL_REGS));
+    if (warp == NEPI) {
         // ============================ producer: weights, input chunks ============================================
         if (lane == 0) {
             uint32_t buf = 0, use = 0;                 // ring slot of the next chunk and how often it has been used
@@ -308,7 +320,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == NEPI + 1) {
         // ============================ MMA issuer (leader CTA, one thread) =======================================
         if (rank == 0 && lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(256, TC_H);
@@ -331,7 +343,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     const uint32_t d = tmem + s * 256;
                     const uint32_t a_hi = d + 128, a_lo = d + 192;
                     const uint32_t w_hi = w_base + (ph * NSI) * WIMG, w_lo = w_hi + WIMG;
-                    uint32_t acc = (ph > 0 && ph < p.n_in) ? 1u : 0u;       // later input phases accumulate into layer 1
+                    // later input phases accumulate into layer 1; with GIN the accumulator already holds P_s[sender] + P_r[receiver]
+                    uint32_t acc = ((ph > 0 && ph < p.n_in) || (GIN && ph == 0)) ? 1u : 0u;
                     // rolled loops: the descriptors advance by one K step (256 bytes of image, 8 TMEM columns) per MMA
                     const uint64_t dw_hi = umma_desc(w_hi, 128, TC_H * 16), dw_lo = umma_desc(w_lo, 128, TC_H * 16);
 #pragma unroll 1
@@ -360,11 +373,13 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     }
     } else {
         // ============================ epilogue groups: thread = row ==============================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
-        const int g = warp >> 2;                        // group = TMEM slot
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SPLIT ? EPI_REGS_SPLIT : EPI_REGS));
+        const int g = warp / GW;                        // group = TMEM slot
         const int wq = warp & 3;                        // lane quarter this warp may touch
+        const int half = SPLIT ? ((warp >> 2) & 1) : 0; // which 64 columns of the row this thread owns (column split)
+        const int C0 = half * 64;                       // first owned accumulator column
         const int r = wq * 32 + lane;                   // row inside the CTA's 128-row tile
-        const int gt = tid - g * 128;                   // thread index inside the group
+        const int gt = tid - g * (GW * 32);             // thread index inside the group
         const uint32_t tslot = tmem + ((uint32_t)(wq * 32) << 16) + g * 256;
         const uint32_t tD = tslot, tAhi = tslot + 128, tAlo = tslot + 192;
         float* lnacc = reinterpret_cast<float*>(smem + Smem::lnacc) + warp * 2 * TC_H;
@@ -383,7 +398,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
         uint32_t ring0 = (uint32_t)g * tile_chunks % uring;
         // sender index of the first tile's row; the next tile's is fetched one tile ahead so its latency never shows
         int32_t snd_next = 0;
-        if (p.gather && g < n_it) {
+        if (GIN && g < n_it) {
             const int64_t first = ((cluster_id + (int64_t)g * n_clusters) * 2 + rank) * 128 + r;
             snd_next = __ldg(p.senders + (first < p.n_rows ? first : p.n_rows - 1));
         }
@@ -399,12 +414,34 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             const size_t rowoff = (size_t)grow * TC_H, recvoff = (size_t)recv * TC_H;
             // the sender index is fetched now so that the address of the gathered P_s row is ready when its epilogue starts
             const int32_t snd = snd_next;
-            if (p.gather && it + 2 < n_it) {
+            if (GIN && it + 2 < n_it) {
                 const int64_t nxt = ((cluster_id + (it + 2) * n_clusters) * 2 + rank) * 128 + r;
                 snd_next = __ldg(p.senders + (nxt < p.n_rows ? nxt : p.n_rows - 1));
             }
             CGNN_STAMP(0);
             // ---- input phases: stream chunks, split, write the A operand -------------------------------------
+            if (GIN) {
+                // layer-1 accumulator := P_s[sender] + P_r[receiver] (FP32, this thread's row and columns); the MMAs of the first
+                // block accumulate e W1e^T onto it.  The scattered P_s loads of a whole column range are issued together, so
+                // their latency is paid once per tile, here, where the thread would otherwise wait for its input chunks.
+                const float* ps = p.Ps + (size_t)snd * TC_H + C0;
+                const float* pr = p.Pr + recvoff + C0;
+#pragma unroll 1
+                for (int c = 0; c < NC; c += 64) {
+                    float a0[16], a1[16], a2[16], a3[16];
+                    ld16(ps + c, a0); ld16(ps + c + 16, a1); ld16(ps + c + 32, a2); ld16(ps + c + 48, a3);
+#pragma unroll
+                    for (int hh = 0; hh < 4; ++hh) {
+                        float* ca = hh == 0 ? a0 : hh == 1 ? a1 : hh == 2 ? a2 : a3;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {       // the P_r row is shared by the k lanes of a receiver: cached loads
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(pr + c + 16 * hh + j));
+                            ca[j] += b.x; ca[j + 1] += b.y; ca[j + 2] += b.z; ca[j + 3] += b.w;
+                        }
+                        tmem_st_32x32b_x16(tD + C0 + c + 16 * hh, reinterpret_cast<const uint32_t*>(ca));
+                    }
+                }
+            }
             for (int ip = 0; ip < p.n_in; ++ip) {
                 if (ip > 0) {                            // A is still being read by the previous phase's MMA
                     mbar_wait_or_trap(&bars->mma_done[g], pm, 140);
@@ -412,8 +449,15 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     tc_fence_after_sync();
                 }
                 for (int q = 0; q < NCW; ++q, buf = buf + 1 == uring ? 0 : buf + 1) {
+                    // (every thread waits on every chunk's barrier, also on chunks of the other column half: a parity wait
+                    //  may never fall two phases behind)
                     mbar_wait_or_trap(&bars->in_full[g][buf], (in_par >> buf) & 1u, 150 + buf);
                     in_par ^= 1u << buf;
+                    if (SPLIT && (q >> 1) != half) {     // not this warp's columns: the slot goes straight back
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
+                        continue;
+                    }
                     const uint8_t* src = sRing + buf * CW_BYTES;
                     uint32_t hi[16], lo[16];
 #pragma unroll
@@ -439,43 +483,34 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             }
             // ---- hidden layers ------------------------------------------------------------------------------------
             for (int l = 0; l + 1 < N_LAYERS; ++l) {
-                const bool gather = p.gather && l == 0;
-                // row streams of this layer, thread = row: a = P_s[sender] | mask source, b = P_r[receiver]
-                const float* pa = !HS ? nullptr : gather ? p.Ps + (size_t)snd * TC_H : (p.hid_mask[l] ? p.hid_mask[l] + rowoff : nullptr);
-                const float* pb = HS && gather ? p.Pr + recvoff : nullptr;
-                const bool masked = !gather && pa != nullptr;
+                // row stream of this layer, thread = row: the mask source of a dgrad chain (the gather is part of the accumulator, GIN)
+                const float* pa = !HS ? nullptr : (p.hid_mask[l] ? p.hid_mask[l] + rowoff : nullptr);
+                const bool masked = pa != nullptr;
                 float* hout = p.hid_out[l] ? p.hid_out[l] + rowoff : nullptr;
                 float* hagg = AGG && p.hid_agg[l] ? p.hid_agg[l] + recvoff : nullptr;
                 const float* bias = sVec + l * TC_H;
-                // operands of the row streams: four 16-column chunk buffers per stream, each reloaded four chunks (64 columns) ahead
-                // (stream b = the P_r row, shared by the k lanes of a receiver and L2-hot: two buffers, reloaded two chunks ahead)
-                float a0[16], a1[16], a2[16], a3[16], b0[16], b1[16];
+                // operands of the row stream: four 16-column chunk buffers, each reloaded four chunks (64 columns) ahead
+                float a0[16], a1[16], a2[16], a3[16];
                 if (pa) { ld16(pa, a0); ld16(pa + 16, a1); ld16(pa + 32, a2); ld16(pa + 48, a3); }
-                if (pb) { ld16(pb, b0); ld16(pb + 16, b1); }
                 mbar_wait_or_trap(&bars->mma_done[g], pm, 160 + l);
                 pm ^= 1u;
                 tc_fence_after_sync();
                 CGNN_STAMP(3 + 4 * l);
                 float va[16], vb[16];
-                tmem_ld_32x32b_x16(tD, va);
+                tmem_ld_32x32b_x16(tD + C0, va);
 #pragma unroll 1
-                for (int c = 0; c < TC_H; c += 64) {
+                for (int c = C0; c < C0 + NC; c += 64) {
 #pragma unroll
                     for (int hh = 0; hh < 4; ++hh) {
                         float* v = (hh & 1) == 0 ? va : vb;
                         float* ca = hh == 0 ? a0 : hh == 1 ? a1 : hh == 2 ? a2 : a3;
-                        float* cb = (hh & 1) == 0 ? b0 : b1;
                         const int cc = c + 16 * hh;
                         tmem_ld_wait16(v);
-                        if (cc + 16 < TC_H) tmem_ld_32x32b_x16(tD + cc + 16, (hh & 1) == 0 ? vb : va);
+                        if (cc + 16 < C0 + NC) tmem_ld_32x32b_x16(tD + cc + 16, (hh & 1) == 0 ? vb : va);
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             const float4 b = *reinterpret_cast<const float4*>(bias + cc + j);
                             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                        }
-                        if (gather) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += ca[j] + cb[j];
                         }
                         if (masked) {
 #pragma unroll
@@ -484,8 +519,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
                         }
-                        if (pa && cc + 64 < TC_H) ld16(pa + cc + 64, ca);
-                        if (pb && cc + 32 < TC_H) ld16(pb + cc + 32, cb);
+                        if (pa && cc + 64 < C0 + NC) ld16(pa + cc + 64, ca);
                         if (hout && valid) st16(hout + cc, v);
                         uint32_t hi[8], lo[8];
 #pragma unroll
@@ -506,15 +540,12 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 CGNN_STAMP(6 + 4 * l);
             }
             // ---- final layer: bias, [gather], [LayerNorm fwd / bwd], [ReLU], [mask], per-receiver sum, residual, store ----
-            const bool fgather = !L3 && SA && SB && p.gather;       // one-layer chain: the gather lands here
             constexpr bool lnb = LNB;
-            // row streams, thread = row:  a = P_s[sender] | dU rows | mask source,  b = P_r[receiver] | dU per receiver | residual
+            // row streams, thread = row:  a = dU rows | mask source,  b = dU per receiver | residual
             const float* pa = !SA     ? nullptr
-                              : fgather ? p.Ps + (size_t)snd * TC_H
                               : lnb   ? (p.du_rows ? p.du_rows + rowoff : nullptr)
                                       : (p.mask_src ? p.mask_src + rowoff : nullptr);
             const float* pb = !SB || RIN ? nullptr
-                              : fgather ? p.Pr + recvoff
                               : lnb   ? (p.du_recv ? p.du_recv + recvoff : nullptr)
                                       : (p.residual ? p.residual + rowoff : nullptr);
             float* outp = p.out + rowoff;
@@ -522,8 +553,18 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             float* aggp = AGG && p.agg_out ? p.agg_out + recvoff : nullptr;
             // four 16-column chunk buffers per stream, each reloaded four chunks (64 columns) ahead
             float a0[16], a1[16], a2[16], a3[16], b0[16], b1[16], b2[16], b3[16];
-            if (pa) { ld16(pa, a0); ld16(pa + 16, a1); ld16(pa + 32, a2); ld16(pa + 48, a3); }
-            if (pb) { ld16(pb, b0); ld16(pb + 16, b1); ld16(pb + 32, b2); ld16(pb + 48, b3); }
+            if (lnb) {
+                // LayerNorm backward: the WHOLE dU row (128 columns, a0..a3 then b0..b3) is requested here, before the wait for the
+                // last MMA, so the scattered 32-byte sectors arrive under that wait instead of chunk by chunk in the moment loop;
+                // the per-receiver part of dU is shared by the k lanes of a receiver and read through the L1 when it is used
+                if (pa) {
+                    ld16(pa, a0); ld16(pa + 16, a1); ld16(pa + 32, a2); ld16(pa + 48, a3);
+                    ld16(pa + 64, b0); ld16(pa + 80, b1); ld16(pa + 96, b2); ld16(pa + 112, b3);
+                }
+            } else {
+                if (pa) { ld16(pa + C0, a0); ld16(pa + C0 + 16, a1); ld16(pa + C0 + 32, a2); ld16(pa + C0 + 48, a3); }
+                if (pb) { ld16(pb + C0, b0); ld16(pb + C0 + 16, b1); ld16(pb + C0 + 32, b2); ld16(pb + C0 + 48, b3); }
+            }
             uint4 mbits = make_uint4(0u, 0u, 0u, 0u);
             if (p.mask_bits != nullptr) mbits = __ldg(reinterpret_cast<const uint4*>(p.mask_bits) + grow);
             mbar_wait_or_trap(&bars->mma_done[g], pm, 180);
@@ -539,9 +580,9 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 // |mean| >> std) and, for the backward, sum g and sum g (y - y0) with g = dU * gamma
                 float y0 = 0.0f, s1 = 0.0f, s2 = 0.0f, g1 = 0.0f, g2 = 0.0f;
                 float va[16], vb[16];
-                tmem_ld_32x32b_x16(tD, va);
+                tmem_ld_32x32b_x16(tD + C0, va);
 #pragma unroll 1
-                for (int c = 0; c < TC_H; c += 64) {
+                for (int c = C0; c < C0 + NC; c += 64) {
 #pragma unroll
                     for (int hh = 0; hh < 4; ++hh) {
                         float* v = (hh & 1) == 0 ? va : vb;
@@ -549,13 +590,13 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         float* cb = hh == 0 ? b0 : hh == 1 ? b1 : hh == 2 ? b2 : b3;
                         const int cc = c + 16 * hh;
                         tmem_ld_wait16(v);
-                        if (cc + 16 < TC_H) tmem_ld_32x32b_x16(tD + cc + 16, (hh & 1) == 0 ? vb : va);
+                        if (cc + 16 < C0 + NC) tmem_ld_32x32b_x16(tD + cc + 16, (hh & 1) == 0 ? vb : va);
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             const float4 b = *reinterpret_cast<const float4*>(bias + cc + j);
                             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                         }
-                        if (cc == 0) y0 = v[0];
+                        if (cc == C0) y0 = v[0];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float d = v[j] - y0;
@@ -567,7 +608,14 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             // for the output pass, so the dU streams are read from global memory only once
                             float du[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) du[j] = valid ? (pa ? ca[j] : 0.0f) + (pb ? cb[j] : 0.0f) : 0.0f;
+                            for (int j = 0; j < 16; j += 4) {
+                                float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (pb) rv = __ldg(reinterpret_cast<const float4*>(pb + cc + j));
+                                const float rvj[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)      // columns 0-63 of the row stream sit in a0..a3, 64-127 in b0..b3
+                                    du[j + u] = valid ? (pa ? (c == 0 ? ca[j + u] : cb[j + u]) : 0.0f) + rvj[u] : 0.0f;
+                            }
                             tmem_st_32x32b_x16(tAhi + cc, reinterpret_cast<const uint32_t*>(du));
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
@@ -580,17 +628,30 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                                     g2 = fmaf(t, v[j + u] - y0, g2);
                                 }
                             }
-                            if (cc + 64 < TC_H) {
-                                if (pa) ld16(pa + cc + 64, ca);
-                                if (pb) ld16(pb + cc + 64, cb);
-                            }
                         }
                     }
                 }
                 if (lnb) tmem_st_wait();
-                const float m1 = s1 * (1.0f / TC_H);
+                float m1 = s1 * (1.0f / NC);
                 mean = y0 + m1;
-                const float var = fmaxf(s2 * (1.0f / TC_H) - m1 * m1, 0.0f);
+                float var = fmaxf(s2 * (1.0f / NC) - m1 * m1, 0.0f);
+                if (SPLIT) {
+                    // This thread has the moments of its 64 columns; the other half of the row lives in the warp that shares the
+                    // lane quarter.  Exchange (mean, M2) through four spare TMEM columns of the row (the A-operand columns are free
+                    // once the last MMA is done) and combine: mean = (m_a + m_b) / 2, M2 = M2_a + M2_b + 32 (m_a - m_b)^2.
+                    tmem_st_32x32b_x2(tAhi + 2 * half, __float_as_uint(mean), __float_as_uint(var * (float)NC));
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    named_bar_sync(1 + g * 4 + wq, 64);
+                    tc_fence_after_sync();
+                    float mm[4];
+                    tmem_ld_32x32b_x4(tAhi, mm);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(mm[0]), "+f"(mm[1]), "+f"(mm[2]), "+f"(mm[3]) :: "memory");
+                    const float dm = mm[0] - mm[2];
+                    mean = 0.5f * (mm[0] + mm[2]);
+                    var = (mm[1] + mm[3] + 32.0f * dm * dm) * (1.0f / TC_H);
+                    m1 = 0.0f;
+                }
                 rstd = 1.0f / sqrtf(var + LN_EPS);
                 gm1 = g1 * (1.0f / TC_H);                                  // mean of g
                 gm2 = (g2 - m1 * g1) * rstd * (1.0f / TC_H);               // mean of g * xhat
@@ -598,9 +659,9 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             CGNN_STAMP(12);
             {
                 float va[16], vb[16];
-                tmem_ld_32x32b_x16(tD, va);
+                tmem_ld_32x32b_x16(tD + C0, va);
 #pragma unroll 1
-                for (int c = 0; c < TC_H; c += 64) {
+                for (int c = C0; c < C0 + NC; c += 64) {
                     uint32_t gate0 = 0u, gate1 = 0u;         // ReLU gates of columns c .. c+31, c+32 .. c+63
                     float held[16];                          // the even 16-column block of a pair, waiting for the joint per-receiver sum
 #pragma unroll
@@ -608,17 +669,13 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         float* v = (hh & 1) == 0 ? va : vb;
                         const int cc = c + 16 * hh;
                         tmem_ld_wait16(v);
-                        if (cc + 16 < TC_H) tmem_ld_32x32b_x16(tD + cc + 16, (hh & 1) == 0 ? vb : va);
+                        if (cc + 16 < C0 + NC) tmem_ld_32x32b_x16(tD + cc + 16, (hh & 1) == 0 ? vb : va);
                         float* ca = hh == 0 ? a0 : hh == 1 ? a1 : hh == 2 ? a2 : a3;
                         float* cb = hh == 0 ? b0 : hh == 1 ? b1 : hh == 2 ? b2 : b3;
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             const float4 b = *reinterpret_cast<const float4*>(bias + cc + j);
                             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                        }
-                        if (fgather) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += ca[j] + cb[j];
                         }
                         if (LN == 1) {
 #pragma unroll
@@ -646,8 +703,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                                     v[j + u] = rstd * (du[j + u] * gmj[u] - gm1 - xh * gm2);
                                 }
                             }
-                            receiver_sum16(dgx, 32, lane);
-                            receiver_sum16(du, 32, lane);
+                            receiver_sum16x2(dgx, du, 32, lane);       // the two column sums share one butterfly (their chains overlap)
                             if ((lane & 1) == 0) {
                                 lnacc[cc + (lane >> 1)] += dgx[0];
                                 lnacc[TC_H + cc + (lane >> 1)] += du[0];
@@ -657,7 +713,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
                         }
-                        if (!fgather && !lnb && pa) {
+                        if (!lnb && pa) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = ca[j] > 0.0f ? v[j] : 0.0f;
                         }
@@ -699,7 +755,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive_local(&bars->in_empty[rbuf]);
                             }
-                        } else if (!fgather && !lnb && pb) {
+                        } else if (!lnb && pb) {
                             // residual: the sum goes out from the stream's own registers, v stays free for the per-receiver sum
 #pragma unroll
                             for (int j = 0; j < 16; ++j) cb[j] += v[j];
@@ -720,7 +776,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                                 }
                             }
                         }
-                        if (!lnb && cc + 64 < TC_H) {
+                        if (!lnb && cc + 64 < C0 + NC) {
                             if (pa) ld16(pa + cc + 64, ca);
                             if (pb) ld16(pb + cc + 64, cb);
                         }
@@ -743,11 +799,10 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 9) tmem_dealloc<2>(tmem, 512);
+    if (warp == NEPI + 1) tmem_dealloc<2>(tmem, 512);
 }
 
 constexpr size_t SMEM_MAX = 227 * 1024;
-bool gather_final(const ChainOp& op) { return op.Ps != nullptr && op.n_layers == 1; }
 
 // sums the per-warp LayerNorm-backward column sums [n_rows_p][2][128] in fixed order: block <-> 8 columns x 32 row slices,
 // combined through shared memory
@@ -788,10 +843,8 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
         while ((1 << kshift) < k) ++kshift;
     }
     if (op.ln_bwd) {
-        CGNN_CHECK_ARG(op.gamma && (op.du_rows || op.du_recv) && op.ln_ws && !gather_final(op) && !op.mask_src && !op.residual && !op.agg_out,
+        CGNN_CHECK_ARG(op.gamma && (op.du_rows || op.du_recv) && op.ln_ws && !op.mask_src && !op.residual && !op.agg_out,
                        "tensor-core chain: bad LayerNorm-backward arguments");
-    } else if (gather && op.n_layers == 1) {
-        CGNN_CHECK_ARG(!op.mask_src && !op.residual, "tensor-core chain: a one-layer gather chain takes no mask / residual");
     }
     TcParams p{};
     p.n_rows = op.rows; p.n_pair_tiles = (op.rows + 255) / 256;
@@ -823,42 +876,56 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     const size_t ring_off = ring_offset(n_blocks, NSI, op.ln_bwd != 0);
     // the residual is the chain's own (first) input and the ring can hold both groups' tiles: no re-read
     static const bool rin_allowed = getenv("CGNN_NO_RIN") == nullptr;       // measurements: force the re-read path
-    const bool rin = rin_allowed && !op.ln_bwd && op.residual != nullptr && op.residual == op.in0 && !(gather && op.n_layers == 1) &&
+    const bool rin = rin_allowed && !op.ln_bwd && op.residual != nullptr && op.residual == op.in0 &&
                      ring_off + (size_t)(2 * NCW * n_in) * CW_BYTES <= SMEM_MAX;
     CGNN_CHECK_ARG(ring_off + 2 * CW_BYTES <= SMEM_MAX, "tensor-core chain: shared memory need %zu exceeds 227 KB", ring_off + 2 * CW_BYTES);
     p.n_ring = (int)((SMEM_MAX - ring_off) / CW_BYTES);
     if (p.n_ring > MAXRING) p.n_ring = MAXRING;
     const size_t smem = ring_off + (size_t)p.n_ring * CW_BYTES;
     // the instantiation for this chain's shape
-    const bool any_hidden = op.n_layers == 3 && (gather || op.hid_mask[0] || op.hid_mask[1]);
-    const bool fin_a = (gather && op.n_layers == 1) || (op.ln_bwd ? op.du_rows != nullptr : op.mask_src != nullptr);
-    const bool fin_b = (gather && op.n_layers == 1) || (op.ln_bwd ? op.du_recv != nullptr : op.residual != nullptr);
+    const bool any_hidden = op.n_layers == 3 && (op.hid_mask[0] || op.hid_mask[1]);
+    const bool fin_a = op.ln_bwd ? op.du_rows != nullptr : op.mask_src != nullptr;
+    const bool fin_b = op.ln_bwd ? op.du_recv != nullptr : op.residual != nullptr;
     const bool any_agg = op.agg_out || op.hid_agg[0] || op.hid_agg[1];
+    // the fused forward chains (3 layers + LayerNorm) are bound by the serial epilogue of a tile, not by memory: their columns
+    // are split over 16 epilogue warps.  The one-layer chains run at the memory rate either way and keep 8 warps.
+    // Measured (profiles/r02_chain_stage_stamps.txt): the split shortens a tile's own time (39.1 k -> 34.0 k cycles) but not
+    // the tile period (39.6 k vs 39.9 k) nor the step, so it is opt-in (CGNN_SPLIT=1) until the coupling is understood.
+    static const bool split_allowed = getenv("CGNN_SPLIT") != nullptr && atoi(getenv("CGNN_SPLIT")) != 0;
+    const bool split = split_allowed && op.n_layers == 3 && op.gamma != nullptr && !op.ln_bwd && !any_hidden && !fin_a &&
+                       !op.hid_out[0] && !op.hid_out[1] && !op.hid_agg[0] && !op.hid_agg[1] && !op.bits_out && !op.mask_bits;
     const int cfg = (op.n_layers == 3 ? C_L3 : 0) | (op.ln_bwd ? C_LNB : (op.gamma ? C_LN : 0)) | (fin_a ? C_SA : 0) | (fin_b ? C_SB : 0) |
-                    (any_hidden ? C_HS : 0) | (any_agg ? C_AGG : 0) | (rin ? C_RIN : 0);
+                    (any_hidden ? C_HS : 0) | (any_agg ? C_AGG : 0) | (rin ? C_RIN : 0) | (gather ? C_GIN : 0) | (split ? C_SPLIT : 0);
     void (*kern)(CUtensorMap, CUtensorMap, TcParams) = nullptr;
     int slot = -1;
 #define CGNN_CHAIN_CFG(i, c) else if (cfg == (c)) { kern = tc_chain_fwd<NS, (c)>; slot = (i); }
     if (false) {}
     CGNN_CHAIN_CFG(0, 0)                                              // 1 layer: plain / ReLU / two inputs
-    CGNN_CHAIN_CFG(1, C_SA | C_SB)                                    // 1 layer + gather (A1 of the edge backward)
+    CGNN_CHAIN_CFG(1, C_GIN)                                          // 1 layer + gather (A1 of the edge backward)
     CGNN_CHAIN_CFG(2, C_SA)                                           // 1 layer + mask (dgrad)
     CGNN_CHAIN_CFG(3, C_SA | C_AGG)                                   // 1 layer + mask + per-receiver sum
     CGNN_CHAIN_CFG(4, C_SB)                                           // 1 layer + residual
     CGNN_CHAIN_CFG(5, C_L3)                                           // decoders
     CGNN_CHAIN_CFG(6, C_L3 | C_LN)                                    // encoders
     CGNN_CHAIN_CFG(7, C_L3 | C_LN | C_SB)                             // node phase forward
-    CGNN_CHAIN_CFG(8, C_L3 | C_LN | C_SB | C_HS)                      // edge phase forward without the per-receiver sum
-    CGNN_CHAIN_CFG(9, C_L3 | C_LN | C_SB | C_HS | C_AGG)              // edge phase forward
-    CGNN_CHAIN_CFG(21, C_L3 | C_LN | C_SB | C_HS | C_AGG | C_RIN)     // edge phase forward, residual from the input ring
-    CGNN_CHAIN_CFG(22, C_L3 | C_LN | C_SB | C_HS | C_RIN)
+    CGNN_CHAIN_CFG(8, C_L3 | C_LN | C_SB | C_GIN)                     // edge phase forward without the per-receiver sum
+    CGNN_CHAIN_CFG(9, C_L3 | C_LN | C_SB | C_GIN | C_AGG)             // edge phase forward
+    CGNN_CHAIN_CFG(21, C_L3 | C_LN | C_SB | C_GIN | C_AGG | C_RIN)    // edge phase forward, residual from the input ring
+    CGNN_CHAIN_CFG(22, C_L3 | C_LN | C_SB | C_GIN | C_RIN)
     CGNN_CHAIN_CFG(23, C_L3 | C_LN | C_SB | C_RIN)                    // node phase forward, residual from the input ring
-    CGNN_CHAIN_CFG(10, C_L3 | C_LNB | C_SA | C_SB | C_HS)             // edge backward, recompute + LayerNorm backward
+    CGNN_CHAIN_CFG(25, C_SPLIT | C_L3 | C_LN)                         // the same forward chains with the column-split epilogue
+    CGNN_CHAIN_CFG(26, C_SPLIT | C_L3 | C_LN | C_SB)
+    CGNN_CHAIN_CFG(27, C_SPLIT | C_L3 | C_LN | C_SB | C_GIN)
+    CGNN_CHAIN_CFG(28, C_SPLIT | C_L3 | C_LN | C_SB | C_GIN | C_AGG)
+    CGNN_CHAIN_CFG(29, C_SPLIT | C_L3 | C_LN | C_SB | C_GIN | C_AGG | C_RIN)
+    CGNN_CHAIN_CFG(30, C_SPLIT | C_L3 | C_LN | C_SB | C_GIN | C_RIN)
+    CGNN_CHAIN_CFG(31, C_SPLIT | C_L3 | C_LN | C_SB | C_RIN)
+    CGNN_CHAIN_CFG(10, C_L3 | C_LNB | C_SA | C_SB | C_GIN)            // edge backward, recompute + LayerNorm backward
     CGNN_CHAIN_CFG(11, C_L3 | C_LNB | C_SA)                           // node backward, recompute + LayerNorm backward
     CGNN_CHAIN_CFG(12, C_L3 | C_SB | C_HS | C_AGG)                    // edge backward, dgrad chain
     CGNN_CHAIN_CFG(13, C_L3 | C_HS)                                   // node backward, dgrad chain
     CGNN_CHAIN_CFG(14, C_AGG)                                         // 1 layer + per-receiver sum
-    CGNN_CHAIN_CFG(15, C_L3 | C_LNB | C_SB | C_HS)                    // edge backward recompute, no gradient on the edge output
+    CGNN_CHAIN_CFG(15, C_L3 | C_LNB | C_SB | C_GIN)                   // edge backward recompute, no gradient on the edge output
     CGNN_CHAIN_CFG(16, C_L3 | C_HS | C_AGG)                           // edge backward dgrad, no gradient on the edge output
     CGNN_CHAIN_CFG(17, C_L3 | C_SB | C_HS)                            // node backward dgrad
     CGNN_CHAIN_CFG(18, C_LNB | C_SA | C_SB)                           // 1 layer + LayerNorm backward (dU per row and per receiver)
@@ -869,7 +936,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
         set_error("tensor-core chain: no kernel instantiated for configuration 0x%x", cfg);
         return CGNN_ERR_UNSUPPORTED;
     }
-    static size_t configured[24] = {0};
+    static size_t configured[33] = {0};
     if (smem > configured[slot]) {
         CGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[slot] = smem;
@@ -878,7 +945,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     if (p.n_pair_tiles < pairs) pairs = p.n_pair_tiles;
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3((unsigned)(pairs * 2));
-    lc.blockDim = dim3(TC_THREADS);
+    lc.blockDim = dim3(split ? TC_THREADS_SPLIT : TC_THREADS);
     lc.dynamicSmemBytes = smem;
     lc.stream = stream;
     cudaLaunchAttribute at[1];

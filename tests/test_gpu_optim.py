@@ -21,10 +21,12 @@ def test_fused_adam_matches_torch_adam(weight_decay):
     for it in range(6):
         grads = [torch.randn(s, device=d) * (10.0 ** (it - 3)) for s in shapes]
         for p, q, g in zip(ref_params, my_params, grads):
-            p.grad = g.clone()
-            q.grad = g.clone() if not (it == 2 and q.numel() == 1) else None      # a parameter without gradient: treated as zero
-            if it == 2 and p.numel() == 1:
-                p.grad = torch.zeros_like(p)
+            # a parameter without gradient is skipped entirely -- no decay, no moment update, its own step count --
+            # exactly as torch.optim.Adam skips it
+            if it == 2 and q.numel() == 1:
+                p.grad = q.grad = None
+            else:
+                p.grad, q.grad = g.clone(), g.clone()
         ref.step()
         mine.step()
         if it % 2 == 1:
