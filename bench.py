@@ -449,7 +449,7 @@ def run_gpu(args):
     }
     if message == "edge" and precision != "fp32":
         from cosmology_gnn_simulation_b200 import graph_network as gn
-        plans = [v for kk, v in gn._STREAM_PLANS.items()]
+        plans = [v for kk, v in gn._STREAM_PLANS.items() if kk[1] == n and kk[3] == n * k]       # (the parity block plans a small box too)
         forced = int(os.environ.get("CGNN_EDGE_BUFFERS", "0"))
         if plans or forced:
             from cosmology_gnn_simulation_b200 import ckpt_plan
@@ -562,7 +562,7 @@ def slab_parity(rank, world, dev, k, L, M, message, precision, n_small=8192):
     worst = max(grads)
     res = {"box": f"{n_small} particles, k={k}, L={L}, M={M}, message={message}, precision={precision}: {world}-rank slab step vs the "
                   f"same box on rank 0 alone",
-           "loss_rel": abs(float(ls["loss"]) - float(ls1["loss"])) / abs(float(ls1["loss"])),
+           "loss_rel": abs(float(ls["loss"].detach()) - float(ls1["loss"].detach())) / abs(float(ls1["loss"].detach())),
            "outputs_rel_l2": rel(out_slab, out1), "worst_gradient_rel_l2": worst[0], "worst_gradient": worst[1],
            "gradients_compared": len(grads),
            "note": "sums over a receiver's k edges and over rows are taken in the same order on both sides; the sender scatter "

@@ -21,7 +21,7 @@ DISP = {"raw": 0, "min_image": 1}
 class CgnnMlp(Structure):
     _fields_ = [("n_layers", c_int32), ("in_dim", c_int32), ("hidden", c_int32), ("out_dim", c_int32),
                 ("W", c_void_p * MAX_LAYERS), ("b", c_void_p * MAX_LAYERS),
-                ("ln_gamma", c_void_p), ("ln_beta", c_void_p)]
+                ("ln_gamma", c_void_p), ("ln_beta", c_void_p), ("ln_dim", c_int32)]
 
 
 class CgnnMlpGrad(Structure):

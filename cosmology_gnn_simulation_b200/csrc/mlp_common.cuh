@@ -12,6 +12,7 @@ struct MlpDev {
     const float* b[CGNN_MAX_LAYERS];
     const float* gamma;
     const float* beta;
+    int ln_dim;                 // LayerNorm width (<= out_dim; the rest is zero padding), see cgnn_mlp
 };
 
 struct GradPtrs {

@@ -230,7 +230,7 @@ mlp_fwd_kernel(MlpTask a, int64_t n_tiles) {
         }
         const int N = m.out_dim;
         const bool ln = m.gamma != nullptr;
-        if (ln) { row_stats(cur, AS, t.rows, N, sMean, sRstd); __syncthreads(); }
+        if (ln) { row_stats(cur, AS, t.rows, m.ln_dim, sMean, sRstd); __syncthreads(); }   // (columns beyond ln_dim are zero padding)
         // epilogue: normalise, residual, write
         for (int idx = threadIdx.x; idx < t.rows * N; idx += NTHREADS) {
             int row = idx / N, c = idx - row * N;
@@ -339,7 +339,7 @@ mlp_bwd_kernel(MlpTask a, int64_t n_tiles, float* __restrict__ partials, int64_t
             }
             sG0[row * AS + c] = v;
         }
-        if (ln) row_stats(sY, AS, t.rows, NO, sMean, sRstd);
+        if (ln) row_stats(sY, AS, t.rows, m.ln_dim, sMean, sRstd);
         __syncthreads();
         if (ln) {
             // dgamma / dbeta: thread per column, rows in fixed order
@@ -366,11 +366,11 @@ mlp_bwd_kernel(MlpTask a, int64_t n_tiles, float* __restrict__ partials, int64_t
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o); s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o); }
-                s1 /= (float)NO; s2 /= (float)NO;
+                s1 /= (float)m.ln_dim; s2 /= (float)m.ln_dim;
                 for (int c = lane; c < NO; c += 32) {
                     float g = sG0[row * AS + c] * m.gamma[c];
                     float yh = (sY[row * AS + c] - sMean[row]) * sRstd[row];
-                    sG0[row * AS + c] = (g - s1 - yh * s2) * sRstd[row];
+                    sG0[row * AS + c] = c < m.ln_dim ? (g - s1 - yh * s2) * sRstd[row] : 0.0f;
                 }
             }
             __syncthreads();
@@ -577,6 +577,7 @@ int validate(const cgnn_mlp* mlp, const char* who) {
     CGNN_CHECK_ARG(mlp->hidden <= 256 && mlp->out_dim <= 256, "%s: hidden/out width > 256 not supported (got %d/%d)", who, mlp->hidden, mlp->out_dim);
     for (int l = 0; l < mlp->n_layers; ++l) CGNN_CHECK_ARG(mlp->W[l] && mlp->b[l], "%s: null weight/bias at layer %d", who, l);
     CGNN_CHECK_ARG((mlp->ln_gamma == nullptr) == (mlp->ln_beta == nullptr), "%s: ln_gamma/ln_beta must both be set or both NULL", who);
+    CGNN_CHECK_ARG(mlp->ln_dim >= 0 && mlp->ln_dim <= mlp->out_dim, "%s: ln_dim must be in 0..out_dim", who);
     return CGNN_OK;
 }
 
@@ -585,6 +586,7 @@ MlpDev to_dev(const cgnn_mlp* mlp) {
     m.n_layers = mlp->n_layers; m.in_dim = mlp->in_dim; m.hidden = mlp->hidden; m.out_dim = mlp->out_dim;
     for (int l = 0; l < CGNN_MAX_LAYERS; ++l) { m.W[l] = l < mlp->n_layers ? mlp->W[l] : nullptr; m.b[l] = l < mlp->n_layers ? mlp->b[l] : nullptr; }
     m.gamma = mlp->ln_gamma; m.beta = mlp->ln_beta;
+    m.ln_dim = mlp->ln_dim > 0 ? mlp->ln_dim : mlp->out_dim;
     return m;
 }
 

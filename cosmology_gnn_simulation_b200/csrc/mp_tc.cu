@@ -58,6 +58,7 @@ struct TcParams {
     int k;                      // rows per receiver (gather / per-receiver sums), a power of two <= 32; 1 when unused
     int kshift;                 // log2(k)
     int ln_mode;                // 0: none, 1: LayerNorm forward, 2: LayerNorm backward (the result is dY)
+    int ln_n;                   // LayerNorm width: columns [ln_n, 128) are zero padding (accumulator, bias, gamma, beta all zero there)
     int gather;                 // layer-1 pre-activation += Ps[sender] + Pr[receiver]
     int relu_out;               // ReLU on the result (before mask / residual)
     const float* mask_src;      // [n_rows][128]: result = mask_src > 0 ? result : 0 (nullable)
@@ -257,7 +258,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     }
     for (int i = tid; i < 5 * TC_H; i += NTHR) {
         const int v = i / TC_H, c = i % TC_H;
-        sVec[i] = (p.vec_src[v] != nullptr && c < p.vec_len[v]) ? __ldg(p.vec_src[v] + c) : (v == 3 ? 1.0f : 0.0f);
+        // (gamma defaults to one where there is no LayerNorm weight at all, and is zero on padded columns)
+        sVec[i] = p.vec_src[v] != nullptr ? (c < p.vec_len[v] ? __ldg(p.vec_src[v] + c) : 0.0f) : (v == 3 ? 1.0f : 0.0f);
     }
     // This CTA's half (64 output rows) of every weight block as K-major BF16 image(s):  B[n][k] = W[(row0 + n) * ld + col0 + k]
     // (transposed: W[(row0 + k) * ld + col0 + n]), element (n, k) at (n / 8) * 2048 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2.
@@ -621,9 +623,13 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     }
                 }
                 if (lnb) tmem_st_wait();
-                float m1 = s1 * (1.0f / NC);
+                // zero-padded columns (y = 0 exactly) took part in the sums with y - y0 = -y0: take them out, then divide by the
+                // LayerNorm's own width
+                const float pad = (float)(TC_H - p.ln_n), inv_n = 1.0f / (float)(SPLIT ? NC : p.ln_n);
+                if (!SPLIT) { s1 = fmaf(pad, y0, s1); s2 = fmaf(-pad * y0, y0, s2); }
+                float m1 = s1 * inv_n;
                 mean = y0 + m1;
-                float var = fmaxf(s2 * (1.0f / NC) - m1 * m1, 0.0f);
+                float var = fmaxf(s2 * inv_n - m1 * m1, 0.0f);
                 if (SPLIT) {
                     // This thread has the moments of its 64 columns; the other half of the row lives in the warp that shares the
                     // lane quarter.  Exchange (mean, M2) through four spare TMEM columns of the row (the A-operand columns are free
@@ -642,8 +648,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     m1 = 0.0f;
                 }
                 rstd = 1.0f / sqrtf(var + LN_EPS);
-                gm1 = g1 * (1.0f / TC_H);                                  // mean of g
-                gm2 = (g2 - m1 * g1) * rstd * (1.0f / TC_H);               // mean of g * xhat
+                gm1 = g1 * inv_n;                                          // mean of g
+                gm2 = (g2 - m1 * g1) * rstd * inv_n;                       // mean of g * xhat
             }
             CGNN_STAMP(12);
             {
@@ -689,7 +695,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                                 for (int u = 0; u < 4; ++u) {
                                     const float xh = (v[j + u] - mean) * rstd;
                                     dgx[j + u] = du[j + u] * xh;
-                                    v[j + u] = rstd * (du[j + u] * gmj[u] - gm1 - xh * gm2);
+                                    v[j + u] = cc + j + u < p.ln_n ? rstd * (du[j + u] * gmj[u] - gm1 - xh * gm2) : 0.0f;   // no gradient into the padding
                                 }
                             }
                             receiver_sum16x2(dgx, du, 32, lane);       // the two column sums share one butterfly (their chains overlap)
@@ -839,6 +845,8 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     p.n_rows = op.rows; p.n_pair_tiles = (op.rows + 255) / 256;
     p.n_in = n_in; p.n_layers = op.n_layers; p.k = k; p.kshift = kshift;
     p.ln_mode = op.ln_bwd ? 2 : (op.gamma != nullptr ? 1 : 0);
+    p.ln_n = op.ln_n > 0 ? op.ln_n : TC_H;
+    CGNN_CHECK_ARG(p.ln_n <= TC_H, "tensor-core chain: LayerNorm width above 128");
     p.gather = gather; p.relu_out = op.relu_out; p.mask_src = op.mask_src; p.residual = op.residual;
     p.agg_out = op.agg_out; p.senders = op.senders; p.Ps = op.Ps; p.Pr = op.Pr;
     for (int l = 0; l < 2; ++l) { p.hid_mask[l] = op.hid_mask[l]; p.hid_out[l] = op.hid_out[l]; p.hid_agg[l] = op.hid_agg[l]; }
@@ -852,6 +860,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     }
     p.vec_src[3] = op.gamma; p.vec_src[4] = op.beta;
     for (int v = 0; v < 5; ++v) p.vec_len[v] = TC_H;
+    p.vec_len[3] = p.vec_len[4] = p.ln_n;
     if (op.out_valid > 0) p.vec_len[op.n_layers - 1] = op.out_valid;       // bias of a narrow last layer
     if (g_stamps != nullptr && g_stamp_next < g_stamp_launches) {
         p.stamps = g_stamps + (size_t)(g_stamp_next++) * 2 * g_stamp_tiles * 16;
@@ -881,7 +890,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     // Measured (profiles/r02_chain_stage_stamps.txt): the split shortens a tile's own time (39.1 k -> 34.0 k cycles) but not
     // the tile period (39.6 k vs 39.9 k) nor the step, so it is opt-in (CGNN_SPLIT=1) until the coupling is understood.
     static const bool split_allowed = getenv("CGNN_SPLIT") != nullptr && atoi(getenv("CGNN_SPLIT")) != 0;
-    const bool split = split_allowed && op.n_layers == 3 && op.gamma != nullptr && !op.ln_bwd && !any_hidden && !fin_a &&
+    const bool split = split_allowed && p.ln_n == TC_H && op.n_layers == 3 && op.gamma != nullptr && !op.ln_bwd && !any_hidden && !fin_a &&
                        !op.hid_out[0] && !op.hid_out[1] && !op.hid_agg[0] && !op.hid_agg[1] && !op.bits_out && !op.mask_bits;
     const int cfg = (op.n_layers == 3 ? C_L3 : 0) | (op.ln_bwd ? C_LNB : (op.gamma ? C_LN : 0)) | (fin_a ? C_SA : 0) | (fin_b ? C_SB : 0) |
                     (any_hidden ? C_HS : 0) | (any_agg ? C_AGG : 0) | (rin ? C_RIN : 0) | (gather ? C_GIN : 0) | (split ? C_SPLIT : 0);

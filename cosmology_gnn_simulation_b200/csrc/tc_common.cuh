@@ -59,6 +59,7 @@ struct ChainOp {
     ChainBlock blk[4];            // n_in + n_layers - 1 weight blocks
     const float* bias[3];         // per layer (nullable)
     const float* gamma; const float* beta;      // LayerNorm after the last layer (nullable)
+    int ln_n;                     // LayerNorm width: the first ln_n of the 128 outputs (0 = all 128; the rest must be zero padding)
     int relu_out;                 // ReLU on the result (before mask / residual)
     int out_valid;                // > 0: the last layer has only this many outputs (bias zero-padded to 128)
     int k;                        // > 0: rows per receiver (gather and/or segmented sum)

@@ -175,7 +175,7 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
         op.blk[1] = {m.W[1], TC_H, 0, 0, 0};
         op.blk[2] = {m.W[2], TC_H, 0, 0, 0};
         op.bias[0] = nullptr;                         // b1 is folded into P_r
-        op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta;
+        op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim;
         op.k = a.k; op.senders = a.senders; op.Ps = Ps; op.Pr = Pr;
         op.residual = a.e_in; op.agg_out = a.agg_out; op.out = a.out;
         return run_chain(op, s);
@@ -200,7 +200,7 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
         op.blk[1] = {m.W[0], 2 * TC_H, 0, TC_H, 0};
         op.blk[2] = {m.W[1], TC_H, 0, 0, 0};
         op.blk[3] = {m.W[2], TC_H, 0, 0, 0};
-        op.bias[0] = m.b[0]; op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta;
+        op.bias[0] = m.b[0]; op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim;
         op.residual = a.h; op.out = a.out;
         return run_chain(op, s);
     }
@@ -230,7 +230,7 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
             op.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim};
             op.blk[1] = {m.W[1], TC_H, 0, 0, 0};
             op.blk[2] = {m.W[2], TC_H, 0, 0, 0, m.out_dim, 0};
-            op.bias[0] = m.b[0]; op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta;
+            op.bias[0] = m.b[0]; op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim;
             op.out_valid = m.out_dim < TC_H ? m.out_dim : 0;
             op.out = m.out_dim == TC_H ? a.out + r0 * TC_H : O;
             if ((rc = run_chain(op, s))) return rc;
@@ -290,7 +290,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
         if (m.gamma != nullptr) {   // dY = LayerNorm backward of (Y = A2 W3^T + b3, dU), in the chain's final epilogue
             ChainOp op = base_op(ns, sc, rows);
             op.in0 = A2; op.blk[0] = {m.W[2], TC_H, 0, 0, 0}; op.bias[0] = m.b[2];
-            op.gamma = m.gamma; op.beta = m.beta; op.ln_bwd = 1; op.k = k;
+            op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim; op.ln_bwd = 1; op.k = k;
             op.du_rows = du_rows; op.du_recv = du_recv; op.dgamma = g->ln_gamma; op.dbeta = g->ln_beta; op.accumulate = accumulate; op.ln_ws = sc.lnb;
             op.out = T;
             if ((rc = run_chain(op, s))) return rc;
@@ -322,7 +322,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
     r.out_valid = m.out_dim < TC_H ? m.out_dim : 0;
     r.hid_out[0] = A1; r.hid_out[1] = A2;
     if (m.gamma != nullptr) {
-        r.gamma = m.gamma; r.beta = m.beta; r.ln_bwd = 1; r.k = k;
+        r.gamma = m.gamma; r.beta = m.beta; r.ln_n = m.ln_dim; r.ln_bwd = 1; r.k = k;
         r.du_rows = du_rows; r.du_recv = du_recv; r.dgamma = g->ln_gamma; r.dbeta = g->ln_beta; r.accumulate = accumulate; r.ln_ws = sc.lnb;
         r.out = T;
     } else {

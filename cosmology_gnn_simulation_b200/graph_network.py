@@ -84,6 +84,27 @@ class _Plan:
         self.edge_buffers = edge_buffers      # forced number of edge-stream buffers (0: from the free memory)
         self.grad_enabled = torch.is_grad_enabled()      # sampled where the module is called (autograd runs Function.forward in no-grad mode)
 
+    def padded_for_tensor_cores(self):
+        """The same plan over zero-padded copies of the parameters (ops.PaddedMlp) when the tensor-core precisions meet a
+        latent / hidden width below 128; None when no padding is needed (or possible: widths above 128 keep the FP32 path)."""
+        L, H = self.enc_node.out_dim, self.enc_node.hidden
+        t = ops.TC_WIDTH
+        if self.precision == "fp32" or (L == t and H == t) or L > t or H > t or len(self.enc_node.weights) != 3:
+            return None
+        pad = {}
+
+        def p(mp, blocks):
+            pad[id(mp)] = ops.PaddedMlp(mp, blocks, L)
+            return pad[id(mp)]
+
+        groups_by_id = {id(mp): first for mp, first in self.groups}
+        q = _Plan(self.n_steps, self.message, self.precision, self.k, p(self.enc_node, 0), p(self.enc_edge, 0),
+                  [p(m, 2) for m in self.proc_node], [p(m, 3) for m in self.proc_edge], p(self.dec_acc, 1), p(self.dec_temp, 1),
+                  None, self.edge_buffers, self.halo)
+        q.groups = [(pad[i], first) for i, first in groups_by_id.items()]
+        q.grad_enabled = self.grad_enabled
+        return q
+
 
 _STREAM_PLANS = {}
 
@@ -124,6 +145,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan: _Plan, senders, transpose_fn, x, edge_attr, *params):
+        plan = plan.padded_for_tensor_cores() or plan       # widths below 128: zero-padded parameters, 128-wide latents inside
         p, M, k, prec = plan, plan.n_steps, plan.k, plan.precision
         n, L = x.shape[0], plan.enc_node.out_dim
         e_count = edge_attr.shape[0]
@@ -229,6 +251,8 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         index_of = {id(mp): first for mp, first in p.groups}
 
         def put(mp: MlpParams, tensors):
+            if isinstance(mp, ops.PaddedMlp):
+                tensors = mp.unpad(tensors)
             first = index_of[id(mp)]
             for i, g in enumerate(tensors):
                 grads[first + i] = g

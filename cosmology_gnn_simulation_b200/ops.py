@@ -99,6 +99,7 @@ class MlpParams:
         self.weights = list(weights)
         self.biases = list(biases)
         self.gamma, self.beta = gamma, beta
+        self.ln_dim = 0                      # LayerNorm width when the outputs are zero-padded to 128 (0: all of out_dim)
         nl = len(self.weights)
         if not (1 <= nl <= _lib.MAX_LAYERS):
             raise ValueError(f"cgnn supports 1..{_lib.MAX_LAYERS} Linear layers per MLP, got {nl}")
@@ -132,6 +133,7 @@ class MlpParams:
             m.b[i] = b.data_ptr()
         m.ln_gamma = None if self.gamma is None else self.gamma.data_ptr()
         m.ln_beta = None if self.beta is None else self.beta.data_ptr()
+        m.ln_dim = self.ln_dim
         return m
 
     def new_grads(self):
@@ -147,6 +149,63 @@ class MlpParams:
             g.ln_gamma, g.ln_beta = gg.data_ptr(), gb.data_ptr()
             outs += [gg, gb]
         return g, outs
+
+
+TC_WIDTH = 128            # latent = hidden width of the tcgen05 tiles
+
+
+class PaddedMlp(MlpParams):
+    """Zero-padded copy of an MLP for the 128-wide tensor-core tiles: hidden layers and LayerNorm'd outputs become 128 wide
+    (padded rows / columns / biases / gamma / beta are zero, the LayerNorm keeps its own width through `ln_dim`), a first
+    layer that reads a concatenation of `in_blocks` latents gets each block at a 128-column offset.  With zero padding every
+    padded activation is exactly zero, so the real columns carry exactly the unpadded network (README.md:59-62 allows latent
+    sizes 64 / 128 / 256; 64 runs this way).  `unpad(grads)` cuts the parameter gradients back to the real shapes."""
+
+    def __init__(self, mp: MlpParams, in_blocks: int, latent: int):
+        t, nl = TC_WIDTH, len(mp.weights)
+        self.orig, self.cuts = mp, []
+        ws, bs = [], []
+        for i, (w, b) in enumerate(zip(mp.weights, mp.biases)):
+            o_real, i_real = w.shape
+            o_pad = t if (i < nl - 1 or mp.gamma is not None) else o_real
+            if i > 0:
+                cols = [(0, 0, i_real)]                                   # (offset in the padded input, offset in the real input, width)
+                i_pad = t
+            elif in_blocks == 0:
+                cols, i_pad = [(0, 0, i_real)], i_real
+            else:
+                assert i_real == in_blocks * latent
+                cols, i_pad = [(j * t, j * latent, latent) for j in range(in_blocks)], in_blocks * t
+            wp = torch.zeros((o_pad, i_pad), dtype=torch.float32, device=w.device)
+            for po, ro, wd in cols:
+                wp[:o_real, po:po + wd] = w.detach()[:, ro:ro + wd]
+            bp = torch.zeros(o_pad, dtype=torch.float32, device=w.device)
+            bp[:o_real] = b.detach()
+            ws.append(wp)
+            bs.append(bp)
+            self.cuts.append((o_real, i_real, cols))
+        gamma = beta = None
+        if mp.gamma is not None:
+            gamma = torch.zeros(t, dtype=torch.float32, device=mp.gamma.device)
+            beta = torch.zeros(t, dtype=torch.float32, device=mp.gamma.device)
+            gamma[:mp.out_dim] = mp.gamma.detach()
+            beta[:mp.out_dim] = mp.beta.detach()
+        super().__init__(ws, bs, gamma, beta)
+        if mp.gamma is not None:
+            self.ln_dim = mp.out_dim
+
+    def unpad(self, grads):
+        out = []
+        for i, (o_real, i_real, cols) in enumerate(self.cuts):
+            gw, gb = grads[2 * i], grads[2 * i + 1]
+            w = torch.empty((o_real, i_real), dtype=torch.float32, device=gw.device)
+            for po, ro, wd in cols:
+                w[:, ro:ro + wd] = gw[:o_real, po:po + wd]
+            out += [w, gb[:o_real].contiguous()]
+        if self.gamma is not None:
+            n = self.orig.out_dim
+            out += [grads[-2][:n].contiguous(), grads[-1][:n].contiguous()]
+        return out
 
 
 def _rows_ws(mlp_c: CgnnMlp, rows: int, precision: str, backward: int, device):

@@ -43,6 +43,10 @@ typedef struct {
     const float* b[CGNN_MAX_LAYERS];    /* b[l]: [out_l] */
     const float* ln_gamma;              /* [out_dim] or NULL: no LayerNorm (decoders) */
     const float* ln_beta;
+    int32_t ln_dim;                     /* 0 = out_dim.  Tensor-core precisions only: the LayerNorm spans the first ln_dim of
+                                         * out_dim = 128 outputs, the rest is zero padding (weights, biases, gamma, beta of the
+                                         * padded rows are zero) -- how latent / hidden widths below 128 run on the 128-wide
+                                         * tcgen05 tiles (graph_network.py zero-pads the parameters, README.md:59-62 shapes) */
 } cgnn_mlp;
 
 /* Gradient destinations, same shapes as cgnn_mlp; written (=), not accumulated. */

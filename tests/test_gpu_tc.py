@@ -291,6 +291,20 @@ def test_model_tensor_core_mode_matches_oracle(message):
     _compare_with_oracle(message, dict(n=1500, k=16, L=128, H=128, nh=2, M=4), "bf16x3", TOL_TC, gtol=1e-2)
 
 
+@pytest.mark.parametrize("message", ["sender", "edge"])
+@pytest.mark.parametrize("cfg", [dict(n=1200, k=16, L=64, H=64, nh=2, M=5),         # BASELINE config 1's shape (latent 64, 5 steps)
+                                 dict(n=500, k=8, L=32, H=96, nh=2, M=2)])          # hidden != latent
+def test_narrow_widths_run_on_the_tensor_cores(message, cfg):
+    """Latent / hidden widths below 128 (README.md:59-62: latent 64) in 'bf16x3': the parameters are zero-padded to the
+    128-wide tcgen05 tiles (ops.PaddedMlp), the LayerNorms keep their own width (cgnn_mlp.ln_dim).  There is no FP32
+    fallback for the processor phases in the tensor-core precisions, so passing means the tensor-core chain ran."""
+    from test_gpu_parity import _compare_with_oracle, TOL_TC
+    from cosmology_gnn_simulation_b200 import _lib
+    l0 = _lib.launch_count()
+    _compare_with_oracle(message, cfg, "bf16x3", TOL_TC, gtol=1e-2)
+    assert _lib.launch_count() > l0
+
+
 # ------------------------------------------------------------------------------------------------
 # row-wise MLPs (encoders: narrow input + LayerNorm; decoders: narrow output, no LayerNorm)
 # ------------------------------------------------------------------------------------------------
