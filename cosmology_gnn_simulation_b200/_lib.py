@@ -54,7 +54,7 @@ SIGNATURES = {
     "cgnn_mlp_rows_bwd": (c_int, [POINTER(CgnnMlp), POINTER(CgnnMlpGrad), c_void_p, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_mp_edge_fwd_workspace_bytes": (c_int64, [POINTER(CgnnMlp), c_int64, c_int32]),
-    "cgnn_mp_edge_fwd": (c_int, [POINTER(CgnnMlp), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p,
+    "cgnn_mp_edge_fwd": (c_int, [POINTER(CgnnMlp), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                  c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_aggregate_senders": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "cgnn_mp_node_fwd_workspace_bytes": (c_int64, [POINTER(CgnnMlp), c_int64, c_int32]),
@@ -64,7 +64,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_mp_bwd_workspace_bytes": (c_int64, [POINTER(CgnnMlp), c_int64, c_int64, c_int32, c_int32]),
     "cgnn_mp_edge_bwd": (c_int, [POINTER(CgnnMlp), POINTER(CgnnMlpGrad), c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_scatter_to_senders": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                         c_void_p, c_void_p]),

@@ -125,15 +125,17 @@ extern "C" int64_t cgnn_mp_edge_fwd_workspace_bytes(const cgnn_mlp* mlp, int64_t
 }
 
 extern "C" int cgnn_mp_edge_fwd(const cgnn_mlp* mlp, const float* h, const float* e_in, const int32_t* senders,
-                                int64_t n, int64_t n_nodes, int32_t k, float* e_out, float* agg_edge, void* workspace,
+                                int64_t n, int64_t n_nodes, int32_t k, int32_t k_valid, float* e_out, float* agg_edge, void* workspace,
                                 int64_t workspace_bytes, int32_t precision, cgnn_stream stream) {
     int rc = mlp_validate(mlp, "cgnn_mp_edge_fwd");
     if (rc) return rc;
     if ((rc = check_latent(mlp, 3, "cgnn_mp_edge_fwd"))) return rc;
     CGNN_CHECK_ARG(h && e_in && senders && (e_out || agg_edge) && n >= 1 && n_nodes >= n, "cgnn_mp_edge_fwd: bad arguments");
     CGNN_CHECK_ARG(k >= 1 && k <= 64, "cgnn_mp_edge_fwd: need 1 <= k <= 64");
+    CGNN_CHECK_ARG(k_valid >= 0 && k_valid <= k && (k_valid == 0 || k_valid == k || is_tc(precision)),
+                   "cgnn_mp_edge_fwd: k_valid must be 0 or in 1..k (padded in-degrees are a tensor-core feature; the FP32 kernels take any k)");
     MlpTask a{};
-    a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.n_nodes = n_nodes; a.k = k; a.L = mlp->out_dim;
+    a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.n_nodes = n_nodes; a.k = k; a.k_valid = k_valid; a.L = mlp->out_dim;
     a.h = h; a.e_in = e_in; a.senders = senders; a.out = e_out; a.agg_out = agg_edge;
     return run_fwd(a, precision, (cudaStream_t)stream, workspace, workspace_bytes);
 }
@@ -186,7 +188,7 @@ extern "C" int cgnn_mp_node_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, 
 
 extern "C" int cgnn_mp_edge_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const float* h, const float* e_in,
                                 const int32_t* senders, const int32_t* t_rowptr, const int32_t* t_perm, int64_t n,
-                                int64_t n_nodes, int32_t k,
+                                int64_t n_nodes, int32_t k, int32_t k_valid,
                                 const float* de_next, const float* dagg, float* de, float* dh, float* gs,
                                 void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream) {
     int rc = mlp_validate(mlp, "cgnn_mp_edge_bwd");
@@ -195,8 +197,9 @@ extern "C" int cgnn_mp_edge_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, 
     CGNN_CHECK_ARG(grad && h && e_in && senders && t_rowptr && t_perm && dagg && de && dh && n >= 1 && n_nodes >= n,
                    "cgnn_mp_edge_bwd: bad arguments");
     CGNN_CHECK_ARG(k >= 1 && k <= 32, "cgnn_mp_edge_bwd: need 1 <= k <= 32 (got %d)", k);      // the FP32 backward tile holds 32 rows
+    CGNN_CHECK_ARG(k_valid >= 0 && k_valid <= k && (k_valid == 0 || k_valid == k || is_tc(precision)), "cgnn_mp_edge_bwd: bad k_valid");
     MlpTask a{};
-    a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.n_nodes = n_nodes; a.k = k; a.L = mlp->out_dim;
+    a.mlp = mlp_to_dev(mlp); a.mode = MODE_EDGE; a.n = n; a.n_nodes = n_nodes; a.k = k; a.k_valid = k_valid; a.L = mlp->out_dim;
     a.h = h; a.e_in = e_in; a.senders = senders; a.de_next = de_next; a.dagg = dagg;
     a.de = de; a.dh = dh; a.gs = gs; a.need_input_grad = 1;
     a.t_rowptr = t_rowptr; a.t_perm = t_perm;

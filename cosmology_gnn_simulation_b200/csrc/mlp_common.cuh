@@ -29,6 +29,7 @@ struct MlpTask {
     int64_t n;                  // ROWS: rows; EDGE/NODE: number of nodes (receivers)
     int64_t n_nodes;            // EDGE: rows of h / dh (receivers first, then halo senders); == n on one GPU
     int k, L;                   // EDGE: in-degree; EDGE/NODE: latent width
+    int k_valid;                // EDGE, tensor-core precisions: real in-degree when k is padded to a power of two (0: k itself)
     int act_stride;             // shared-memory row stride of the activation buffers
     // forward inputs
     const float* x;             // ROWS  [rows][in_dim]

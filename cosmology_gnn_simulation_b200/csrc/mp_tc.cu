@@ -57,6 +57,8 @@ struct TcParams {
     int n_layers;               // Linear layers (1 or 3)
     int k;                      // rows per receiver (gather / per-receiver sums), a power of two <= 32; 1 when unused
     int kshift;                 // log2(k)
+    int k_valid;                // 0, or the real in-degree when the k rows of a receiver are padded up to the power of two: rows of
+                                // rank >= k_valid are dummies (no part in per-receiver sums, no gradient)
     int ln_mode;                // 0: none, 1: LayerNorm forward, 2: LayerNorm backward (the result is dY)
     int ln_n;                   // LayerNorm width: columns [ln_n, 128) are zero padding (accumulator, bias, gamma, beta all zero there)
     int gather;                 // layer-1 pre-activation += Ps[sender] + Pr[receiver]
@@ -413,6 +415,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             const bool valid = row0 + r < p.n_rows;
             const int64_t grow = valid ? row0 + r : p.n_rows - 1;           // clamped: loads of padded rows stay in bounds
             const int64_t recv = grow >> p.kshift;
+            const bool dummy = p.k_valid > 0 && (int)(grow & (int64_t)(k - 1)) >= p.k_valid;     // padded edge of a non-power-of-two in-degree
             const size_t rowoff = (size_t)grow * TC_H, recvoff = (size_t)recv * TC_H;
             // the sender index is fetched now so that the address of the gathered P_s row is ready when its epilogue starts
             const int32_t snd = snd_next;
@@ -602,7 +605,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             // for the output pass, so the dU streams are read from global memory only once
                             float du[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) du[j] = valid ? (pa ? ca[j] : 0.0f) + (pb ? cb[j] : 0.0f) : 0.0f;
+                            for (int j = 0; j < 16; ++j) du[j] = valid && !dummy ? (pa ? ca[j] : 0.0f) + (pb ? cb[j] : 0.0f) : 0.0f;
                             tmem_st_32x32b_x16(tAhi + cc, reinterpret_cast<const uint32_t*>(du));
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
@@ -759,6 +762,10 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             st16(outp + cc, v);
                         }
                         if (aggp) {
+                            if (dummy) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+                            }
                             // per-receiver sums, two 16-column blocks per butterfly: the even block waits for the odd one
                             if ((hh & 1) == 0) {
 #pragma unroll
@@ -844,6 +851,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     TcParams p{};
     p.n_rows = op.rows; p.n_pair_tiles = (op.rows + 255) / 256;
     p.n_in = n_in; p.n_layers = op.n_layers; p.k = k; p.kshift = kshift;
+    p.k_valid = (uses_k && op.k_valid > 0 && op.k_valid < k) ? op.k_valid : 0;
     p.ln_mode = op.ln_bwd ? 2 : (op.gamma != nullptr ? 1 : 0);
     p.ln_n = op.ln_n > 0 ? op.ln_n : TC_H;
     CGNN_CHECK_ARG(p.ln_n <= TC_H, "tensor-core chain: LayerNorm width above 128");

@@ -63,6 +63,7 @@ struct ChainOp {
     int relu_out;                 // ReLU on the result (before mask / residual)
     int out_valid;                // > 0: the last layer has only this many outputs (bias zero-padded to 128)
     int k;                        // > 0: rows per receiver (gather and/or segmented sum)
+    int k_valid;                  // 0 or the real in-degree below a padded k (rows of rank >= k_valid are dummies)
     const int32_t* senders; const float* Ps; const float* Pr;   // gather: layer-1 pre-activation += Ps[sender] + Pr[row / k]
     const float* mask_src;        // result = mask_src > 0 ? result : 0   (nullable)
     const float* residual;        // result += residual                   (nullable)

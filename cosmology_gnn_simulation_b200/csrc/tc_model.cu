@@ -176,7 +176,7 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
         op.blk[2] = {m.W[2], TC_H, 0, 0, 0};
         op.bias[0] = nullptr;                         // b1 is folded into P_r
         op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim;
-        op.k = a.k; op.senders = a.senders; op.Ps = Ps; op.Pr = Pr;
+        op.k = a.k; op.k_valid = a.k_valid; op.senders = a.senders; op.Ps = Ps; op.Pr = Pr;
         op.residual = a.e_in; op.agg_out = a.agg_out; op.out = a.out;
         return run_chain(op, s);
     }
@@ -272,7 +272,7 @@ static int bwd_mode(int64_t rows) {
 // (decoders) the caller has put dY, zero padded to 128 columns, into T.
 static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn_mlp_grad* g, int64_t rows, ChainOp r,
                           float* A1, float* A2, float* T, float* G2, uint32_t* gate1, uint32_t* gate2,
-                          const float* du_rows, const float* du_recv, int k,
+                          const float* du_rows, const float* du_recv, int k, int k_valid,
                           ChainBlock last, const float* residual, float* d_in, float* g1_out, float* g1_agg,
                           int accumulate, cudaStream_t s) {
     int rc;
@@ -290,7 +290,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
         if (m.gamma != nullptr) {   // dY = LayerNorm backward of (Y = A2 W3^T + b3, dU), in the chain's final epilogue
             ChainOp op = base_op(ns, sc, rows);
             op.in0 = A2; op.blk[0] = {m.W[2], TC_H, 0, 0, 0}; op.bias[0] = m.b[2];
-            op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim; op.ln_bwd = 1; op.k = k;
+            op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim; op.ln_bwd = 1; op.k = k; op.k_valid = k_valid;
             op.du_rows = du_rows; op.du_recv = du_recv; op.dgamma = g->ln_gamma; op.dbeta = g->ln_beta; op.accumulate = accumulate; op.ln_ws = sc.lnb;
             op.out = T;
             if ((rc = run_chain(op, s))) return rc;
@@ -322,7 +322,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
     r.out_valid = m.out_dim < TC_H ? m.out_dim : 0;
     r.hid_out[0] = A1; r.hid_out[1] = A2;
     if (m.gamma != nullptr) {
-        r.gamma = m.gamma; r.beta = m.beta; r.ln_n = m.ln_dim; r.ln_bwd = 1; r.k = k;
+        r.gamma = m.gamma; r.beta = m.beta; r.ln_n = m.ln_dim; r.ln_bwd = 1; r.k = k; r.k_valid = k_valid;
         r.du_rows = du_rows; r.du_recv = du_recv; r.dgamma = g->ln_gamma; r.dbeta = g->ln_beta; r.accumulate = accumulate; r.ln_ws = sc.lnb;
         r.out = T;
     } else {
@@ -381,7 +381,7 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             ChainOp r{};
             r.in0 = in; r.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim}; r.bias[0] = m.b[0];
             // dx = G1 W1 (in_dim == 128) comes out of the dgrad chain's last layer
-            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, dU, nullptr, 1, {m.W[0], m.in_dim, 0, 0, 1, m.in_dim, 0},
+            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, dU, nullptr, 1, 0, {m.W[0], m.in_dim, 0, 0, 1, m.in_dim, 0},
                                      nullptr, a.dx ? a.dx + r0 * TC_H : nullptr, G1, nullptr, acc, s))) return rc;
             if ((rc = run_wgrad(ns, G1, in, rows, g->W[0], m.in_dim, 0, g->b[0], acc, sc.wg, s, 0, m.in_dim))) return rc;
         }
@@ -405,7 +405,7 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         r.blk[0] = {m.W[0], 2 * TC_H, 0, 0, 0}; r.blk[1] = {m.W[0], 2 * TC_H, 0, TC_H, 0};
         r.bias[0] = m.b[0];
         // dh = dh_next + G1 W1[:, 0:L] is the dgrad chain's last layer
-        if ((rc = fused_backward(ns, sc, m, g, n, r, A1, A2, T, G2, gate1, gate2, a.dout, nullptr, 1, {m.W[0], 2 * TC_H, 0, 0, 1}, a.dout, a.dh, G1,
+        if ((rc = fused_backward(ns, sc, m, g, n, r, A1, A2, T, G2, gate1, gate2, a.dout, nullptr, 1, 0, {m.W[0], 2 * TC_H, 0, 0, 1}, a.dout, a.dh, G1,
                                  nullptr, 0, s))) return rc;
         // dW1 = G1^T [h | agg], db1
         if ((rc = run_wgrad(ns, G1, a.h, n, g->W[0], 2 * TC_H, 0, g->b[0], 0, sc.wg, s))) return rc;
@@ -446,8 +446,8 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             // de = de_next + G1 W1e is the dgrad chain's last layer, the per-receiver sum of G1 is d P_r
             ChainOp r{};
             r.in0 = e_in; r.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 0};
-            r.k = a.k; r.senders = a.senders + r0; r.Ps = Ps; r.Pr = Pr + (r0 / k) * TC_H;
-            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, de_next, a.dagg + (r0 / k) * TC_H, a.k,
+            r.k = a.k; r.k_valid = a.k_valid; r.senders = a.senders + r0; r.Ps = Ps; r.Pr = Pr + (r0 / k) * TC_H;
+            if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, de_next, a.dagg + (r0 / k) * TC_H, a.k, a.k_valid,
                                      {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}, de_next, a.de + r0 * TC_H, G1, dPr + (r0 / k) * TC_H, acc, s))) return rc;
             // dW1e = G1^T e, db1
             if ((rc = run_wgrad(ns, G1, e_in, rows, g->W[0], 3 * TC_H, 2 * TC_H, g->b[0], acc, sc.wg, s))) return rc;

@@ -74,9 +74,10 @@ class _Plan:
     """Static description of one forward call, shared by forward and backward."""
 
     def __init__(self, n_steps, message, precision, k, enc_node, enc_edge, proc_node, proc_edge, dec_acc,
-                 dec_temp, groups, edge_buffers, halo=None):
+                 dec_temp, groups, edge_buffers, halo=None, k_valid=0):
         self.halo = halo                      # slab.HaloPlan of a sharded box, or None
         self.n_steps, self.message, self.precision, self.k = n_steps, message, precision, k
+        self.k_valid = k_valid                # real in-degree when k is the padded power of two (0: k itself)
         self.enc_node, self.enc_edge = enc_node, enc_edge
         self.proc_node, self.proc_edge = proc_node, proc_edge
         self.dec_acc, self.dec_temp = dec_acc, dec_temp
@@ -100,7 +101,7 @@ class _Plan:
         groups_by_id = {id(mp): first for mp, first in self.groups}
         q = _Plan(self.n_steps, self.message, self.precision, self.k, p(self.enc_node, 0), p(self.enc_edge, 0),
                   [p(m, 2) for m in self.proc_node], [p(m, 3) for m in self.proc_edge], p(self.dec_acc, 1), p(self.dec_temp, 1),
-                  None, self.edge_buffers, self.halo)
+                  None, self.edge_buffers, self.halo, self.k_valid)
         q.groups = [(pad[i], first) for i, first in groups_by_id.items()]
         q.grad_enabled = self.grad_enabled
         return q
@@ -191,7 +192,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
             e = ops.mlp_rows_fwd(p.enc_edge, edge_attr, prec)
             for t in range(M):
                 agg = torch.empty((n, L), dtype=torch.float32, device=dev)
-                ops.mp_edge_fwd(p.proc_edge[t], h, e, senders, k, e if t + 1 < M else None, agg, prec)   # e^M is never read
+                ops.mp_edge_fwd(p.proc_edge[t], h, e, senders, k, e if t + 1 < M else None, agg, prec, p.k_valid)   # e^M is never read
                 h = node_phase(t, h, agg)
             del e
         else:
@@ -206,7 +207,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
                 _EncodeProcessDecodeFn._advance(p, act, bufs, edge_attr, senders, hs, e_count, L, first=True,
                                                 node_phase=node_phase)
             agg = torch.empty((n, L), dtype=torch.float32, device=dev)
-            ops.mp_edge_fwd(p.proc_edge[M - 1], hs[M - 1], bufs[last], senders, k, None, agg, prec)     # e^M is never read
+            ops.mp_edge_fwd(p.proc_edge[M - 1], hs[M - 1], bufs[last], senders, k, None, agg, prec, p.k_valid)     # e^M is never read
             node_phase(M - 1, hs[M - 1], agg)
             h = hs[M]
         acc = ops.mlp_rows_fwd(p.dec_acc, h[:n], prec)
@@ -235,10 +236,10 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         if first:                                           # the real forward of step t
             h = hs[t]
             agg = torch.empty((h.shape[0] if p.halo is None else p.halo.n_own, L), dtype=torch.float32, device=h.device)
-            ops.mp_edge_fwd(p.proc_edge[t], h, bufs[src], senders, k, bufs[dst], agg, prec)
+            ops.mp_edge_fwd(p.proc_edge[t], h, bufs[src], senders, k, bufs[dst], agg, prec, p.k_valid)
             node_phase(t, h, agg)
         else:                                               # recompute of the edge phase alone
-            ops.mp_edge_fwd(p.proc_edge[t], hs[t], bufs[src], senders, k, bufs[dst], None, prec)
+            ops.mp_edge_fwd(p.proc_edge[t], hs[t], bufs[src], senders, k, bufs[dst], None, prec, p.k_valid)
 
     @staticmethod
     def backward(ctx, d_acc, d_temp):
@@ -291,7 +292,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
                 de_new = de if de is not None else torch.empty_like(e_t)
                 gs = torch.empty_like(e_t) if fp32 else None
                 put(p.proc_edge[t], ops.mp_edge_bwd(p.proc_edge[t], hs[t], e_t, senders, rowptr, perm, k, de, dagg,
-                                                    de_new, dh_new, gs, prec))
+                                                    de_new, dh_new, gs, prec, p.k_valid))
                 return dh_new, de_new
             ops.scatter_to_senders(dagg, True, rowptr, perm, k, dh_new)
             return dh_new, None
@@ -402,6 +403,20 @@ class EncodeProcessDecode(nn.Module):
         n_nodes = n if halo is None else halo.n_loc          # transpose rows: owned + halo senders
         if self.num_neighbors is not None and k != self.num_neighbors:
             raise ValueError(f"graph has in-degree {k}, model was built with num_neighbors={self.num_neighbors}")
+        k_valid = 0
+        if self.precision != "fp32" and self.message == "edge" and (k & (k - 1)) != 0:
+            # The tensor-core chain takes a power-of-two in-degree (a receiver's rows are a warp-aligned group): pad every
+            # receiver to the next power of two with dummy edges (sender = the receiver itself); the kernels keep rows of
+            # rank >= k_valid out of the per-receiver sums and give them no gradient.
+            if k > 32:
+                raise ValueError(f"the tensor-core precisions support at most 32 neighbours (graph has in-degree {k})")
+            k_pad = 1 << (k - 1).bit_length()
+            key = (senders.data_ptr(), senders._version, n, k_pad)
+            if self._graph_cache.get("pad_key") != key:
+                sp = torch.arange(n, dtype=torch.int32, device=senders.device).view(n, 1).repeat(1, k_pad)
+                sp[:, :k] = senders.view(n, k)
+                self._graph_cache["pad_key"], self._graph_cache["pad_senders"] = key, sp.reshape(-1).contiguous()
+            senders, k_valid, k = self._graph_cache["pad_senders"], k, k_pad
         holder = {}
 
         def transpose():
@@ -409,7 +424,7 @@ class EncodeProcessDecode(nn.Module):
                 holder["t"] = ops.csr_transpose(senders, n_nodes)
             return holder["t"]
 
-        return senders, k, transpose
+        return senders, k, k_valid, transpose
 
     def forward(self, input_graph) -> Dict[str, torch.Tensor]:
         x, edge_attr = input_graph.x, input_graph.edge_attr
@@ -440,9 +455,13 @@ class EncodeProcessDecode(nn.Module):
             flat += mp.tensors()
 
         n = x.shape[0]
-        senders, k, transpose = self._graph_tables(input_graph, n)
+        senders, k, k_valid, transpose = self._graph_tables(input_graph, n)
+        if k_valid:                                       # dummy edges carry zero features (differentiable w.r.t. the real ones)
+            padded = edge_attr.new_zeros((n, k, edge_attr.shape[1]))
+            padded[:, :k_valid] = edge_attr.view(n, k_valid, edge_attr.shape[1])
+            edge_attr = padded.view(n * k, -1)
         plan = _Plan(self._num_message_passing_steps, self.message, self.precision, k, enc_node, enc_edge,
                      proc_node, proc_edge, dec_acc, dec_temp, groups, self.edge_buffers,
-                     halo=getattr(input_graph, "halo", None))
+                     halo=getattr(input_graph, "halo", None), k_valid=k_valid)
         acc, temp = _EncodeProcessDecodeFn.apply(plan, senders, transpose, x, edge_attr, *flat)
         return {"acceleration": acc, "temp_rate": temp}

@@ -258,8 +258,9 @@ def mlp_rows_bwd(p: MlpParams, x: torch.Tensor, dout: torch.Tensor, need_dx: boo
 EDGE_FWD_EVENTS = None
 
 
-def mp_edge_fwd(p: MlpParams, h, e_in, senders, k: int, e_out, agg_edge, precision: str = "fp32"):
-    """h may carry halo rows after the receivers (slab sharding): receivers = e_in rows / k, nodes = h rows."""
+def mp_edge_fwd(p: MlpParams, h, e_in, senders, k: int, e_out, agg_edge, precision: str = "fp32", k_valid: int = 0):
+    """h may carry halo rows after the receivers (slab sharding): receivers = e_in rows / k, nodes = h rows.
+    `k_valid`: the real in-degree when the k rows per receiver are padded (tensor-core precisions)."""
     m = p.c_struct()
     n_recv = e_in.shape[0] // k
     with torch.cuda.device(h.device):
@@ -271,7 +272,7 @@ def mp_edge_fwd(p: MlpParams, h, e_in, senders, k: int, e_out, agg_edge, precisi
         if nbytes < 0:
             check(-1, "cgnn_mp_edge_fwd_workspace_bytes")
         ws = workspace.get(h.device, "mlp", nbytes) if nbytes > 0 else None
-        check(lib().cgnn_mp_edge_fwd(byref(m), ptr(h), ptr(e_in), ptr(senders), n_recv, h.shape[0], k, ptr(e_out),
+        check(lib().cgnn_mp_edge_fwd(byref(m), ptr(h), ptr(e_in), ptr(senders), n_recv, h.shape[0], k, int(k_valid), ptr(e_out),
                                      ptr(agg_edge), ptr(ws), 0 if ws is None else ws.numel(), PREC[precision],
                                      stream_ptr(h.device)), "cgnn_mp_edge_fwd")
         if ev is not None:
@@ -330,7 +331,7 @@ def mp_node_bwd(p: MlpParams, h, agg, dh_next, dh, dagg, precision: str = "fp32"
 
 
 def mp_edge_bwd(p: MlpParams, h, e_in, senders, rowptr, perm, k: int, de_next, dagg, de, dh, gs,
-                precision: str = "fp32"):
+                precision: str = "fp32", k_valid: int = 0):
     """Edge-phase backward including the deterministic scatter of the sender gradients into `dh`
     (`rowptr`, `perm`: sender-sorted transpose from `csr_transpose`).  `de` may be `de_next` (in place); `gs` [E,L] is
     the scratch of the FP32 kernels (None for the tensor-core precisions)."""
@@ -340,7 +341,7 @@ def mp_edge_bwd(p: MlpParams, h, e_in, senders, rowptr, perm, k: int, de_next, d
     with torch.cuda.device(h.device):
         ws = _mp_bwd_ws(m, n_recv, k, precision, h.device, n_nodes=h.shape[0])
         check(lib().cgnn_mp_edge_bwd(byref(m), byref(g), ptr(h), ptr(e_in), ptr(senders), ptr(rowptr), ptr(perm),
-                                     n_recv, h.shape[0], k, ptr(de_next), ptr(dagg), ptr(de), ptr(dh), ptr(gs), ptr(ws),
+                                     n_recv, h.shape[0], k, int(k_valid), ptr(de_next), ptr(dagg), ptr(de), ptr(dh), ptr(gs), ptr(ws),
                                      ws.numel(), PREC[precision], stream_ptr(h.device)), "cgnn_mp_edge_bwd")
     return grads
 

@@ -165,8 +165,12 @@ int cgnn_mlp_rows_bwd(const cgnn_mlp* mlp, const cgnn_mlp_grad* grad, const floa
 /* Slab sharding: a rank's node array is [n owned receivers | halo senders], n_nodes rows in all; the
  * receivers are rows 0..n-1, `senders` index all n_nodes rows.  Single GPU: n_nodes == n. */
 int64_t cgnn_mp_edge_fwd_workspace_bytes(const cgnn_mlp* edge_mlp, int64_t n_nodes, int32_t precision);
+/* k_valid (tensor-core precisions; 0 or k = off): the chain needs k to be a power of two, so a graph of in-degree
+ * k_valid < k is padded per receiver to k rows -- rows of rank >= k_valid are dummies: they take no part in the
+ * per-receiver sums and get / give no gradient (graph_network.py pads senders and edge features; README.md:59-62
+ * allows 8..32 neighbours). */
 int cgnn_mp_edge_fwd(const cgnn_mlp* edge_mlp, const float* h, const float* e_in,
-                     const int32_t* senders, int64_t n, int64_t n_nodes, int32_t k, float* e_out,
+                     const int32_t* senders, int64_t n, int64_t n_nodes, int32_t k, int32_t k_valid, float* e_out,
                      float* agg_edge, void* workspace, int64_t workspace_bytes, int32_t precision,
                      cgnn_stream stream);
 int cgnn_aggregate_senders(const float* h, const int32_t* senders, int64_t n, int32_t k,
@@ -196,7 +200,7 @@ int cgnn_mp_node_bwd(const cgnn_mlp* node_mlp, const cgnn_mlp_grad* grad, const 
                      void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
 int cgnn_mp_edge_bwd(const cgnn_mlp* edge_mlp, const cgnn_mlp_grad* grad, const float* h,
                      const float* e_in, const int32_t* senders, const int32_t* t_rowptr,
-                     const int32_t* t_perm, int64_t n, int64_t n_nodes, int32_t k,
+                     const int32_t* t_perm, int64_t n, int64_t n_nodes, int32_t k, int32_t k_valid,
                      const float* de_next, const float* dagg, float* de, float* dh, float* gs,
                      void* workspace, int64_t workspace_bytes, int32_t precision, cgnn_stream stream);
 int cgnn_scatter_to_senders(const float* src, int32_t src_is_per_receiver, const int32_t* rowptr,

@@ -305,6 +305,15 @@ def test_narrow_widths_run_on_the_tensor_cores(message, cfg):
     assert _lib.launch_count() > l0
 
 
+@pytest.mark.parametrize("k", [5, 12, 24])
+def test_non_power_of_two_in_degree_on_the_tensor_cores(k):
+    """README.md:59-62 allows any neighbour count in 8..32; the tensor-core chain wants a power of two.  The model pads
+    every receiver with dummy edges (cgnn_mp_edge_fwd/_bwd `k_valid`): outputs, parameter gradients and the gradient
+    with respect to the real edge features must be those of the unpadded graph."""
+    from test_gpu_parity import _compare_with_oracle, TOL_TC
+    _compare_with_oracle("edge", dict(n=700, k=k, L=128, H=128, nh=2, M=3), "bf16x3", TOL_TC, gtol=1e-2)
+
+
 # ------------------------------------------------------------------------------------------------
 # row-wise MLPs (encoders: narrow input + LayerNorm; decoders: narrow output, no LayerNorm)
 # ------------------------------------------------------------------------------------------------
