@@ -239,7 +239,7 @@ def test_model_matches_oracle_fp32(message, cfg):
     _compare_with_oracle(message, cfg, "fp32", TOL_FP32)
 
 
-def _compare_with_oracle(message, cfg, precision, tol, ckpt=0, seed=0, gtol=None):
+def _compare_with_oracle(message, cfg, precision, tol, ckpt=0, seed=0, gtol=None, in_gtol=None):
     from cosmology_gnn_simulation_b200 import ops, synthetic
     from cosmology_gnn_simulation_b200.graph import Data
     from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
@@ -288,10 +288,10 @@ def _compare_with_oracle(message, cfg, precision, tol, ckpt=0, seed=0, gtol=None
     assert abs(ls["loss"].item() - lo["loss"].item()) < 10 * tol * abs(lo["loss"].item())
     gtol = tol * 5 if gtol is None else gtol
 
-    def grad_ok(got, ref64, ref32, what, slack=2.0):
+    def grad_ok(got, ref64, ref32, what, slack=2.0, bar=None):
         err = rel_l2(got.cpu(), ref64)
         floor = slack * rel_l2(ref32, ref64)
-        assert err < max(gtol, floor), (what, err, floor)
+        assert err < max(gtol if bar is None else bar, floor), (what, err, floor)
 
     for name, prm in model.named_parameters():
         ref = p64[name].grad
@@ -302,9 +302,9 @@ def _compare_with_oracle(message, cfg, precision, tol, ckpt=0, seed=0, gtol=None
             grad_ok(prm.grad, ref, p32[name].grad, name)
     # input gradients (never taken by the reference's training loop) are the most gate-flip sensitive
     # quantities: the CPU fp32 path itself sits 2e-3 from float64 on edge_attr at these sizes
-    grad_ok(xg.grad, x64.grad, x32.grad, "x", slack=4.0)
+    grad_ok(xg.grad, x64.grad, x32.grad, "x", slack=4.0, bar=in_gtol)
     if message == "edge":
-        grad_ok(eag.grad, ea64.grad, ea32.grad, "edge_attr", slack=4.0)
+        grad_ok(eag.grad, ea64.grad, ea32.grad, "edge_attr", slack=4.0, bar=in_gtol)
     return model, graph
 
 

