@@ -220,13 +220,17 @@ __device__ __forceinline__ void receiver_store16(float* dst, int c, const float*
 // C_GIN: the gather P_s[sender] + P_r[receiver] INITIALISES the layer-1 accumulator (written to TMEM in the input phase, the
 // MMAs then accumulate onto it) instead of being added in an epilogue.  C_SPLIT: 16 epilogue warps -- the two warps that
 // share a TMEM lane quarter take 64 columns each (LayerNorm moments combined through two spare TMEM columns).
-constexpr int C_L3 = 1, C_LN = 2, C_LNB = 4, C_SA = 8, C_SB = 16, C_HS = 32, C_AGG = 64, C_RIN = 128, C_GIN = 256, C_SPLIT = 512;
+// C_T1: one epilogue row stream of a one-layer chain (the dU rows of the LayerNorm backward, or the residual) comes through the
+// TMA ring as a second stream of the tile (tensor map 1) instead of thread = row global loads: 16 KB per instruction, requested by
+// the producer tiles ahead, where the scattered 32-byte sectors of the thread = row loads were the slowest part of those chains.
+constexpr int C_L3 = 1, C_LN = 2, C_LNB = 4, C_SA = 8, C_SB = 16, C_HS = 32, C_AGG = 64, C_RIN = 128, C_GIN = 256, C_SPLIT = 512, C_T1 = 1024;
 template <int NS, int CFG>
 __global__ void __launch_bounds__((CFG & C_SPLIT) ? TC_THREADS_SPLIT : TC_THREADS, 1)
 tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1, const TcParams p) {
     constexpr int NSI = NS == 3 ? 2 : 1;                    // weight / activation images per value (hi [, lo])
     constexpr bool L3 = (CFG & C_L3) != 0, SA = (CFG & C_SA) != 0, SB = (CFG & C_SB) != 0, HS = (CFG & C_HS) != 0, AGG = (CFG & C_AGG) != 0;
-    constexpr bool RIN = (CFG & C_RIN) != 0, GIN = (CFG & C_GIN) != 0, SPLIT = (CFG & C_SPLIT) != 0;
+    constexpr bool RIN = (CFG & C_RIN) != 0, GIN = (CFG & C_GIN) != 0, SPLIT = (CFG & C_SPLIT) != 0, T1 = (CFG & C_T1) != 0;
+    static_assert(!T1 || (!(CFG & C_L3) && !RIN && !SPLIT), "the ring-fed epilogue stream belongs to the one-layer chains");
     constexpr int NEPI = SPLIT ? 16 : 8;                    // epilogue warps
     constexpr int GW = NEPI / 2;                            // warps per epilogue group (= per tile in flight)
     constexpr int NTHR = (NEPI + 4) * 32;
@@ -314,7 +318,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             uint32_t buf = 0, use = 0;                 // ring slot of the next chunk and how often it has been used
             for (int64_t it = 0; it < n_it; ++it) {
                 const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
-                for (int ip = 0; ip < p.n_in; ++ip)
+                for (int ip = 0; ip < p.n_in + (T1 ? 1 : 0); ++ip)      // T1: the epilogue stream follows the MMA input(s), map 1
                     for (int q = 0; q < NCW; ++q) {
                         mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 100 + buf);
                         uint64_t* full = &bars->in_full[it & 1][buf];
@@ -337,8 +341,10 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             while (active > 0) {
                 for (int s = 0; s < 2; ++s) {
                     if (it_s[s] >= n_it) continue;
-                    if (!mbar_try_wait(&bars->a_ready[s], par[s])) {
-                        if (++spins > (1u << 27)) { printf("cgnn: MMA issuer timeout slot %d it %lld ph %d\n", s, (long long)it_s[s], ph_s[s]); __trap(); }
+                    // non-blocking probe: try_wait may suspend the thread for a while when the phase is not complete, and this
+                    // thread serves TWO barriers -- the other slot's operands may become ready in the meantime
+                    if (!mbar_test_wait(&bars->a_ready[s], par[s])) {
+                        if (++spins > (1u << 28)) { printf("cgnn: MMA issuer timeout slot %d it %lld ph %d\n", s, (long long)it_s[s], ph_s[s]); __trap(); }
                         continue;
                     }
                     spins = 0;
@@ -398,7 +404,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 
         // ring slot of this group's next tile's first chunk: advanced by the chunks of two tiles (its own and the other group's) per
         // iteration, wrapped by subtraction -- no division in the loops
-        const uint32_t uring = (uint32_t)NRING, tile_chunks = (uint32_t)(NCW * p.n_in);
+        const uint32_t uring = (uint32_t)NRING, tile_chunks = (uint32_t)(NCW * (p.n_in + (T1 ? 1 : 0)));
         uint32_t ring0 = (uint32_t)g * tile_chunks % uring;
         // sender index of the first tile's row; the next tile's is fetched one tile ahead so its latency never shows
         int32_t snd_next = 0;
@@ -546,6 +552,27 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             }
             // ---- final layer: bias, [gather], [LayerNorm fwd / bwd], [ReLU], [mask], per-receiver sum, residual, store ----
             constexpr bool lnb = LNB;
+            // T1: the dU rows (LayerNorm backward) or the residual arrive through the ring, 32 columns per slot, after the tile's
+            // MMA input; every thread reads its own row of a slot (two 16-column halves) and the slot goes back after the second
+            uint32_t tbuf = buf;
+            auto t1_load16 = [&](int cc, float* dst) {
+                if ((cc & 31) == 0) {
+                    mbar_wait_or_trap(&bars->in_full[g][tbuf], (in_par >> tbuf) & 1u, 190);
+                    in_par ^= 1u << tbuf;
+                }
+                const uint8_t* src = sRing + tbuf * CW_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 e4 = *reinterpret_cast<const float4*>(src + swz128(r, ((cc & 31) >> 2) + j));
+                    dst[4 * j] = e4.x; dst[4 * j + 1] = e4.y; dst[4 * j + 2] = e4.z; dst[4 * j + 3] = e4.w;
+                }
+                if ((cc & 31) == 16) {
+                    consume16(reinterpret_cast<const uint32_t*>(dst));      // (see the input phase: consume, then arrive)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_local(&bars->in_empty[tbuf]);
+                    tbuf = tbuf + 1 == uring ? 0 : tbuf + 1;
+                }
+            };
             // row streams, thread = row:  a = dU rows | mask source,  b = dU per receiver | residual
             const float* pa = !SA     ? nullptr
                               : lnb   ? (p.du_rows ? p.du_rows + rowoff : nullptr)
@@ -605,7 +632,15 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             // for the output pass, so the dU streams are read from global memory only once
                             float du[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) du[j] = valid && !dummy ? (pa ? ca[j] : 0.0f) + (pb ? cb[j] : 0.0f) : 0.0f;
+                            if (T1) {
+                                float t1v[16];
+                                t1_load16(cc, t1v);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) du[j] = valid && !dummy ? t1v[j] + (pb ? cb[j] : 0.0f) : 0.0f;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) du[j] = valid && !dummy ? (pa ? ca[j] : 0.0f) + (pb ? cb[j] : 0.0f) : 0.0f;
+                            }
                             tmem_st_32x32b_x16(tAhi + cc, reinterpret_cast<const uint32_t*>(du));
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
@@ -753,6 +788,12 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive_local(&bars->in_empty[rbuf]);
                             }
+                        } else if (T1 && !lnb) {
+                            float t1v[16];
+                            t1_load16(cc, t1v);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) t1v[j] += v[j];
+                            if (vout) st16(outp + cc, t1v);
                         } else if (!lnb && pb) {
                             // residual: the sum goes out from the stream's own registers, v stays free for the per-receiver sum
 #pragma unroll
@@ -877,7 +918,6 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     CUtensorMap m0, m1;
     int rc;
     if ((rc = make_row_map32(&m0, op.in0, op.rows))) return rc;
-    if ((rc = make_row_map32(&m1, op.in1 ? op.in1 : op.in0, op.rows))) return rc;
     // the shared memory the weights leave goes to the input ring
     const size_t ring_off = ring_offset(n_blocks, NSI, op.ln_bwd != 0);
     // the residual is the chain's own (first) input and the ring can hold both groups' tiles: no re-read
@@ -890,8 +930,14 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     const size_t smem = ring_off + (size_t)p.n_ring * CW_BYTES;
     // the instantiation for this chain's shape
     const bool any_hidden = op.n_layers == 3 && (op.hid_mask[0] || op.hid_mask[1]);
-    const bool fin_a = op.ln_bwd ? op.du_rows != nullptr : op.mask_src != nullptr;
-    const bool fin_b = op.ln_bwd ? op.du_recv != nullptr : op.residual != nullptr;
+    // one-layer chains: the dU rows / the residual ride the TMA ring (CGNN_NO_T1=1: thread = row global loads, as measured before)
+    static const bool t1_allowed = getenv("CGNN_NO_T1") == nullptr;
+    const float* t1_src = !t1_allowed || op.n_layers != 1 || op.in1 || gather ? nullptr
+                          : op.ln_bwd ? op.du_rows
+                          : (op.residual != op.in0 && !op.mask_src ? op.residual : nullptr);
+    const bool t1 = t1_src != nullptr;
+    const bool fin_a = op.ln_bwd ? (op.du_rows != nullptr && !t1) : op.mask_src != nullptr;
+    const bool fin_b = op.ln_bwd ? op.du_recv != nullptr : (op.residual != nullptr && !t1);
     const bool any_agg = op.agg_out || op.hid_agg[0] || op.hid_agg[1];
     // the fused forward chains (3 layers + LayerNorm) are bound by the serial epilogue of a tile, not by memory: their columns
     // are split over 16 epilogue warps.  The one-layer chains run at the memory rate either way and keep 8 warps.
@@ -901,7 +947,9 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     const bool split = split_allowed && p.ln_n == TC_H && op.n_layers == 3 && op.gamma != nullptr && !op.ln_bwd && !any_hidden && !fin_a &&
                        !op.hid_out[0] && !op.hid_out[1] && !op.hid_agg[0] && !op.hid_agg[1] && !op.bits_out && !op.mask_bits;
     const int cfg = (op.n_layers == 3 ? C_L3 : 0) | (op.ln_bwd ? C_LNB : (op.gamma ? C_LN : 0)) | (fin_a ? C_SA : 0) | (fin_b ? C_SB : 0) |
-                    (any_hidden ? C_HS : 0) | (any_agg ? C_AGG : 0) | (rin ? C_RIN : 0) | (gather ? C_GIN : 0) | (split ? C_SPLIT : 0);
+                    (any_hidden ? C_HS : 0) | (any_agg ? C_AGG : 0) | (rin ? C_RIN : 0) | (gather ? C_GIN : 0) | (split ? C_SPLIT : 0) |
+                    (t1 ? C_T1 : 0);
+    if ((rc = make_row_map32(&m1, t1 ? t1_src : (op.in1 ? op.in1 : op.in0), op.rows))) return rc;
     void (*kern)(CUtensorMap, CUtensorMap, TcParams) = nullptr;
     int slot = -1;
 #define CGNN_CHAIN_CFG(i, c) else if (cfg == (c)) { kern = tc_chain_fwd<NS, (c)>; slot = (i); }
@@ -937,12 +985,15 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     CGNN_CHAIN_CFG(18, C_LNB | C_SA | C_SB)                           // 1 layer + LayerNorm backward (dU per row and per receiver)
     CGNN_CHAIN_CFG(19, C_LNB | C_SA)
     CGNN_CHAIN_CFG(20, C_LNB | C_SB)
+    CGNN_CHAIN_CFG(24, C_T1)                                          // 1 layer + residual through the ring
+    CGNN_CHAIN_CFG(32, C_LNB | C_T1)                                  // 1 layer + LayerNorm backward, dU rows through the ring
+    CGNN_CHAIN_CFG(33, C_LNB | C_SB | C_T1)                           //   ... plus dU per receiver
 #undef CGNN_CHAIN_CFG
     if (kern == nullptr) {
         set_error("tensor-core chain: no kernel instantiated for configuration 0x%x", cfg);
         return CGNN_ERR_UNSUPPORTED;
     }
-    static size_t configured[33] = {0};
+    static size_t configured[34] = {0};
     if (smem > configured[slot]) {
         CGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[slot] = smem;
