@@ -223,7 +223,10 @@ __device__ __forceinline__ void receiver_store16(float* dst, int c, const float*
 // C_T1: one epilogue row stream of a one-layer chain (the dU rows of the LayerNorm backward, or the residual) comes through the
 // TMA ring as a second stream of the tile (tensor map 1) instead of thread = row global loads: 16 KB per instruction, requested by
 // the producer tiles ahead, where the scattered 32-byte sectors of the thread = row loads were the slowest part of those chains.
-constexpr int C_L3 = 1, C_LN = 2, C_LNB = 4, C_SA = 8, C_SB = 16, C_HS = 32, C_AGG = 64, C_RIN = 128, C_GIN = 256, C_SPLIT = 512, C_T1 = 1024;
+// C_G4 (with C_GIN): the gathered P_s rows come through the ring too -- the producer WARP issues tile::gather4 loads (lane l the
+// rows 4l..4l+3 of the tile, 32 columns per slot, tensor map 1) ahead of the tile's input chunks.
+constexpr int C_L3 = 1, C_LN = 2, C_LNB = 4, C_SA = 8, C_SB = 16, C_HS = 32, C_AGG = 64, C_RIN = 128, C_GIN = 256, C_SPLIT = 512, C_T1 = 1024,
+              C_G4 = 2048;
 template <int NS, int CFG>
 __global__ void __launch_bounds__((CFG & C_SPLIT) ? TC_THREADS_SPLIT : TC_THREADS, 1)
 tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1, const TcParams p) {
@@ -231,6 +234,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     constexpr bool L3 = (CFG & C_L3) != 0, SA = (CFG & C_SA) != 0, SB = (CFG & C_SB) != 0, HS = (CFG & C_HS) != 0, AGG = (CFG & C_AGG) != 0;
     constexpr bool RIN = (CFG & C_RIN) != 0, GIN = (CFG & C_GIN) != 0, SPLIT = (CFG & C_SPLIT) != 0, T1 = (CFG & C_T1) != 0;
     static_assert(!T1 || (!(CFG & C_L3) && !RIN && !SPLIT), "the ring-fed epilogue stream belongs to the one-layer chains");
+    constexpr bool G4 = (CFG & C_G4) != 0;
+    static_assert(!G4 || (GIN && !T1 && !RIN && !SPLIT), "gather4 feeds the accumulator initialisation; map 1 and the ring must be free for it");
     constexpr int NEPI = SPLIT ? 16 : 8;                    // epilogue warps
     constexpr int GW = NEPI / 2;                            // warps per epilogue group (= per tile in flight)
     constexpr int NTHR = (NEPI + 4) * 32;
@@ -314,18 +319,38 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SPLIT ? CTL_REGS_SPLIT : CTL_REGS));
     if (warp == NEPI) {
         // ============================ producer: weights, input chunks ============================================
-        if (lane == 0) {
+        if (G4 || lane == 0) {                         // (G4: the whole warp walks the ring, lane 0 alone issues the tiled loads)
             uint32_t buf = 0, use = 0;                 // ring slot of the next chunk and how often it has been used
             for (int64_t it = 0; it < n_it; ++it) {
                 const int64_t row0 = ((cluster_id + it * n_clusters) * 2 + rank) * 128;
-                for (int ip = 0; ip < p.n_in + (T1 ? 1 : 0); ++ip)      // T1: the epilogue stream follows the MMA input(s), map 1
+                if (G4) {
+                    // the tile's gathered rows first (the accumulator is initialised before the input is converted)
+                    int sidx[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int64_t row = row0 + 4 * lane + j;
+                        sidx[j] = __ldg(p.senders + (row < p.n_rows ? row : p.n_rows - 1));
+                    }
                     for (int q = 0; q < NCW; ++q) {
                         mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 100 + buf);
                         uint64_t* full = &bars->in_full[it & 1][buf];
-                        mbar_expect_tx(full, CW_BYTES);
-                        tma_load_2d(sRing + buf * CW_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CW, (int)row0, full);
+                        if (lane == 0) mbar_expect_tx(full, CW_BYTES);
+                        __syncwarp();
+                        tma_gather4_2d(sRing + buf * CW_BYTES + lane * 512, &tm_in1, q * CW, sidx[0], sidx[1], sidx[2], sidx[3], full);
                         if (++buf == (uint32_t)NRING) { buf = 0; ++use; }
                     }
+                }
+                for (int ip = 0; ip < p.n_in + (T1 ? 1 : 0); ++ip)      // T1: the epilogue stream follows the MMA input(s), map 1
+                    for (int q = 0; q < NCW; ++q) {
+                        if (lane == 0) {
+                            mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 100 + buf);
+                            uint64_t* full = &bars->in_full[it & 1][buf];
+                            mbar_expect_tx(full, CW_BYTES);
+                            tma_load_2d(sRing + buf * CW_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CW, (int)row0, full);
+                        }
+                        if (++buf == (uint32_t)NRING) { buf = 0; ++use; }
+                    }
+                if (G4) __syncwarp();
             }
         }
     } else if (warp == NEPI + 1) {
@@ -404,7 +429,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 
         // ring slot of this group's next tile's first chunk: advanced by the chunks of two tiles (its own and the other group's) per
         // iteration, wrapped by subtraction -- no division in the loops
-        const uint32_t uring = (uint32_t)NRING, tile_chunks = (uint32_t)(NCW * (p.n_in + (T1 ? 1 : 0)));
+        const uint32_t uring = (uint32_t)NRING, tile_chunks = (uint32_t)(NCW * (p.n_in + (T1 ? 1 : 0) + (G4 ? 1 : 0)));
         uint32_t ring0 = (uint32_t)g * tile_chunks % uring;
         // sender index of the first tile's row; the next tile's is fetched one tile ahead so its latency never shows
         int32_t snd_next = 0;
@@ -440,7 +465,30 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 #pragma unroll 1
                 for (int c = 0; c < NC; c += 64) {
                     float a0[16], a1[16], a2[16], a3[16];
-                    ld16(ps + c, a0); ld16(ps + c + 16, a1); ld16(ps + c + 32, a2); ld16(ps + c + 48, a3);
+                    if (G4) {
+                        // the gathered rows of this tile sit in the next ring slots (32 columns each), row r at its swizzled place
+#pragma unroll
+                        for (int qq = 0; qq < 2; ++qq, buf = buf + 1 == uring ? 0 : buf + 1) {
+                            mbar_wait_or_trap(&bars->in_full[g][buf], (in_par >> buf) & 1u, 130 + buf);
+                            in_par ^= 1u << buf;
+                            const uint8_t* src = sRing + buf * CW_BYTES;
+                            float* lo16 = qq == 0 ? a0 : a2;
+                            float* hi16 = qq == 0 ? a1 : a3;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 u = *reinterpret_cast<const float4*>(src + swz128(r, j));
+                                const float4 w = *reinterpret_cast<const float4*>(src + swz128(r, 4 + j));
+                                lo16[4 * j] = u.x; lo16[4 * j + 1] = u.y; lo16[4 * j + 2] = u.z; lo16[4 * j + 3] = u.w;
+                                hi16[4 * j] = w.x; hi16[4 * j + 1] = w.y; hi16[4 * j + 2] = w.z; hi16[4 * j + 3] = w.w;
+                            }
+                            consume16(reinterpret_cast<const uint32_t*>(hi16));
+                            consume16(reinterpret_cast<const uint32_t*>(lo16));
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
+                        }
+                    } else {
+                        ld16(ps + c, a0); ld16(ps + c + 16, a1); ld16(ps + c + 32, a2); ld16(ps + c + 48, a3);
+                    }
 #pragma unroll
                     for (int hh = 0; hh < 4; ++hh) {
                         float* ca = hh == 0 ? a0 : hh == 1 ? a1 : hh == 2 ? a2 : a3;
@@ -936,6 +984,9 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
                           : op.ln_bwd ? op.du_rows
                           : (op.residual != op.in0 && !op.mask_src ? op.residual : nullptr);
     const bool t1 = t1_src != nullptr;
+    // gather chains whose ring and second tensor map are free: the P_s rows come by tile::gather4 (CGNN_GATHER4=0: thread = row loads)
+    static const bool g4_allowed = getenv("CGNN_GATHER4") == nullptr || atoi(getenv("CGNN_GATHER4")) != 0;
+    const bool g4 = g4_allowed && gather && !op.in1 && !t1 && !rin && op.n_layers == 1;
     const bool fin_a = op.ln_bwd ? (op.du_rows != nullptr && !t1) : op.mask_src != nullptr;
     const bool fin_b = op.ln_bwd ? op.du_recv != nullptr : (op.residual != nullptr && !t1);
     const bool any_agg = op.agg_out || op.hid_agg[0] || op.hid_agg[1];
@@ -948,8 +999,12 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
                        !op.hid_out[0] && !op.hid_out[1] && !op.hid_agg[0] && !op.hid_agg[1] && !op.bits_out && !op.mask_bits;
     const int cfg = (op.n_layers == 3 ? C_L3 : 0) | (op.ln_bwd ? C_LNB : (op.gamma ? C_LN : 0)) | (fin_a ? C_SA : 0) | (fin_b ? C_SB : 0) |
                     (any_hidden ? C_HS : 0) | (any_agg ? C_AGG : 0) | (rin ? C_RIN : 0) | (gather ? C_GIN : 0) | (split ? C_SPLIT : 0) |
-                    (t1 ? C_T1 : 0);
-    if ((rc = make_row_map32(&m1, t1 ? t1_src : (op.in1 ? op.in1 : op.in0), op.rows))) return rc;
+                    (t1 ? C_T1 : 0) | (g4 ? C_G4 : 0);
+    if (g4) {
+        // (the node table's row count is not part of the op; the gather only ever names valid sender rows, so the map's extent is
+        //  set to the int32 index range the senders can express)
+        if ((rc = make_gather_map32(&m1, op.Ps, op.ps_rows))) return rc;
+    } else if ((rc = make_row_map32(&m1, t1 ? t1_src : (op.in1 ? op.in1 : op.in0), op.rows))) return rc;
     void (*kern)(CUtensorMap, CUtensorMap, TcParams) = nullptr;
     int slot = -1;
 #define CGNN_CHAIN_CFG(i, c) else if (cfg == (c)) { kern = tc_chain_fwd<NS, (c)>; slot = (i); }
@@ -985,6 +1040,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     CGNN_CHAIN_CFG(18, C_LNB | C_SA | C_SB)                           // 1 layer + LayerNorm backward (dU per row and per receiver)
     CGNN_CHAIN_CFG(19, C_LNB | C_SA)
     CGNN_CHAIN_CFG(20, C_LNB | C_SB)
+    CGNN_CHAIN_CFG(34, C_GIN | C_G4)                                  // 1 layer + gather through the ring (tile::gather4)
     CGNN_CHAIN_CFG(24, C_T1)                                          // 1 layer + residual through the ring
     CGNN_CHAIN_CFG(32, C_LNB | C_T1)                                  // 1 layer + LayerNorm backward, dU rows through the ring
     CGNN_CHAIN_CFG(33, C_LNB | C_SB | C_T1)                           //   ... plus dU per receiver
@@ -993,7 +1049,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
         set_error("tensor-core chain: no kernel instantiated for configuration 0x%x", cfg);
         return CGNN_ERR_UNSUPPORTED;
     }
-    static size_t configured[34] = {0};
+    static size_t configured[35] = {0};
     if (smem > configured[slot]) {
         CGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[slot] = smem;
@@ -1025,10 +1081,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz);
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows = 128);
 int make_row_map(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, CH, CU_TENSOR_MAP_SWIZZLE_64B); }
 
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz) {
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows) {
     static EncodeTiledFn fn = nullptr;
     if (fn == nullptr) {
         void* f = nullptr;
@@ -1039,7 +1095,7 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_col
     }
     cuuint64_t dims[2] = {(cuuint64_t)TC_H, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)TC_H * 4};
-    cuuint32_t box[2] = {(cuuint32_t)box_cols, 128};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1052,6 +1108,7 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_col
 }
 
 int make_row_map32(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B); }
+int make_gather_map32(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B, 1); }
 
 void set_debug_stamps(unsigned long long* buf, int tiles, int launches) {
     g_stamps = buf; g_stamp_tiles = tiles; g_stamp_launches = launches; g_stamp_next = 0;

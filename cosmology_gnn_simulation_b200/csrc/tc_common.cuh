@@ -46,6 +46,8 @@ __device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 
 int make_row_map(CUtensorMap* m, const float* base, int64_t rows);
 // boxes of 128 rows x 32 columns, 128-byte swizzle (the chain kernel's input ring)
 int make_row_map32(CUtensorMap* m, const float* base, int64_t rows);
+// boxes of 1 row x 32 columns, 128-byte swizzle: the map of tile::gather4 loads (four arbitrary rows per instruction)
+int make_gather_map32(CUtensorMap* m, const float* base, int64_t rows);
 
 // ---- building blocks used by the backward orchestration (defined in mp_tc.cu / wgrad_tc.cu) -----------
 // B[n][k] = W[(row0 + n) * ld + col0 + k] (transpose: W[(row0 + k) * ld + col0 + n]); zero where n >= nmax or k >= kmax (0 = 128)
@@ -65,6 +67,7 @@ struct ChainOp {
     int k;                        // > 0: rows per receiver (gather and/or segmented sum)
     int k_valid;                  // 0 or the real in-degree below a padded k (rows of rank >= k_valid are dummies)
     const int32_t* senders; const float* Ps; const float* Pr;   // gather: layer-1 pre-activation += Ps[sender] + Pr[row / k]
+    int64_t ps_rows;              // rows of Ps (the node table the senders index)
     const float* mask_src;        // result = mask_src > 0 ? result : 0   (nullable)
     const float* residual;        // result += residual                   (nullable)
     float* agg_out;               // [rows / k][128] = per-receiver sum of the result before the residual (nullable)

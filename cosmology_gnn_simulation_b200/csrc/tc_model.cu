@@ -176,7 +176,7 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
         op.blk[2] = {m.W[2], TC_H, 0, 0, 0};
         op.bias[0] = nullptr;                         // b1 is folded into P_r
         op.bias[1] = m.b[1]; op.bias[2] = m.b[2]; op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim;
-        op.k = a.k; op.k_valid = a.k_valid; op.senders = a.senders; op.Ps = Ps; op.Pr = Pr;
+        op.k = a.k; op.k_valid = a.k_valid; op.senders = a.senders; op.Ps = Ps; op.Pr = Pr; op.ps_rows = nn;
         op.residual = a.e_in; op.agg_out = a.agg_out; op.out = a.out;
         return run_chain(op, s);
     }
@@ -446,7 +446,7 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             // de = de_next + G1 W1e is the dgrad chain's last layer, the per-receiver sum of G1 is d P_r
             ChainOp r{};
             r.in0 = e_in; r.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 0};
-            r.k = a.k; r.k_valid = a.k_valid; r.senders = a.senders + r0; r.Ps = Ps; r.Pr = Pr + (r0 / k) * TC_H;
+            r.k = a.k; r.k_valid = a.k_valid; r.senders = a.senders + r0; r.Ps = Ps; r.ps_rows = nn; r.Pr = Pr + (r0 / k) * TC_H;
             if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, de_next, a.dagg + (r0 / k) * TC_H, a.k, a.k_valid,
                                      {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}, de_next, a.de + r0 * TC_H, G1, dPr + (r0 / k) * TC_H, acc, s))) return rc;
             // dW1e = G1^T e, db1

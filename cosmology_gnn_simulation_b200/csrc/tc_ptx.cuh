@@ -216,6 +216,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, in
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1) : "memory");
 }
+// four rows (row indices r0..r3, any order) x the map's box width starting at column crd0 -> four consecutive rows at dst
+// (the tensor map's box is {width, 1}); completes 4 * width * elemsize bytes on `bar`
+__device__ __forceinline__ void tma_gather4_2d(void* dst_smem, const void* tmap, int crd0, int r0, int r1, int r2, int r3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(smem_u32(bar)), "r"(crd0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src_smem, int crd0, int crd1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(tmap), "r"(smem_u32(src_smem)), "r"(crd0), "r"(crd1) : "memory");
