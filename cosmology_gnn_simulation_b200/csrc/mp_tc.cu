@@ -984,8 +984,9 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
                           : op.ln_bwd ? op.du_rows
                           : (op.residual != op.in0 && !op.mask_src ? op.residual : nullptr);
     const bool t1 = t1_src != nullptr;
-    // gather chains whose ring and second tensor map are free: the P_s rows come by tile::gather4 (CGNN_GATHER4=0: thread = row loads)
-    static const bool g4_allowed = getenv("CGNN_GATHER4") == nullptr || atoi(getenv("CGNN_GATHER4")) != 0;
+    // gather chains whose ring and second tensor map are free can take the P_s rows by tile::gather4 (CGNN_GATHER4=1).  Measured
+    // slower than the thread = row loads (128 four-row gathers per tile: 25.2 k vs 20.4 k cycles per tile of the A1 chain), so opt-in.
+    static const bool g4_allowed = getenv("CGNN_GATHER4") != nullptr && atoi(getenv("CGNN_GATHER4")) != 0;
     const bool g4 = g4_allowed && gather && !op.in1 && !t1 && !rin && op.n_layers == 1;
     const bool fin_a = op.ln_bwd ? (op.du_rows != nullptr && !t1) : op.mask_src != nullptr;
     const bool fin_b = op.ln_bwd ? op.du_recv != nullptr : (op.residual != nullptr && !t1);
