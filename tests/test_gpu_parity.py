@@ -418,3 +418,35 @@ def test_config1_one_step_inference_parity():
                             ref_g["edge_attr"].double(), 2, 5, message="sender")
     assert rel_l2(pred["acceleration"].cpu(), ref["acceleration"]) < TOL_FP32
     assert rel_l2(pred["temp_rate"].cpu(), ref["temp_rate"]) < TOL_FP32
+
+
+@pytest.mark.parametrize("message,precision", [("edge", "fp32"), ("edge", "bf16x3"), ("sender", "fp32")])
+def test_space_filling_curve_renumbering_is_invisible(message, precision, monkeypatch):
+    """Large graphs are renumbered along a Z-order curve inside the model (gathers hit L2).  Rows are computed independently,
+    so the outputs must be bit-identical with and without it; gradients are sums over edges in another order."""
+    from cosmology_gnn_simulation_b200 import synthetic
+    from cosmology_gnn_simulation_b200.data_utils import preprocess
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    from oracle import model_ref
+    n, k, L, M = 3000, 12, 128, 3
+    box = synthetic.make_box(n, "clustered", seed=6)
+    md = box["metadata"]
+    g = preprocess(box["Coordinates"][:5], box["InternalEnergy"][:5], md, box["Coordinates"][5:6], box["InternalEnergy"][5:6],
+                   num_neighbors=k, dt=md["dt"], box_size=md["box_size"], device=_dev())
+    params = model_ref.init_params(L, L, 2, M, 3, seed=4)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CGNN_REORDER", flag)
+        model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision)
+        model.load_state_dict(params)
+        model = model.to(_dev())
+        pred = model(g)
+        ls = combined_loss(pred, g, md["dt"], 1.0, 1.0, 0.1)
+        ls["loss"].backward()
+        res[flag] = (pred["acceleration"].detach().clone(), pred["temp_rate"].detach().clone(),
+                     {k_: p.grad.clone() for k_, p in model.named_parameters() if p.grad is not None})
+        assert (model._graph_cache.get("order") is not None) == (flag == "1")
+    assert torch.equal(res["0"][0], res["1"][0]) and torch.equal(res["0"][1], res["1"][1])
+    for name, gr in res["0"][2].items():
+        assert rel_l2(res["1"][2][name].cpu(), gr.cpu()) < (1e-5 if precision == "fp32" else 1e-3), name
