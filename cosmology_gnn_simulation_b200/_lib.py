@@ -142,9 +142,15 @@ class Workspace:
             if buf is not None and torch.cuda.is_current_stream_capturing():
                 raise RuntimeError(f"cgnn: workspace '{tag}' would have to grow inside a CUDA-graph capture "
                                    "(warm the step up at its final size before capturing)")
+            self._bufs.pop(key, None)
+            buf = None                       # the old buffer goes before the new one comes (they can be tens of GiB)
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self._bufs[key] = buf
         return buf
+
+    def tagged_bytes(self, device, prefix: str) -> int:
+        """Bytes currently held under tags that start with `prefix` (the planner counts them as available)."""
+        return sum(b.numel() for (dev, tag), b in self._bufs.items() if dev == str(device) and tag.startswith(prefix) and b is not None)
 
     @contextlib.contextmanager
     def scope(self):

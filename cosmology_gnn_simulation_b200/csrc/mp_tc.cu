@@ -1109,6 +1109,7 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_col
 }
 
 int make_row_map32(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B); }
+int make_row_map32_rows(CUtensorMap* m, const float* base, int64_t rows, int box_rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B, box_rows); }
 int make_gather_map32(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B, 1); }
 
 void set_debug_stamps(unsigned long long* buf, int tiles, int launches) {

@@ -46,6 +46,8 @@ __device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 
 int make_row_map(CUtensorMap* m, const float* base, int64_t rows);
 // boxes of 128 rows x 32 columns, 128-byte swizzle (the chain kernel's input ring)
 int make_row_map32(CUtensorMap* m, const float* base, int64_t rows);
+// boxes of box_rows rows x 32 columns, 128-byte swizzle
+int make_row_map32_rows(CUtensorMap* m, const float* base, int64_t rows, int box_rows);
 // boxes of 1 row x 32 columns, 128-byte swizzle: the map of tile::gather4 loads (four arbitrary rows per instruction)
 int make_gather_map32(CUtensorMap* m, const float* base, int64_t rows);
 

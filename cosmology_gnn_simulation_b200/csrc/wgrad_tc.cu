@@ -18,34 +18,40 @@ namespace {
 
 using namespace ptx;
 
-constexpr int WG_THREADS = 320;           // 8 converter warps (two per row quarter, alternating chunks) + producer warp + MMA warp
+constexpr int WG_THREADS = 320;           // 8 converter warps (four sets of two: set s takes the chunks with seq % 4 == s) + producer warp + MMA warp
 constexpr int WG_PROD = 8, WG_MMA = 9;
-constexpr int WG_RING = 4;                // input ring: 128 rows x 32 columns (128-byte rows, SWIZZLE_128B) per chunk.  EVEN, so that
-                                          // a ring slot is always consumed by the same converter set (chunk parity) and the phase
-                                          // parity a set waits on can never alias a phase that belongs to the other set
-constexpr int CW = 32, NCW = TC_H / CW, CW_BYTES = 128 * CW * 4;
-constexpr int OP_BYTES = 128 * 128 * 2;   // one BF16 operand image (128 mn x 128 k)
-constexpr int ONES_BYTES = 16 * 128 * 2;
+constexpr int TR = 64;                    // rows per tile (the K extent of one accumulation step).  Round 1 used 128-row tiles with a 4-slot
+                                          // ring: the operand images took 128 KB, the ring held half a tile, and ncu showed the converter
+                                          // warps waiting for TMA data in 46 % of their samples.  64-row tiles halve the images, the freed
+                                          // shared memory goes to the ring: two tiles of input in flight per SM.
+constexpr int WG_SETS = 4;
+constexpr int WG_RING = 16;               // input ring: TR rows x 32 columns (128-byte rows, SWIZZLE_128B) per chunk.  A multiple of WG_SETS,
+                                          // so that a ring slot is always consumed by the same converter set and the phase parity a set
+                                          // waits on can never alias a phase that belongs to another set
+constexpr int CW = 32, NCW = TC_H / CW, CW_BYTES = TR * CW * 4;
+constexpr int OP_BYTES = 128 * TR * 2;    // one BF16 operand image (128 mn x TR k)
+constexpr int MN_STRIDE = (TR / 8) * 128; // bytes between groups of 8 mn in an MN-major image
+constexpr int ONES_BYTES = 16 * TR * 2;
 constexpr int PW = 132;                   // floats per partial row: 128 dW columns + db + pad
 constexpr float LN_EPS = 1e-5f;
 
-static_assert(WG_RING % 2 == 0, "ring slots must keep the chunk parity");
+static_assert(WG_RING % WG_SETS == 0 && (2 * NCW) % WG_SETS == 0, "ring slots and a tile's chunks must keep the set of a chunk");
 struct WgSmem {
     static constexpr int ring = 0;
     static constexpr int bars = ring + WG_RING * CW_BYTES;
-    static constexpr int ones = bars + 256;
+    static constexpr int ones = bars + 512;
     static constexpr int ops = ones + ONES_BYTES;          // X images (NSI), then A images (NSI)
 };
 static_assert(WgSmem::ops % 128 == 0, "operand images need 128-byte alignment");
 
 struct WgBars {
     uint64_t in_full[WG_RING], in_empty[WG_RING];
-    uint64_t ops_full;       // 4 converter warps
+    uint64_t ops_full;       // 8 converter warps
     uint64_t ops_empty;      // tcgen05.commit
     uint32_t tmem_base;
 };
 
-// MN-major image: element (mn, k) at (mn/8)*2048 + (k/8)*128 + (k%8)*16 + (mn%8)*2
+// MN-major image: element (mn, k) at (mn/8)*MN_STRIDE + (k/8)*128 + (k%8)*16 + (mn%8)*2
 template <int NS>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_a,
@@ -60,14 +66,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int64_t n_it = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid == 0) {
-        for (int i = 0; i < WG_RING; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 4); }
+        for (int i = 0; i < WG_RING; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 2); }
         mbar_init(&bars->ops_full, 8);
         mbar_init(&bars->ops_empty, 1);
         fence_mbar_init();
     }
     for (int i = tid; i < ONES_BYTES / 4; i += WG_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0u;
     __syncthreads();
-    for (int k = tid; k < 128; k += WG_THREADS)
+    for (int k = tid; k < TR; k += WG_THREADS)
         *reinterpret_cast<uint16_t*>(sOnes + (k >> 3) * 128 + (k & 7) * 16) = 0x3F80;     // bf16(1.0) at mn = 0
     if (warp == WG_MMA) tmem_alloc<1>(&bars->tmem_base, 256);
     if (warp == WG_PROD && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_a); }
@@ -82,7 +88,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         if (lane == 0) {
             uint32_t seq = 0;
             for (int64_t it = 0; it < n_it; ++it) {
-                const int64_t row0 = (blockIdx.x + it * gridDim.x) * 128;
+                const int64_t row0 = (blockIdx.x + it * gridDim.x) * TR;
                 for (int op = 0; op < 2; ++op)
                     for (int q = 0; q < NCW; ++q, ++seq) {
                         const uint32_t buf = seq % WG_RING, use = seq / WG_RING;
@@ -105,33 +111,33 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 tc_fence_after_sync();
                 const uint32_t first = it == 0 ? 0u : 1u;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
+                for (int ks = 0; ks < TR / 16; ++ks) {
                     const uint32_t acc = (ks > 0) ? 1u : first;
-                    const uint64_t dxh = umma_desc(x_hi + ks * 256, 128, 2048);
-                    umma_bf16<1>(tmem, dxh, umma_desc(a_hi + ks * 256, 128, 2048), idesc, acc);
-                    umma_bf16<1>(tmem + 128, dxh, umma_desc(ones + ks * 256, 128, 2048), idesc1, acc);
+                    const uint64_t dxh = umma_desc(x_hi + ks * 256, 128, MN_STRIDE);
+                    umma_bf16<1>(tmem, dxh, umma_desc(a_hi + ks * 256, 128, MN_STRIDE), idesc, acc);
+                    umma_bf16<1>(tmem + 128, dxh, umma_desc(ones + ks * 256, 128, MN_STRIDE), idesc1, acc);
                     if (NS == 3) {
-                        const uint64_t dxl = umma_desc(x_lo + ks * 256, 128, 2048);
-                        umma_bf16<1>(tmem, dxl, umma_desc(a_hi + ks * 256, 128, 2048), idesc, 1u);
-                        umma_bf16<1>(tmem, dxh, umma_desc(a_lo + ks * 256, 128, 2048), idesc, 1u);
-                        umma_bf16<1>(tmem + 128, dxl, umma_desc(ones + ks * 256, 128, 2048), idesc1, 1u);
+                        const uint64_t dxl = umma_desc(x_lo + ks * 256, 128, MN_STRIDE);
+                        umma_bf16<1>(tmem, dxl, umma_desc(a_hi + ks * 256, 128, MN_STRIDE), idesc, 1u);
+                        umma_bf16<1>(tmem, dxh, umma_desc(a_lo + ks * 256, 128, MN_STRIDE), idesc, 1u);
+                        umma_bf16<1>(tmem + 128, dxl, umma_desc(ones + ks * 256, 128, MN_STRIDE), idesc1, 1u);
                     }
                 }
                 umma_commit<1>(&bars->ops_empty);
             }
         }
     } else {
-        // ---- converters: thread = row of the tile; warps 0-3 take the even chunks, warps 4-7 the odd ones, so every
+        // ---- converters: thread = row of the tile; set s (two warps) takes the chunks with seq % 4 == s, so every
         //      scheduler has two converter warps to interleave ---------------------------------------------------
-        const int r = tid & 127;
-        const int cpar = tid >> 7;
+        const int r = tid & (TR - 1);
+        const int cset = tid >> 6;
         uint32_t seq = 0;
         for (int64_t it = 0; it < n_it; ++it) {
             if (it > 0) mbar_wait_or_trap(&bars->ops_empty, (uint32_t)((it - 1) & 1), 220);      // previous tile's MMAs read the images
             for (int op = 0; op < 2; ++op) {
                 uint8_t* img = op == 0 ? sX : sA;
                 for (int q = 0; q < NCW; ++q, ++seq) {
-                    if ((q & 1) != cpar) continue;
+                    if ((int)(seq & (WG_SETS - 1)) != cset) continue;
                     const uint32_t buf = seq % WG_RING, use = seq / WG_RING;
                     mbar_wait_or_trap(&bars->in_full[buf], use & 1, 230 + buf);
                     const uint8_t* src = smem + WgSmem::ring + buf * CW_BYTES;
@@ -146,11 +152,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
                     // columns 32q .. 32q+31 = mn groups 4q .. 4q+3; k = r
-                    uint8_t* dst = img + (4 * q) * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+                    uint8_t* dst = img + (4 * q) * MN_STRIDE + (r >> 3) * 128 + (r & 7) * 16;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        *reinterpret_cast<uint4*>(dst + j * 2048) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        if (NS == 3) *reinterpret_cast<uint4*>(dst + OP_BYTES + j * 2048) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(dst + j * MN_STRIDE) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        if (NS == 3) *reinterpret_cast<uint4*>(dst + OP_BYTES + j * MN_STRIDE) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
                 }
             }
@@ -163,10 +169,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             mbar_wait_or_trap(&bars->ops_empty, (uint32_t)((n_it - 1) & 1), 240);
             tc_fence_after_sync();
         }
-        float* dst = partials + ((size_t)blockIdx.x * 128 + r) * PW;
+        // accumulator row = TMEM lane: warp w reads lane quarter w & 3; the two warps of a quarter alternate 16-column blocks
+        const int orow = tid & 127, ocpar = tid >> 7;
+        float* dst = partials + ((size_t)blockIdx.x * 128 + orow) * PW;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
-        for (int c0 = cpar * 16; c0 < 144; c0 += 32) {
+        for (int c0 = ocpar * 16; c0 < 144; c0 += 32) {
             float v[16];
             if (n_it > 0) {
                 tmem_ld_32x32b_x16(trow + c0, v);
@@ -284,13 +292,13 @@ int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, i
               int accumulate, void* ws, cudaStream_t stream, int nrows, int ncols) {
     CGNN_CHECK_ARG(X && A && dW && ws && rows >= 1, "tensor-core wgrad: bad arguments");
     const int nsi = ns == 3 ? 2 : 1;
-    const int64_t n_tiles = (rows + 127) / 128;
+    const int64_t n_tiles = (rows + TR - 1) / TR;
     int grid = num_sms() < 148 ? num_sms() : 148;
     if (n_tiles < grid) grid = (int)n_tiles;
     CUtensorMap mx, ma;
     int rc;
-    if ((rc = make_row_map32(&mx, X, rows))) return rc;
-    if ((rc = make_row_map32(&ma, A, rows))) return rc;
+    if ((rc = make_row_map32_rows(&mx, X, rows, TR))) return rc;
+    if ((rc = make_row_map32_rows(&ma, A, rows, TR))) return rc;
     const size_t smem = (size_t)WgSmem::ops + (size_t)2 * nsi * OP_BYTES;
     float* partials = static_cast<float*>(ws);
     if (ns == 3) {

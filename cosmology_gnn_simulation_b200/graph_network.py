@@ -131,6 +131,38 @@ class _Plan:
 _STREAM_PLANS = {}
 
 
+class _StreamLease:
+    """The edge-stream buffers of one training application: nbuf copies of e^t plus the gradient stream, E x L x 4 bytes each.
+
+    They are slices of the grow-only shared scratch (`_lib.workspace`, tags "edge_stream_i"; a CUDA-graph capture has its own):
+    32 GiB blocks that come and go through the caching allocator every step fragment it until a block no longer fits although
+    the memory is there (seen at 2.1 M particles: 134 GiB allocated, 32 GiB reserved in pieces, 32 GiB request fails).  One
+    application holds the lease from its forward to the end of its backward; a second one started in between (no reference
+    loop does that) falls back to private tensors."""
+    _busy = set()
+
+    def __init__(self, device, n_buffers: int, e_count: int, latent: int):
+        from ._lib import workspace
+        self.key = (str(device), id(workspace._bufs))
+        self.shared = self.key not in _StreamLease._busy
+        nbytes = e_count * latent * 4
+        if self.shared:
+            _StreamLease._busy.add(self.key)
+            self.bufs = [workspace.get(device, f"edge_stream_{i}", nbytes)[:nbytes].view(torch.float32).view(e_count, latent)
+                         for i in range(n_buffers)]
+        else:
+            self.bufs = [torch.empty((e_count, latent), dtype=torch.float32, device=device) for _ in range(n_buffers)]
+
+    def release(self):
+        if self.shared:
+            _StreamLease._busy.discard(self.key)
+            self.shared = False
+        self.bufs = None
+
+    def __del__(self):
+        self.release()
+
+
 def _edge_stream_buffers(plan: _Plan, n: int, n_loc: int, e_count: int, L: int, device) -> int:
     """How many copies of the edge latent stream (E x L x 4 bytes each) message="edge" training may keep next to the
     gradient stream; ckpt_plan.schedule() turns that into the checkpoint / recompute schedule of the backward.
@@ -150,6 +182,8 @@ def _edge_stream_buffers(plan: _Plan, n: int, n_loc: int, e_count: int, L: int, 
         torch.cuda.empty_cache()          # large streams: hand cached fragments back before measuring
     free, total = torch.cuda.mem_get_info(device)
     free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    from ._lib import workspace
+    free += workspace.tagged_bytes(device, "edge_stream_")      # stream buffers of an earlier plan are reused, not added
     # still to come besides the stream copies: h^t (M+1) and agg^t (M) for every step, six node-sized temporaries of the
     # backward, the sender-sorted transpose, 1 GiB of small tensors -- and 3 % of the device is left untouched
     other = (2 * M + 7) * n_loc * L * 4 + 6 * e_count + (1 << 30) + (total * 3) // 100
@@ -201,7 +235,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
                 aggs.append(agg)
             return h_next
 
-        bufs, acts, pos = None, None, 0
+        bufs, acts, pos, lease = None, None, 0, None
         if not edge_mode:
             # What the reference computes (PyG's default message): the receivers sum SENDER latents.  The edge
             # latents never reach h, the decoders or any gradient, so the edge stream is not computed at all.
@@ -210,16 +244,19 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
                 ops.aggregate_senders(h, senders, k, agg)
                 h = node_phase(t, h, agg)
         elif not train:
-            e = ops.mlp_rows_fwd(p.enc_edge, edge_attr, prec)
+            lease = _StreamLease(dev, 1, e_count, L)
+            e = ops.mlp_rows_fwd(p.enc_edge, edge_attr, prec, out=lease.bufs[0])
             for t in range(M):
                 agg = torch.empty((n, L), dtype=torch.float32, device=dev)
                 ops.mp_edge_fwd(p.proc_edge[t], h, e, senders, k, e if t + 1 < M else None, agg, prec, p.k_valid)   # e^M is never read
                 h = node_phase(t, h, agg)
             del e
+            lease.release()
         else:
             nbuf = _edge_stream_buffers(p, n, n_loc, e_count, L, dev)
             acts = ckpt_plan.schedule(M, nbuf)
-            bufs = [None] * nbuf
+            lease = _StreamLease(dev, nbuf + 1, e_count, L)           # nbuf copies of e^t + the gradient stream
+            bufs = lease.bufs[:nbuf]
             last = None
             for pos, act in enumerate(acts):
                 if act[0] == "bwd":
@@ -238,6 +275,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
             ctx.plan, ctx.senders, ctx.transpose_fn = plan, senders, transpose_fn
             ctx.x, ctx.edge_attr = x, edge_attr
             ctx.hs, ctx.aggs, ctx.bufs, ctx.acts, ctx.pos = hs, aggs, bufs, acts, pos
+            ctx.lease = lease
             ctx.n_params = len(params)
         return acc, temp
 
@@ -247,13 +285,9 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         prec, k = p.precision, p.k
         if act[0] == "enc":
             b = act[1]
-            if bufs[b] is None:
-                bufs[b] = torch.empty((e_count, L), dtype=torch.float32, device=edge_attr.device)
             ops.mlp_rows_fwd(p.enc_edge, edge_attr, prec, out=bufs[b])
             return
         _, t, src, dst = act
-        if bufs[dst] is None:
-            bufs[dst] = torch.empty((e_count, L), dtype=torch.float32, device=edge_attr.device)
         if first:                                           # the real forward of step t
             h = hs[t]
             agg = torch.empty((h.shape[0] if p.halo is None else p.halo.n_own, L), dtype=torch.float32, device=h.device)
@@ -310,7 +344,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
             if edge_mode:
                 # the gradient stream is updated in place (de^t over de^{t+1}); only the FP32 kernels need the per-edge
                 # scratch gs, the tensor-core path accumulates the sender sums chunk by chunk in its workspace
-                de_new = de if de is not None else torch.empty_like(e_t)
+                de_new = de if de is not None else ctx.lease.bufs[-1]
                 gs = torch.empty_like(e_t) if fp32 else None
                 put(p.proc_edge[t], ops.mp_edge_bwd(p.proc_edge[t], hs[t], e_t, senders, rowptr, perm, k, de, dagg,
                                                     de_new, dh_new, gs, prec, p.k_valid))
@@ -329,8 +363,6 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
                     aggs[t] = None
                 else:
                     _EncodeProcessDecodeFn._advance(p, act, bufs, ctx.edge_attr, senders, hs, e_count, L, first=False)
-            for i in range(len(bufs)):
-                bufs[i] = None
         else:
             for t in range(M - 1, -1, -1):
                 dh, de = step_backward(t, None, dh, None)
@@ -344,7 +376,9 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         if edge_mode:
             g_ee, dea = ops.mlp_rows_bwd(p.enc_edge, ctx.edge_attr, de, need_dea, prec)
             put(p.enc_edge, g_ee)
-        ctx.hs = ctx.aggs = ctx.bufs = None
+        if ctx.lease is not None:
+            ctx.lease.release()
+        ctx.hs = ctx.aggs = ctx.bufs = ctx.lease = None
         return (None, None, None, dx, dea, *grads)
 
 
