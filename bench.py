@@ -30,6 +30,7 @@ WORKLOADS = {
     "config1": (4096, 16, 64, 5, "uniform"),
     "config2": (32 ** 3, 16, 128, 10, "uniform"),
     "config3": (128 ** 3, 32, 128, 10, "uniform"),
+    "config4": (128 ** 3, 16, 128, 10, "uniform"),       # --rollout: per-GPU share of the 256^3 rollout box at 8 GPUs (k = 16, render_rollout.py:49)
     "config2-clustered": (32 ** 3, 16, 128, 10, "clustered"),
     "config3-clustered": (128 ** 3, 32, 128, 10, "clustered"),
     "tiny": (2048, 8, 32, 2, "uniform"),
@@ -572,38 +573,59 @@ def slab_parity(rank, world, dev, k, L, M, message, precision, n_small=8192):
 
 
 def run_rollout(args):
-    """Inference rollout (BASELINE configs[3] shape at one GPU's share): per step the k-NN graph is rebuilt, the
-    model runs forward only and the integrator advances the box, all device resident (rollout.py)."""
+    """Inference rollout (BASELINE configs[3]): per step the k-NN graph is rebuilt, the model runs forward only and the
+    integrator advances the box, all device resident (rollout.py).  N > 1: ONE box of N x the workload's particles,
+    re-partitioned into x-slabs every step (rollout_slab: particles change owner as they move), one all-gather of the new
+    frame per step."""
     from cosmology_gnn_simulation_b200 import _lib, synthetic
+    from cosmology_gnn_simulation_b200 import distributed as cd
     from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
-    from cosmology_gnn_simulation_b200.rollout import rollout
-    dev = torch.device("cuda", 0)
+    from cosmology_gnn_simulation_b200.rollout import rollout, rollout_slab
+    import torch.distributed as dist
+    rank, world, local = cd.init_from_env()
+    dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     n, k, L, M, kind = WORKLOADS[args.workload]
-    box = synthetic.make_box(n, kind, seed=0)
+    box = synthetic.make_box(n * world, kind, seed=0)
     md = box["metadata"]
     torch.manual_seed(0)
     model = EncodeProcessDecode(L, L, 2, M, 3, message=args.message, precision=args.precision).to(dev)
     data = {"Coordinates": box["Coordinates"][:6].to(dev), "InternalEnergy": box["InternalEnergy"][:6].to(dev)}
-    rollout(model, data, md, 0.0, md["dt"], md["box_size"], window_size=5, num_neighbors=k, n_steps=max(args.warmup, 3))
+
+    def run(steps):
+        if world == 1:
+            return rollout(model, data, md, 0.0, md["dt"], md["box_size"], window_size=5, num_neighbors=k, n_steps=steps)
+        return rollout_slab(model, data, md, 0.0, md["dt"], md["box_size"], window_size=5, num_neighbors=k, n_steps=steps,
+                            rank=rank, world=world)
+
+    run(max(args.warmup, 3))
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize(dev)
     l0 = _lib.launch_count()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(0) as clocks:
+    with ClockSampler(local) as clocks:
         s.record()
-        out = rollout(model, data, md, 0.0, md["dt"], md["box_size"], window_size=5, num_neighbors=k, n_steps=args.steps)
+        out = run(args.steps)
         e.record()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize(dev)
-    ms = s.elapsed_time(e)
-    line = {"metric": "particle-steps/sec of an inference rollout (k-NN rebuild + forward + integrator per step)",
-            "value": n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"rollout of {args.workload}: {n} particles, k={k}, latent={L}, {M} MP steps, "
-                                   f"graph rebuilt every step, device-resident trajectory", "message": args.message},
-            "clocks": clocks.summary(), "gpu_launches": int(_lib.launch_count() - l0),
-            "finite": bool(torch.isfinite(out["Coordinates"]).all())}
-    print(json.dumps(line), flush=True)
+    ms = cd.max_over_ranks(s.elapsed_time(e), dev)
+    if rank == 0:
+        line = {"metric": "particle-steps/sec of an inference rollout (k-NN rebuild + forward + integrator per step)",
+                "value": n * world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": f"rollout of {args.workload}: {n} particles per GPU, ONE box of {n * world}, k={k}, latent={L}, {M} MP steps, "
+                                       f"graph rebuilt every step, device-resident trajectory"
+                                       + (", re-partitioned into x-slabs every step (migration), one all-gather of the new frame per step" if world > 1 else ""),
+                           "message": args.message},
+                "clocks": clocks.summary(), "gpu_launches": int(_lib.launch_count() - l0),
+                "finite": bool(torch.isfinite(out["Coordinates"]).all())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

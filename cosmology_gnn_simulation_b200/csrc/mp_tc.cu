@@ -965,7 +965,7 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     }
     CUtensorMap m0, m1;
     int rc;
-    if ((rc = make_row_map32(&m0, op.in0, op.rows))) return rc;
+    if ((rc = make_row_map32_rows(&m0, op.in0, op.rows, 128, op.in0_cols > 0 ? op.in0_cols : TC_H))) return rc;
     // the shared memory the weights leave goes to the input ring
     const size_t ring_off = ring_offset(n_blocks, NSI, op.ln_bwd != 0);
     // the residual is the chain's own (first) input and the ring can hold both groups' tiles: no re-read
@@ -1082,10 +1082,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows = 128);
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows = 128, int cols = TC_H);
 int make_row_map(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, CH, CU_TENSOR_MAP_SWIZZLE_64B); }
 
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows) {
+// `cols`: width of the array in global memory (row pitch cols * 4 bytes, a multiple of 16).  A box may reach beyond it: the TMA
+// fills the columns outside the tensor with zeros and reads nothing for them -- how a narrow array (edge features, 4 columns)
+// enters the 128-column chains without a padded copy in HBM.
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows, int cols) {
     static EncodeTiledFn fn = nullptr;
     if (fn == nullptr) {
         void* f = nullptr;
@@ -1094,8 +1097,8 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_col
         CGNN_CHECK_ARG(f != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
         fn = reinterpret_cast<EncodeTiledFn>(f);
     }
-    cuuint64_t dims[2] = {(cuuint64_t)TC_H, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)TC_H * 4};
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
@@ -1109,7 +1112,7 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_col
 }
 
 int make_row_map32(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B); }
-int make_row_map32_rows(CUtensorMap* m, const float* base, int64_t rows, int box_rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B, box_rows); }
+int make_row_map32_rows(CUtensorMap* m, const float* base, int64_t rows, int box_rows, int cols) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B, box_rows, cols); }
 int make_gather_map32(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B, 1); }
 
 void set_debug_stamps(unsigned long long* buf, int tiles, int launches) {

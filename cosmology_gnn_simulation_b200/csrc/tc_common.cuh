@@ -47,7 +47,7 @@ int make_row_map(CUtensorMap* m, const float* base, int64_t rows);
 // boxes of 128 rows x 32 columns, 128-byte swizzle (the chain kernel's input ring)
 int make_row_map32(CUtensorMap* m, const float* base, int64_t rows);
 // boxes of box_rows rows x 32 columns, 128-byte swizzle
-int make_row_map32_rows(CUtensorMap* m, const float* base, int64_t rows, int box_rows);
+int make_row_map32_rows(CUtensorMap* m, const float* base, int64_t rows, int box_rows, int cols = TC_H);
 // boxes of 1 row x 32 columns, 128-byte swizzle: the map of tile::gather4 loads (four arbitrary rows per instruction)
 int make_gather_map32(CUtensorMap* m, const float* base, int64_t rows);
 
@@ -58,6 +58,7 @@ struct ChainOp {
     int ns;                       // 1 (bf16) or 3 (bf16x3)
     int64_t rows;
     const float* in0;             // [rows][128]
+    int in0_cols;                 // > 0: in0 is [rows][in0_cols] with in0_cols * 4 a multiple of 16 (the TMA zero-fills up to 128)
     const float* in1;             // second input phase (nullable)
     int n_layers;                 // 1 or 3
     ChainBlock blk[4];            // n_in + n_layers - 1 weight blocks
@@ -87,8 +88,9 @@ int run_chain(const ChainOp& op, cudaStream_t stream);
 // dW[n][col0 + c] (=|+=) sum_rows X[row][n] * A[row][c];  db[n] (=|+=) sum_rows X[row][n]   (deterministic)
 int64_t wgrad_workspace_bytes();
 // only the first nrows rows / ncols columns of the 128 x 128 product are written (0 = all 128)
+// a_cols > 0: A is [rows][a_cols] (a_cols * 4 a multiple of 16), zero-filled up to 128 by the TMA
 int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, int ld, int col0, float* db,
-              int accumulate, void* ws, cudaStream_t stream, int nrows = 0, int ncols = 0);
+              int accumulate, void* ws, cudaStream_t stream, int nrows = 0, int ncols = 0, int a_cols = 0);
 
 
 // dY = LayerNorm backward of (Y, dU), dU = (dU_rows ? dU_rows[row] : 0) + (dU_recv ? dU_recv[row / k] : 0); dY may alias Y

@@ -220,13 +220,16 @@ int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s)
         for (int64_t r0 = 0; r0 < a.n; r0 += chunk) {
             const int64_t rows = a.n - r0 < chunk ? a.n - r0 : chunk;
             const float* in = a.x + r0 * m.in_dim;
-            if (m.in_dim < TC_H) {
+            // narrow inputs whose row pitch the TMA accepts (a multiple of 16 bytes: the 4 edge features) are read in place,
+            // zero-filled to 128 columns on the way into shared memory; others (17 node features) take a padded copy
+            const bool narrow_tma = m.in_dim < TC_H && (m.in_dim * 4) % 16 == 0 && ((uintptr_t)in & 15) == 0;
+            if (m.in_dim < TC_H && !narrow_tma) {
                 if ((rc = pad_rows(in, m.in_dim, rows, Xp, s))) return rc;
                 in = Xp;
             }
             ChainOp op = base_op(ns, sc, rows);
             op.n_layers = 3;
-            op.in0 = in;
+            op.in0 = in; op.in0_cols = narrow_tma ? m.in_dim : 0;
             op.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim};
             op.blk[1] = {m.W[1], TC_H, 0, 0, 0};
             op.blk[2] = {m.W[2], TC_H, 0, 0, 0, m.out_dim, 0};
@@ -369,7 +372,8 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             const int64_t rows = a.n - r0 < chunk ? a.n - r0 : chunk;
             const int acc = c > 0;
             const float* in = a.x + r0 * m.in_dim;
-            if (m.in_dim < TC_H) {
+            const bool narrow_tma = m.in_dim < TC_H && (m.in_dim * 4) % 16 == 0 && ((uintptr_t)in & 15) == 0;
+            if (m.in_dim < TC_H && !narrow_tma) {
                 if ((rc = pad_rows(in, m.in_dim, rows, Xp, s))) return rc;
                 in = Xp;
             }
@@ -379,11 +383,11 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
                 else CGNN_CUDA(cudaMemcpyAsync(T, dU, (size_t)rows * TC_H * 4, cudaMemcpyDeviceToDevice, s));
             }
             ChainOp r{};
-            r.in0 = in; r.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim}; r.bias[0] = m.b[0];
+            r.in0 = in; r.in0_cols = narrow_tma ? m.in_dim : 0; r.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim}; r.bias[0] = m.b[0];
             // dx = G1 W1 (in_dim == 128) comes out of the dgrad chain's last layer
             if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, dU, nullptr, 1, 0, {m.W[0], m.in_dim, 0, 0, 1, m.in_dim, 0},
                                      nullptr, a.dx ? a.dx + r0 * TC_H : nullptr, G1, nullptr, acc, s))) return rc;
-            if ((rc = run_wgrad(ns, G1, in, rows, g->W[0], m.in_dim, 0, g->b[0], acc, sc.wg, s, 0, m.in_dim))) return rc;
+            if ((rc = run_wgrad(ns, G1, in, rows, g->W[0], m.in_dim, 0, g->b[0], acc, sc.wg, s, 0, m.in_dim, narrow_tma ? m.in_dim : 0))) return rc;
         }
         return CGNN_OK;
     }

@@ -289,7 +289,7 @@ constexpr int LNB_BLOCKS = 592;       // 4 per SM
 int64_t wgrad_workspace_bytes() { return align_up((int64_t)148 * 128 * PW * 4, 256); }
 
 int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, int ld, int col0, float* db,
-              int accumulate, void* ws, cudaStream_t stream, int nrows, int ncols) {
+              int accumulate, void* ws, cudaStream_t stream, int nrows, int ncols, int a_cols) {
     CGNN_CHECK_ARG(X && A && dW && ws && rows >= 1, "tensor-core wgrad: bad arguments");
     const int nsi = ns == 3 ? 2 : 1;
     const int64_t n_tiles = (rows + TR - 1) / TR;
@@ -298,7 +298,7 @@ int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, i
     CUtensorMap mx, ma;
     int rc;
     if ((rc = make_row_map32_rows(&mx, X, rows, TR))) return rc;
-    if ((rc = make_row_map32_rows(&ma, A, rows, TR))) return rc;
+    if ((rc = make_row_map32_rows(&ma, A, rows, TR, a_cols > 0 ? a_cols : TC_H))) return rc;
     const size_t smem = (size_t)WgSmem::ops + (size_t)2 * nsi * OP_BYTES;
     float* partials = static_cast<float*>(ws);
     if (ns == 3) {

@@ -126,3 +126,53 @@ def test_overlapped_step_equals_plain_step_on_one_rank():
         oa.step()
         ob.step_overlapped(n_buckets=3)
     assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
+def _overlap_worker(rank, world, port, out):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from cosmology_gnn_simulation_b200 import distributed as cd
+    from cosmology_gnn_simulation_b200.optim import FusedAdam
+    cd.init_from_env("nccl")
+    d = torch.device("cuda", rank)
+    torch.manual_seed(3)
+    shapes = [(128, 384), (128,), (128, 128), (3, 128), (3,)]
+    params = [torch.nn.Parameter(torch.randn(s, device=d)) for s in shapes]
+    opt = FusedAdam(params, lr=1e-2)
+    gen = torch.Generator(device=d).manual_seed(100 + rank)              # every rank has its own partial gradient
+    for _ in range(3):
+        for p in params:
+            p.grad = torch.randn(p.shape, device=d, generator=gen)
+        opt.step_overlapped(n_buckets=3, average=False)
+    torch.save([p.detach().cpu() for p in params], f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_overlapped_step_on_two_ranks_equals_summed_gradient_step(tmp_path):
+    """FusedAdam.step_overlapped (bucketed all-reduce, the update of bucket i under the reduction of bucket i+1) against a
+    single-process Adam on the SUM of the two ranks' gradients."""
+    import socket
+    import torch.multiprocessing as mp
+    from cosmology_gnn_simulation_b200.optim import FusedAdam
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "p")
+    mp.spawn(_overlap_worker, args=(2, port, out), nprocs=2, join=True)
+    r0, r1 = torch.load(f"{out}.0"), torch.load(f"{out}.1")
+    assert all(torch.equal(a, b) for a, b in zip(r0, r1))
+    d = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    shapes = [(128, 384), (128,), (128, 128), (3, 128), (3,)]
+    params = [torch.nn.Parameter(torch.randn(s, device=d)) for s in shapes]
+    opt = FusedAdam(params, lr=1e-2)
+    gens = [torch.Generator(device=d).manual_seed(100 + r) for r in range(2)]
+    for _ in range(3):
+        for p in params:
+            p.grad = torch.randn(p.shape, device=d, generator=gens[0]) + torch.randn(p.shape, device=d, generator=gens[1])
+        opt.step()
+    for a, p in zip(r0, params):
+        assert torch.allclose(a, p.detach().cpu(), rtol=1e-6, atol=1e-7)
