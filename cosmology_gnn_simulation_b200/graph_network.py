@@ -464,7 +464,7 @@ class EncodeProcessDecode(nn.Module):
         order = inv = None
         pos = getattr(graph, "pos", None)
         want = os.environ.get("CGNN_REORDER")
-        if halo is None and torch.is_tensor(pos) and pos.dim() == 2 and pos.shape[0] == n and pos.shape[1] == 3 and pos.device == senders.device \
+        if torch.is_tensor(pos) and pos.dim() == 2 and pos.shape[0] == n and pos.shape[1] == 3 and pos.device == senders.device \
                 and (want == "1" or (want is None and n >= REORDER_MIN_NODES)):
             key = (senders.data_ptr(), senders._version, pos.data_ptr(), pos._version, n, k)
             if self._graph_cache.get("order_key") != key:
@@ -473,9 +473,14 @@ class EncodeProcessDecode(nn.Module):
                 o = _morton_order(pos, box)
                 iv = torch.empty_like(o)
                 iv[o] = torch.arange(n, device=o.device)
-                sp = iv.to(torch.int32)[senders.view(n, k)[o].long()].reshape(-1).contiguous()     # new id of every edge's sender, receivers in new order
-                self._graph_cache.update(order_key=key, order=o, inv=iv, order_senders=sp)
+                # new id of every edge's sender, receivers in new order (a slab rank's halo senders keep their ids behind the owned rows)
+                new_id = iv.to(torch.int32) if n_nodes == n else torch.cat([iv.to(torch.int32),
+                                                                             torch.arange(n, n_nodes, dtype=torch.int32, device=o.device)])
+                sp = new_id[senders.view(n, k)[o].long()].reshape(-1).contiguous()
+                self._graph_cache.update(order_key=key, order=o, inv=iv, order_senders=sp,
+                                         order_halo=None if halo is None else halo.renumbered(iv))
             order, inv, senders = self._graph_cache["order"], self._graph_cache["inv"], self._graph_cache["order_senders"]
+            halo = self._graph_cache["order_halo"]
         if self.num_neighbors is not None and k != self.num_neighbors:
             raise ValueError(f"graph has in-degree {k}, model was built with num_neighbors={self.num_neighbors}")
         k_valid = 0
@@ -499,7 +504,7 @@ class EncodeProcessDecode(nn.Module):
                 holder["t"] = ops.csr_transpose(senders, n_nodes)
             return holder["t"]
 
-        return senders, k, k_valid, transpose, order, inv
+        return senders, k, k_valid, transpose, order, inv, halo
 
     def forward(self, input_graph) -> Dict[str, torch.Tensor]:
         x, edge_attr = input_graph.x, input_graph.edge_attr
@@ -530,7 +535,7 @@ class EncodeProcessDecode(nn.Module):
             flat += mp.tensors()
 
         n = x.shape[0]
-        senders, k, k_valid, transpose, order, inv = self._graph_tables(input_graph, n)
+        senders, k, k_valid, transpose, order, inv, halo = self._graph_tables(input_graph, n)
         if order is not None:                             # the model works in the curve order, the caller never sees it
             k_real = k_valid or k
             x = x[order]
@@ -541,7 +546,7 @@ class EncodeProcessDecode(nn.Module):
             edge_attr = padded.view(n * k, -1)
         plan = _Plan(self._num_message_passing_steps, self.message, self.precision, k, enc_node, enc_edge,
                      proc_node, proc_edge, dec_acc, dec_temp, groups, self.edge_buffers,
-                     halo=getattr(input_graph, "halo", None), k_valid=k_valid)
+                     halo=halo, k_valid=k_valid)
         acc, temp = _EncodeProcessDecodeFn.apply(plan, senders, transpose, x, edge_attr, *flat)
         if order is not None:
             acc, temp = acc[inv], temp[inv]

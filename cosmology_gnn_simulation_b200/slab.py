@@ -88,6 +88,14 @@ class HaloPlan:
         self.send_idx = [s.to(device) for s in self.send_idx]
         return self
 
+    def renumbered(self, new_id_of_owned: torch.Tensor) -> "HaloPlan":
+        """The same plan for a rank whose OWNED rows have been renumbered (row i now lives at new_id_of_owned[i]; the halo
+        rows keep their places behind them): only the rows to send move."""
+        import copy
+        other = copy.copy(self)
+        other.send_idx = [new_id_of_owned[s] if s.numel() else s for s in self.send_idx]
+        return other
+
 
 def plan_from_global_senders(senders_global: torch.Tensor, bounds: Sequence[int], rank: int, world: int, group=None):
     """Builds the halo plan and the local sender table of one rank.

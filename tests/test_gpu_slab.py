@@ -87,7 +87,9 @@ def _compare(full, slabs, n, tol, gtol):
 
 
 @pytest.mark.parametrize("message", ["edge", "sender"])
-def test_slab_world1_equals_plain_graph(message):
+@pytest.mark.parametrize("reorder", ["0", "1"])
+def test_slab_world1_equals_plain_graph(message, reorder, monkeypatch):
+    monkeypatch.setenv("CGNN_REORDER", reorder)
     dev = torch.device("cuda", 0)
     n, k, L, M = 3000, 16, 64, 3
     box, params = _setup(n, k, L, M)
@@ -112,8 +114,11 @@ def _worker(rank, world, port, out, message, precision):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("message,precision", [("edge", "fp32"), ("sender", "fp32"), ("edge", "bf16x3")])
-def test_slab_world2_equals_single_gpu(tmp_path, message, precision):
+@pytest.mark.parametrize("message,precision,reorder", [("edge", "fp32", "0"), ("sender", "fp32", "0"), ("edge", "bf16x3", "0"),
+                                                       ("edge", "fp32", "1"), ("edge", "bf16x3", "1")])
+def test_slab_world2_equals_single_gpu(tmp_path, message, precision, reorder, monkeypatch):
+    # reorder = "1": every rank renumbers its owned rows along a Z-order curve inside the model (the halo plan's send lists move with them)
+    monkeypatch.setenv("CGNN_REORDER", reorder)
     world = 2
     out = str(tmp_path / "res")
     mp.spawn(_worker, args=(world, _free_port(), out, message, precision), nprocs=world, join=True)
