@@ -380,3 +380,34 @@ def test_tc_rows_forward_backward(precision, in_dim, out_dim, ln, rows):
         assert rel_l2(got.cpu(), want) < tol, (i, rel_l2(got.cpu(), want))
     if need_dx:
         assert rel_l2(dx.cpu(), x64.grad) < tol
+
+
+@pytest.mark.parametrize("n,halo", [(6000, 0), (3000, 600)])
+def test_edge_backward_is_reproducible(n, halo):
+    """Every kernel is deterministic (fixed-order reductions, no float atomics): repeated calls on the same inputs must be
+    bit-identical.  This is the race detector for the ring / barrier protocols of the chain kernels -- it caught the
+    LayerNorm-backward chain reading its dU rows through the TMA ring (17 of 39 repetitions differed)."""
+    from cosmology_gnn_simulation_b200 import ops
+    d = _dev()
+    gen = torch.Generator(device=d).manual_seed(0)
+    k, nn = 16, n + halo
+    ws = [torch.randn(L, i, device=d, generator=gen) / i ** 0.5 for i in (3 * L, L, L)]
+    bs = [torch.randn(L, device=d, generator=gen) * 0.1 for _ in range(3)]
+    from cosmology_gnn_simulation_b200.ops import MlpParams
+    p = MlpParams(ws, bs, torch.ones(L, device=d), torch.zeros(L, device=d))
+    h = torch.randn(nn, L, device=d, generator=gen)
+    e = torch.randn(n * k, L, device=d, generator=gen)
+    senders = torch.randint(0, nn, (n * k,), device=d, generator=gen, dtype=torch.int32)
+    rowptr, perm = ops.csr_transpose(senders, nn)
+    de0 = torch.randn(n * k, L, device=d, generator=gen)
+    dagg = torch.randn(n, L, device=d, generator=gen)
+    dh0 = torch.randn(nn, L, device=d, generator=gen)
+    ref = None
+    for rep in range(25):
+        de, dh = de0.clone(), dh0.clone()
+        grads = ops.mp_edge_bwd(p, h, e, senders, rowptr, perm, k, de, dagg, de, dh, None, "bf16x3")
+        cur = [de, dh] + list(grads)
+        if ref is None:
+            ref = [t.clone() for t in cur]
+        else:
+            assert all(torch.equal(x, y) for x, y in zip(cur, ref)), f"repetition {rep} differs"
