@@ -411,3 +411,31 @@ def test_edge_backward_is_reproducible(n, halo):
             ref = [t.clone() for t in cur]
         else:
             assert all(torch.equal(x, y) for x, y in zip(cur, ref)), f"repetition {rep} differs"
+
+
+@pytest.mark.parametrize("message", ["edge", "sender"])
+def test_whole_model_training_step_is_reproducible(message):
+    """The benched mode end to end: six training applications on the same graph, bit-identical outputs and gradients."""
+    from cosmology_gnn_simulation_b200 import synthetic
+    from cosmology_gnn_simulation_b200.data_utils import preprocess
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode
+    from cosmology_gnn_simulation_b200.loss import combined_loss
+    n, k, M = 20000, 16, 3
+    box = synthetic.make_box(n, "uniform", seed=11)
+    md = box["metadata"]
+    g = preprocess(box["Coordinates"][:5], box["InternalEnergy"][:5], md, box["Coordinates"][5:6], box["InternalEnergy"][5:6],
+                   num_neighbors=k, dt=md["dt"], box_size=md["box_size"], device=_dev())
+    torch.manual_seed(0)
+    model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision="bf16x3").to(_dev())
+    ref = None
+    for rep in range(6):
+        for p in model.parameters():
+            p.grad = None
+        pred = model(g)
+        combined_loss(pred, g, md["dt"], 1.0, 1.0, 0.1)["loss"].backward()
+        cur = [pred["acceleration"].detach().clone(), pred["temp_rate"].detach().clone()] + \
+              [p.grad.clone() for p in model.parameters() if p.grad is not None]
+        if ref is None:
+            ref = cur
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(cur, ref)), f"repetition {rep} differs"

@@ -56,6 +56,12 @@ else:
     h = torch.randn(n, L, device=dev, generator=gen)
     e = torch.randn(n * k, L, device=dev, generator=gen)
     senders = g._cgnn_senders
+    if n >= (1 << 17):                                         # the model's own Z-order renumbering of large graphs (graph_network.py)
+        from cosmology_gnn_simulation_b200.graph_network import _morton_order
+        o = _morton_order(g.pos, g.box_size.reshape(-1)[0])
+        iv = torch.empty_like(o)
+        iv[o] = torch.arange(n, device=dev)
+        senders = iv.to(torch.int32)[senders.view(n, k)[o].long()].reshape(-1).contiguous()
     e_out, agg = torch.empty_like(e), torch.empty_like(h)
     if a.phase == "edge_fwd":
         run = lambda: ops.mp_edge_fwd(p, h, e, senders, k, e_out, agg, a.precision)  # noqa: E731
