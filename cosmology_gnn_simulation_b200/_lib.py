@@ -13,7 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcgnn.so")
 MAX_LAYERS = 4
 
-PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+# "bf16x3g" (CGNN_PREC_BF16X3_G16): bf16x3 whose long-stream backward keeps dY / G2 / G1 as bfloat16; chosen per call by the
+# model for the edge MLPs (graph_network.py, grad_stream), not a model-level precision
+PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "bf16x3g": 3}
 MSG = {"sender": 0, "edge": 1}
 DISP = {"raw": 0, "min_image": 1}
 

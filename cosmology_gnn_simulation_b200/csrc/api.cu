@@ -40,7 +40,7 @@ int64_t tc_rows_workspace(const cgnn_mlp* mlp, int64_t rows, int precision, int 
 
 void set_debug_stamps(unsigned long long* buf, int tiles, int launches);
 
-static bool is_tc(int precision) { return precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16; }
+static bool is_tc(int precision) { return precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16 || precision == CGNN_PREC_BF16X3_G16; }
 
 static int run_fwd(MlpTask& a, int precision, cudaStream_t s, void* ws = nullptr, int64_t wsb = 0) {
     if (precision == CGNN_PREC_FP32) return simt_mlp_fwd(a, s);

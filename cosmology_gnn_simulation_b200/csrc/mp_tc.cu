@@ -81,6 +81,9 @@ struct TcParams {
     uint32_t* bits_out;         // [n_rows][4]: bit c = (result column c > 0) -- the ReLU gate of the backward, 16 B per row (nullable)
     const uint32_t* mask_bits;  // [n_rows][4]: result = bit c ? result : 0 -- the same gate read back (nullable)
     int n_ring;                 // input ring depth
+    int in16;                   // the chain input is a bfloat16 [n_rows][128] stream (the 2-byte gradient stream of the long-stream backward):
+                                // two 64-column ring slots per tile, written to the A operand as they are -- no low part, two MMA passes
+    int out16;                  // `out` is a bfloat16 [n_rows][128] stream (round to nearest even)
     ChainBlock blk[MAX_BLOCKS]; // weight blocks in FP32 (torch layout): every CTA builds its BF16 images in shared memory itself
     const float* vec_src[5];    // bias of layer 1, 2, 3, gamma, beta (nullable -> zeros / ones for gamma)
     int vec_len[5];             // valid entries (zero padded to 128)
@@ -126,6 +129,14 @@ __device__ __forceinline__ void ld256(const float* p, float* v) {
 __device__ __forceinline__ void st256(float* p, const float* v) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+// 16 columns as bfloat16 (round to nearest even): one 32-byte sector of the row's 256 bytes
+__device__ __forceinline__ void st16h(uint16_t* p, const float* v) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 __device__ __forceinline__ void ld16(const float* p, float* v) { ld256(p, v); ld256(p + 8, v + 8); }
 __device__ __forceinline__ void st16(float* p, const float* v) { st256(p, v); st256(p + 8, v + 8); }
@@ -235,6 +246,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     constexpr bool RIN = (CFG & C_RIN) != 0, GIN = (CFG & C_GIN) != 0, SPLIT = (CFG & C_SPLIT) != 0, T1 = (CFG & C_T1) != 0;
     static_assert(!T1 || (!(CFG & C_L3) && !RIN && !SPLIT), "the ring-fed epilogue stream belongs to the one-layer chains");
     constexpr bool G4 = (CFG & C_G4) != 0;
+    // the bfloat16 row streams (p.in16 / p.out16) exist in the one-layer chains only: no trace of them in the fused forward kernels
+    constexpr bool IO16 = !(CFG & C_L3) && !RIN && !SPLIT && !G4 && !GIN;
     static_assert(!G4 || (GIN && !T1 && !RIN && !SPLIT), "gather4 feeds the accumulator initialisation; map 1 and the ring must be free for it");
     constexpr int NEPI = SPLIT ? 16 : 8;                    // epilogue warps
     constexpr int GW = NEPI / 2;                            // warps per epilogue group (= per tile in flight)
@@ -340,16 +353,20 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         if (++buf == (uint32_t)NRING) { buf = 0; ++use; }
                     }
                 }
-                for (int ip = 0; ip < p.n_in + (T1 ? 1 : 0); ++ip)      // T1: the epilogue stream follows the MMA input(s), map 1
-                    for (int q = 0; q < NCW; ++q) {
+                for (int ip = 0; ip < p.n_in + (T1 ? 1 : 0); ++ip) {    // T1: the epilogue stream follows the MMA input(s), map 1
+                    // a bfloat16 input has 64 columns per slot (the same 128-byte rows): two slots per tile
+                    const bool in16 = IO16 && p.in16 && ip < p.n_in;
+                    const int nq = in16 ? NCW / 2 : NCW, qcols = in16 ? 2 * CW : CW;
+                    for (int q = 0; q < nq; ++q) {
                         if (lane == 0) {
                             mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 100 + buf);
                             uint64_t* full = &bars->in_full[it & 1][buf];
                             mbar_expect_tx(full, CW_BYTES);
-                            tma_load_2d(sRing + buf * CW_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * CW, (int)row0, full);
+                            tma_load_2d(sRing + buf * CW_BYTES, ip == 0 ? &tm_in0 : &tm_in1, q * qcols, (int)row0, full);
                         }
                         if (++buf == (uint32_t)NRING) { buf = 0; ++use; }
                     }
+                }
                 if (G4) __syncwarp();
             }
         }
@@ -388,9 +405,11 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                         acc = 1u;
                     }
                     if (NS == 3) {
+                        if (!(IO16 && p.in16)) {           // (a bfloat16 input has no low part)
 #pragma unroll 1
-                        for (int ks = 0; ks < TC_H / 16; ++ks)
-                            umma_bf16_ts<2>(d, a_lo + ks * 8, dw_hi + (uint64_t)(ks * 16), idesc, 1u);
+                            for (int ks = 0; ks < TC_H / 16; ++ks)
+                                umma_bf16_ts<2>(d, a_lo + ks * 8, dw_hi + (uint64_t)(ks * 16), idesc, 1u);
+                        }
 #pragma unroll 1
                         for (int ks = 0; ks < TC_H / 16; ++ks)
                             umma_bf16_ts<2>(d, a_hi + ks * 8, dw_lo + (uint64_t)(ks * 16), idesc, 1u);
@@ -409,6 +428,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
     } else {
         // ============================ epilogue groups: thread = row ==============================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SPLIT ? EPI_REGS_SPLIT : EPI_REGS));
+        const uint32_t zero_rt = (uint32_t)((unsigned long long)p.n_rows >> 62);     // 0, but not to the assembler (fold_zero)
         const int g = warp / GW;                        // group = TMEM slot
         const int wq = warp & 3;                        // lane quarter this warp may touch
         const int half = SPLIT ? ((warp >> 2) & 1) : 0; // which 64 columns of the row this thread owns (column split)
@@ -429,7 +449,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 
         // ring slot of this group's next tile's first chunk: advanced by the chunks of two tiles (its own and the other group's) per
         // iteration, wrapped by subtraction -- no division in the loops
-        const uint32_t uring = (uint32_t)NRING, tile_chunks = (uint32_t)(NCW * (p.n_in + (T1 ? 1 : 0) + (G4 ? 1 : 0)));
+        const uint32_t uring = (uint32_t)NRING, tile_chunks = (uint32_t)((IO16 && p.in16 ? NCW / 2 : NCW) * p.n_in + NCW * ((T1 ? 1 : 0) + (G4 ? 1 : 0)));
         uint32_t ring0 = (uint32_t)g * tile_chunks % uring;
         // sender index of the first tile's row; the next tile's is fetched one tile ahead so its latency never shows
         int32_t snd_next = 0;
@@ -481,10 +501,10 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                                 lo16[4 * j] = u.x; lo16[4 * j + 1] = u.y; lo16[4 * j + 2] = u.z; lo16[4 * j + 3] = u.w;
                                 hi16[4 * j] = w.x; hi16[4 * j + 1] = w.y; hi16[4 * j + 2] = w.z; hi16[4 * j + 3] = w.w;
                             }
-                            consume16(reinterpret_cast<const uint32_t*>(hi16));
-                            consume16(reinterpret_cast<const uint32_t*>(lo16));
+                            const uint32_t fz = fold_zero<16>(reinterpret_cast<const uint32_t*>(hi16), zero_rt) ^
+                                                fold_zero<16>(reinterpret_cast<const uint32_t*>(lo16), zero_rt);
                             __syncwarp();
-                            if (lane == 0) mbar_arrive_local(&bars->in_empty[buf]);
+                            if (lane == 0) mbar_arrive_local(&bars->in_empty[buf] + fz);
                         }
                     } else {
                         ld16(ps + c, a0); ld16(ps + c + 16, a1); ld16(ps + c + 32, a2); ld16(ps + c + 48, a3);
@@ -507,6 +527,29 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     pm ^= 1u;
                     tc_fence_after_sync();
                 }
+                if (IO16 && p.in16) {
+                    // bfloat16 input: a slot holds 64 columns of this thread's row (128 bytes, swizzled like the FP32 chunks) and
+                    // they ARE the A operand's 32 words
+                    for (int q = 0; q < NCW / 2; ++q, buf = buf + 1 == uring ? 0 : buf + 1) {
+                        mbar_wait_or_trap(&bars->in_full[g][buf], (in_par >> buf) & 1u, 150 + buf);
+                        in_par ^= 1u << buf;
+                        const uint8_t* src = sRing + buf * CW_BYTES;
+                        uint32_t w0[16], w1[16];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(src + swz128(r, j));
+                            const uint4 v = *reinterpret_cast<const uint4*>(src + swz128(r, 4 + j));
+                            w0[4 * j] = u.x; w0[4 * j + 1] = u.y; w0[4 * j + 2] = u.z; w0[4 * j + 3] = u.w;
+                            w1[4 * j] = v.x; w1[4 * j + 1] = v.y; w1[4 * j + 2] = v.z; w1[4 * j + 3] = v.w;
+                        }
+                        // the raw words go to TMEM first (a real reader of every loaded register), then the slot goes back
+                        tmem_st_32x32b_x16(tAhi + q * 32, w0);
+                        tmem_st_32x32b_x16(tAhi + q * 32 + 16, w1);
+                        const uint32_t fz = fold_zero<16>(w0, zero_rt) ^ fold_zero<16>(w1, zero_rt);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_local(&bars->in_empty[buf] + fz);
+                    }
+                } else
                 for (int q = 0; q < NCW; ++q, buf = buf + 1 == uring ? 0 : buf + 1) {
                     // (every thread waits on every chunk's barrier, also on chunks of the other column half: a parity wait
                     //  may never fall two phases behind)
@@ -602,7 +645,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             constexpr bool lnb = LNB;
             // T1: the dU rows (LayerNorm backward) or the residual arrive through the ring, 32 columns per slot, after the tile's
             // MMA input; every thread reads its own row of a slot (two 16-column halves) and the slot goes back after the second
-            uint32_t tbuf = buf;
+            uint32_t tbuf = buf, t1fold = 0u;
             auto t1_load16 = [&](int cc, float* dst) {
                 if ((cc & 31) == 0) {
                     mbar_wait_or_trap(&bars->in_full[g][tbuf], (in_par >> tbuf) & 1u, 190);
@@ -614,10 +657,12 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                     const float4 e4 = *reinterpret_cast<const float4*>(src + swz128(r, ((cc & 31) >> 2) + j));
                     dst[4 * j] = e4.x; dst[4 * j + 1] = e4.y; dst[4 * j + 2] = e4.z; dst[4 * j + 3] = e4.w;
                 }
+                // raw loaded values: the arrival that hands the slot back is made to depend on both halves (fold_zero)
+                t1fold ^= fold_zero<16>(reinterpret_cast<const uint32_t*>(dst), zero_rt);
                 if ((cc & 31) == 16) {
-                    consume16(reinterpret_cast<const uint32_t*>(dst));      // (see the input phase: consume, then arrive)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_local(&bars->in_empty[tbuf]);
+                    if (lane == 0) mbar_arrive_local(&bars->in_empty[tbuf] + t1fold);
+                    t1fold = 0u;
                     tbuf = tbuf + 1 == uring ? 0 : tbuf + 1;
                 }
             };
@@ -629,6 +674,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                               : lnb   ? (p.du_recv ? p.du_recv + recvoff : nullptr)
                                       : (p.residual ? p.residual + rowoff : nullptr);
             float* outp = p.out + rowoff;
+            uint16_t* outh = reinterpret_cast<uint16_t*>(p.out) + rowoff;      // out16: the same rows at 2 bytes per column
             const bool vout = valid && p.out != nullptr;            // the last processor step of a forward has no use for e'
             float* aggp = AGG && p.agg_out ? p.agg_out + recvoff : nullptr;
             // four 16-column chunk buffers per stream, each reloaded four chunks (64 columns) ahead
@@ -848,7 +894,8 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             for (int j = 0; j < 16; ++j) cb[j] += v[j];
                             if (vout) st16(outp + cc, cb);
                         } else if (vout) {
-                            st16(outp + cc, v);
+                            if (IO16 && p.out16) st16h(outh + cc, v);
+                            else st16(outp + cc, v);
                         }
                         if (aggp) {
                             if (dummy) {
@@ -949,6 +996,11 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     for (int l = 0; l < 2; ++l) { p.hid_mask[l] = op.hid_mask[l]; p.hid_out[l] = op.hid_out[l]; p.hid_agg[l] = op.hid_agg[l]; }
     p.du_rows = op.du_rows; p.du_recv = op.du_recv; p.ln_partials = static_cast<float*>(op.ln_ws);
     p.out = op.out; p.bits_out = op.bits_out; p.mask_bits = op.mask_bits;
+    p.in16 = op.in16 != 0; p.out16 = op.out16 != 0;
+    CGNN_CHECK_ARG(!op.in16 || (op.n_layers == 1 && !op.in1 && !gather && op.in0_cols == 0 && op.residual != op.in0),
+                   "tensor-core chain: a bfloat16 input stream feeds one-layer chains with a single input");
+    CGNN_CHECK_ARG(!op.out16 || (op.out && !op.residual && op.n_layers == 1 && !gather),
+                   "tensor-core chain: a bfloat16 output stream belongs to one-layer chains without gather or residual");
     for (int b = 0; b < n_blocks; ++b) p.blk[b] = op.blk[b];
     if (op.n_layers == 1) {
         p.vec_src[0] = op.bias[0];
@@ -965,7 +1017,9 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     }
     CUtensorMap m0, m1;
     int rc;
-    if ((rc = make_row_map32_rows(&m0, op.in0, op.rows, 128, op.in0_cols > 0 ? op.in0_cols : TC_H))) return rc;
+    if (op.in16) rc = make_row_map_bf16(&m0, op.in0, op.rows, 128);
+    else rc = make_row_map32_rows(&m0, op.in0, op.rows, 128, op.in0_cols > 0 ? op.in0_cols : TC_H);
+    if (rc) return rc;
     // the shared memory the weights leave goes to the input ring
     const size_t ring_off = ring_offset(n_blocks, NSI, op.ln_bwd != 0);
     // the residual is the chain's own (first) input and the ring can hold both groups' tiles: no re-read
@@ -1086,13 +1140,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows = 128, int cols = TC_H);
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows = 128, int cols = TC_H,
+                    bool bf16 = false);
 int make_row_map(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, CH, CU_TENSOR_MAP_SWIZZLE_64B); }
 
 // `cols`: width of the array in global memory (row pitch cols * 4 bytes, a multiple of 16).  A box may reach beyond it: the TMA
 // fills the columns outside the tensor with zeros and reads nothing for them -- how a narrow array (edge features, 4 columns)
 // enters the 128-column chains without a padded copy in HBM.
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows, int cols) {
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int box_cols, CUtensorMapSwizzle swz, int box_rows, int cols, bool bf16) {
     static EncodeTiledFn fn = nullptr;
     if (fn == nullptr) {
         void* f = nullptr;
@@ -1102,10 +1157,10 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_col
         fn = reinterpret_cast<EncodeTiledFn>(f);
     }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * (bf16 ? 2 : 4)};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+    CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1118,6 +1173,10 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_col
 int make_row_map32(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B); }
 int make_row_map32_rows(CUtensorMap* m, const float* base, int64_t rows, int box_rows, int cols) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B, box_rows, cols); }
 int make_gather_map32(CUtensorMap* m, const float* base, int64_t rows) { return make_map(m, base, rows, 32, CU_TENSOR_MAP_SWIZZLE_128B, 1); }
+// bfloat16 [rows][128]: boxes of box_rows rows x 64 columns -- the same 128-byte rows and swizzle as the FP32 boxes of 32 columns
+int make_row_map_bf16(CUtensorMap* m, const void* base, int64_t rows, int box_rows) {
+    return make_map(m, base, rows, 64, CU_TENSOR_MAP_SWIZZLE_128B, box_rows, TC_H, true);
+}
 
 void set_debug_stamps(unsigned long long* buf, int tiles, int launches) {
     g_stamps = buf; g_stamp_tiles = tiles; g_stamp_launches = launches; g_stamp_next = 0;

@@ -39,6 +39,21 @@ __device__ __forceinline__ void consume16(const uint32_t* r) {
                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
+// consume16 only pins the compiler's front end: where the loaded values feed arithmetic first (split2 ...) real instructions read
+// them ahead of the arrival, but RAW loaded registers (a bfloat16 stream that goes to tcgen05.st / shared memory as it is, ring-fed
+// row streams) are read by nothing the assembler has to keep in front of it -- the loads are then merely in flight when the slot is
+// handed back, and the TMA refill lands under them (seen as a few wrong rows of one tile in the fifth tile of a CTA, only when the
+// timing was tight).  fold_zero makes the arrival itself depend on them: it XORs the registers together with real instructions and
+// masks the result with `z`, a run-time zero the assembler cannot know (callers pass the top bits of a 64-bit row count); the
+// result (0) offsets the barrier address of the arrival.
+template <int N>
+__device__ __forceinline__ uint32_t fold_zero(const uint32_t* r, uint32_t z) {
+    uint32_t x = r[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) x ^= r[j];
+    return x & z;
+}
+
 // byte offset of the 16-byte piece j (0..3) of row r inside a 64-byte-swizzled chunk buffer
 __device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
 
@@ -50,6 +65,8 @@ int make_row_map32(CUtensorMap* m, const float* base, int64_t rows);
 int make_row_map32_rows(CUtensorMap* m, const float* base, int64_t rows, int box_rows, int cols = TC_H);
 // boxes of 1 row x 32 columns, 128-byte swizzle: the map of tile::gather4 loads (four arbitrary rows per instruction)
 int make_gather_map32(CUtensorMap* m, const float* base, int64_t rows);
+// bfloat16 [rows][128] array: boxes of box_rows rows x 64 columns, 128-byte swizzle (the 2-byte gradient stream)
+int make_row_map_bf16(CUtensorMap* m, const void* base, int64_t rows, int box_rows);
 
 // ---- building blocks used by the backward orchestration (defined in mp_tc.cu / wgrad_tc.cu) -----------
 // B[n][k] = W[(row0 + n) * ld + col0 + k] (transpose: W[(row0 + k) * ld + col0 + n]); zero where n >= nmax or k >= kmax (0 = 128)
@@ -82,6 +99,9 @@ struct ChainOp {
     // LayerNorm backward instead of forward after the last layer: out = dY of (Y, dU), dU = du_rows[row] + du_recv[row / k];
     // d gamma / d beta (=|+=) their column sums (fixed-order reduction through ln_ws, ln_bwd_workspace_bytes())
     int ln_bwd; const float* du_rows; const float* du_recv; float* dgamma; float* dbeta; int accumulate; void* ln_ws;
+    // the 2-byte gradient stream of the long-stream backward: in0 / out are bfloat16 [rows][128] arrays behind the float pointers
+    // (one-layer chains; in16: single input, no gather; out16: no residual)
+    int in16; int out16;
 };
 int run_chain(const ChainOp& op, cudaStream_t stream);
 
@@ -89,8 +109,9 @@ int run_chain(const ChainOp& op, cudaStream_t stream);
 int64_t wgrad_workspace_bytes();
 // only the first nrows rows / ncols columns of the 128 x 128 product are written (0 = all 128)
 // a_cols > 0: A is [rows][a_cols] (a_cols * 4 a multiple of 16), zero-filled up to 128 by the TMA
+// x16: X is a bfloat16 [rows][128] array (the 2-byte gradient stream) -- taken as it is, no low part
 int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, int ld, int col0, float* db,
-              int accumulate, void* ws, cudaStream_t stream, int nrows = 0, int ncols = 0, int a_cols = 0);
+              int accumulate, void* ws, cudaStream_t stream, int nrows = 0, int ncols = 0, int a_cols = 0, int x16 = 0);
 
 
 // dY = LayerNorm backward of (Y, dU), dU = (dU_rows ? dU_rows[row] : 0) + (dU_recv ? dU_recv[row / k] : 0); dY may alias Y

@@ -86,30 +86,76 @@ int slice_rows(const float* src, int w, int64_t rows, float* dst, cudaStream_t s
     return CGNN_OK;
 }
 
-// dPs[j] += sum of G1[e - r0] over the out-edges e of sender j with r0 <= e < r1, in perm order (= ascending edge id, so
-// chunk after chunk in ascending r0 adds every row's terms in exactly the order of a one-shot pass: deterministic and
-// independent of the chunk size).  A warp-sized group of threads per node, thread <-> 4 columns.
-__global__ void scatter_chunk_kernel(const float4* __restrict__ G1, int r0, int r1, const int32_t* __restrict__ rowptr,
-                                     const int32_t* __restrict__ perm, int64_t n, float4* __restrict__ dPs) {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= n * (TC_H / 4)) return;
-    const int64_t j = idx / (TC_H / 4);
-    const int c = (int)(idx - j * (TC_H / 4));
-    const int a = rowptr[j], b = rowptr[j + 1];
-    int lo = a, hi = b;
-    while (lo < hi) {                          // first out-edge of j inside the chunk (rows are ~k long)
-        const int mid = (lo + hi) >> 1;
-        if (perm[mid] < r0) lo = mid + 1; else hi = mid;
+// ---- per-node sums of G1 by SENDER, chunk by chunk ------------------------------------------------------------------------
+// dPs[j] += sum of G1[e - r0] over the out-edges e of sender j with r0 <= e < r1, in perm order (= ascending edge id, so chunk
+// after chunk in ascending r0 adds every row's terms in exactly the order of a one-shot pass: deterministic and independent of the
+// chunk size).  Which nodes have out-edges inside a chunk is worked out ONCE per call (round 2 scanned every node's list in every
+// chunk: 574 us per 2 Mi-row chunk at 2.1 M particles, 7 % of the training step, for 1 GiB of useful reads): a node's out-edge
+// list is ascending, so one walk over it yields its (chunk, first position) pairs; they are counted, offset and filled into
+// per-chunk entry lists (the order of the entries inside a list is whatever the atomics give -- every entry owns its dPs row, so
+// the sums do not depend on it), and a chunk's kernel visits its own entries only, a warp per entry.
+__global__ void sender_chunks_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, int64_t n, int chunk,
+                                     int32_t* __restrict__ cnt, const int32_t* __restrict__ off, int2* __restrict__ ent) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int prev = -1;
+    for (int p = rowptr[j], b = rowptr[j + 1]; p < b; ++p) {
+        const int c = perm[p] / chunk;
+        if (c == prev) continue;
+        prev = c;
+        const int slot = atomicAdd(cnt + c, 1);
+        if (ent != nullptr) ent[off[c] + slot] = make_int2((int)j, p);      // second pass: fill
     }
-    if (lo == b || perm[lo] >= r1) return;
-    float4 s = dPs[idx];
-    for (int p = lo; p < b; ++p) {
-        const int e = perm[p];
-        if (e >= r1) break;
-        const float4 v = G1[(int64_t)(e - r0) * (TC_H / 4) + c];
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+}
+// off[c] = entries of the chunks before c (exclusive scan; at most a few thousand chunks), counters back to zero for the fill pass
+__global__ void sender_chunks_offsets_kernel(int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n_chunks) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int acc = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        off[c] = acc;
+        acc += cnt[c];
+        cnt[c] = 0;
     }
-    dPs[idx] = s;
+    off[n_chunks] = acc;
+}
+constexpr int SCATTER_WARPS = 8;
+// G16: G1 is the bfloat16 gradient stream (8 bytes per lane and row instead of 16).  lane <-> 4 columns.
+template <bool G16>
+__global__ void __launch_bounds__(SCATTER_WARPS * 32)
+scatter_chunk_kernel(const void* __restrict__ G1v, int r0, int r1, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                     const int2* __restrict__ ent, const int32_t* __restrict__ off, float4* __restrict__ dPs) {
+    const int lane = threadIdx.x & 31;
+    const int first = off[0], count = off[1] - first;
+    for (int i = blockIdx.x * SCATTER_WARPS + (threadIdx.x >> 5); i < count; i += gridDim.x * SCATTER_WARPS) {
+        const int2 en = ent[first + i];
+        const int b = rowptr[en.x + 1];
+        float4* dst = dPs + (int64_t)en.x * (TC_H / 4) + lane;
+        float4 s = *dst;
+        for (int base = en.y; base < b; base += 32) {
+            // the list is ascending: the edges of this chunk are a prefix of what is left of it
+            const int e = base + lane < b ? perm[base + lane] : 0x7FFFFFFF;
+            const int m = __popc(__ballot_sync(0xFFFFFFFFu, e < r1));
+#pragma unroll 4
+            for (int t = 0; t < m; ++t) {
+                const int64_t row = __shfl_sync(0xFFFFFFFFu, e, t) - r0;
+                float4 v;
+                if (G16) {
+                    const uint2 w = reinterpret_cast<const uint2*>(G1v)[row * (TC_H / 4) + lane];
+                    v = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
+                                    __uint_as_float(w.y & 0xFFFF0000u));
+                } else {
+                    v = reinterpret_cast<const float4*>(G1v)[row * (TC_H / 4) + lane];
+                }
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            if (m < 32) break;
+        }
+        *dst = s;
+    }
+}
+int64_t scatter_entries(int64_t E, int64_t nn, int64_t chunk) {
+    const int64_t n_chunks = (E + chunk - 1) / chunk;
+    return E < nn * n_chunks ? E : nn * n_chunks;          // every edge opens at most one entry, every node at most one per chunk
 }
 
 // encoder / decoder MLPs: 3 layers, hidden 128, in <= 128, out <= 128 (LayerNorm only with out == 128)
@@ -141,14 +187,16 @@ int64_t tc_bwd_workspace(const cgnn_mlp* mlp, int64_t n, int64_t n_nodes, int k,
     (void)mlp; (void)precision;
     if (k == 0) return Scratch::bytes() + 5 * rows_bytes(n) + 2 * gate_bytes(n);
     int64_t chunk = n * k < CHUNK_ROWS ? n * k : CHUNK_ROWS;
-    return Scratch::bytes() + 5 * rows_bytes(chunk) + 2 * gate_bytes(chunk) + 2 * rows_bytes(n) + 2 * rows_bytes(n_nodes);
+    const int64_t n_chunks = (n * k + chunk - 1) / chunk;
+    return Scratch::bytes() + 5 * rows_bytes(chunk) + 2 * gate_bytes(chunk) + 2 * rows_bytes(n) + 2 * rows_bytes(n_nodes) +
+           align_up(scatter_entries(n * k, n_nodes, chunk) * 8, 256) + 2 * align_up((n_chunks + 1) * 4, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 int tc_mlp_fwd(MlpTask& a, int precision, void* ws, int64_t wsb, cudaStream_t s) {
-    const int ns = precision == CGNN_PREC_BF16X3 ? 3 : 1;
+    const int ns = precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16X3_G16 ? 3 : 1;
     const MlpDev& m = a.mlp;
     if (a.mode == MODE_EDGE) {
         if (!tc_shape_ok(m, 3) || !tc_k_ok(a.k)) {
@@ -264,6 +312,15 @@ static int bwd_mode(int64_t rows) {
     return pair_tiles <= 2 * clusters ? 1 : 0;
 }
 
+// The 2-byte gradient stream (CGNN_PREC_BF16X3_G16): on long row streams of an MLP with LayerNorm the three gradient
+// intermediates dY, G2, G1 are bfloat16 in HBM -- 10 of the 21 row-stream passes of a processor step become half passes.
+// Forward values (the activations that decide the ReLU gates) are untouched; what the rounding does to the parameter gradients
+// is measured on the oracle by tests/study_grad_stream.py (2.6e-4 at 1 024 particles, 1.3e-4 at 4 096: it averages out over the
+// rows a weight gradient sums).  Short streams (the fused chains) keep FP32 intermediates.
+static bool grad16(int precision, const MlpDev& m, int64_t rows) {
+    return precision == CGNN_PREC_BF16X3_G16 && m.gamma != nullptr && bwd_mode(rows) == 0;
+}
+
 // Backward of one 3-layer MLP (+ LayerNorm) over a row range as TWO fused chains plus the weight gradients:
 //   R  recompute:  in -> A1 -> A2 -> Y, LayerNorm backward of (Y, dU) in the final epilogue -> dY (T);
 //                  A1, A2 are written from the hidden epilogues (the dgrad masks and the wgrad operands),
@@ -277,9 +334,11 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
                           float* A1, float* A2, float* T, float* G2, uint32_t* gate1, uint32_t* gate2,
                           const float* du_rows, const float* du_recv, int k, int k_valid,
                           ChainBlock last, const float* residual, float* d_in, float* g1_out, float* g1_agg,
-                          int accumulate, cudaStream_t s) {
+                          int accumulate, cudaStream_t s, int g16 = 0) {
     int rc;
     const int n_in = r.in1 ? 2 : 1;
+    // g16 (see grad16()): T, G2 and g1_out hold bfloat16 rows -- written rounded to nearest even by the chain that produces them,
+    // read as they are by the next dgrad chain, the weight gradient and the caller (sender scatter, dW1)
     if (bwd_mode(rows) == 0) {
         // A1 = relu(layer 1), A2 = relu(A1 W2^T + b2)
         r.ns = ns; r.rows = rows; r.n_layers = 1;
@@ -295,29 +354,32 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
             op.in0 = A2; op.blk[0] = {m.W[2], TC_H, 0, 0, 0}; op.bias[0] = m.b[2];
             op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim; op.ln_bwd = 1; op.k = k; op.k_valid = k_valid;
             op.du_rows = du_rows; op.du_recv = du_recv; op.dgamma = g->ln_gamma; op.dbeta = g->ln_beta; op.accumulate = accumulate; op.ln_ws = sc.lnb;
-            op.out = T;
+            op.out = T; op.out16 = g16;
             if ((rc = run_chain(op, s))) return rc;
         }
-        if ((rc = run_wgrad(ns, T, A2, rows, g->W[2], TC_H, 0, g->b[2], accumulate, sc.wg, s, m.out_dim, 0))) return rc;
+        if ((rc = run_wgrad(ns, T, A2, rows, g->W[2], TC_H, 0, g->b[2], accumulate, sc.wg, s, m.out_dim, 0, 0, g16))) return rc;
         {   // G2 = (dY W3) * [A2 > 0]
             ChainOp op = base_op(ns, sc, rows);
             op.in0 = T; op.blk[0] = {m.W[2], TC_H, 0, 0, 1, 0, m.out_dim}; op.mask_bits = gate2; op.out = G2;
+            op.in16 = g16; op.out16 = g16;
             if ((rc = run_chain(op, s))) return rc;
         }
-        if ((rc = run_wgrad(ns, G2, A1, rows, g->W[1], TC_H, 0, g->b[1], accumulate, sc.wg, s))) return rc;
-        {   // G1 = (G2 W2) * [A1 > 0]   (+ per-receiver sum)
+        if ((rc = run_wgrad(ns, G2, A1, rows, g->W[1], TC_H, 0, g->b[1], accumulate, sc.wg, s, 0, 0, 0, g16))) return rc;
+        {   // G1 = (G2 W2) * [A1 > 0]   (+ per-receiver sum, taken from the FP32 accumulators)
             ChainOp op = base_op(ns, sc, rows);
             op.in0 = G2; op.blk[0] = {m.W[1], TC_H, 0, 0, 1}; op.mask_bits = gate1; op.out = g1_out;
             op.k = k; op.agg_out = g1_agg;
+            op.in16 = g16; op.out16 = g16;
             if ((rc = run_chain(op, s))) return rc;
         }
         if (d_in != nullptr) {   // d_in = G1 last^T (+ residual)
             ChainOp op = base_op(ns, sc, rows);
-            op.in0 = g1_out; op.blk[0] = last; op.residual = residual; op.out = d_in;
+            op.in0 = g1_out; op.blk[0] = last; op.residual = residual; op.out = d_in; op.in16 = g16;
             if ((rc = run_chain(op, s))) return rc;
         }
         return CGNN_OK;
     }
+    CGNN_CHECK_ARG(!g16, "the bfloat16 gradient stream belongs to the layered composition");
     r.ns = ns; r.rows = rows; r.n_layers = 3;
     r.blk[n_in] = {m.W[1], TC_H, 0, 0, 0};
     r.blk[n_in + 1] = {m.W[2], TC_H, 0, 0, 0, m.out_dim, 0};
@@ -351,7 +413,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
 }
 
 int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int precision, cudaStream_t s) {
-    const int ns = precision == CGNN_PREC_BF16X3 ? 3 : 1;
+    const int ns = precision == CGNN_PREC_BF16X3 || precision == CGNN_PREC_BF16X3_G16 ? 3 : 1;
     const MlpDev& m = a.mlp;
     int rc;
     if (a.mode == MODE_ROWS) {
@@ -385,9 +447,10 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             ChainOp r{};
             r.in0 = in; r.in0_cols = narrow_tma ? m.in_dim : 0; r.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim}; r.bias[0] = m.b[0];
             // dx = G1 W1 (in_dim == 128) comes out of the dgrad chain's last layer
+            const int g16 = grad16(precision, m, rows);
             if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, dU, nullptr, 1, 0, {m.W[0], m.in_dim, 0, 0, 1, m.in_dim, 0},
-                                     nullptr, a.dx ? a.dx + r0 * TC_H : nullptr, G1, nullptr, acc, s))) return rc;
-            if ((rc = run_wgrad(ns, G1, in, rows, g->W[0], m.in_dim, 0, g->b[0], acc, sc.wg, s, 0, m.in_dim, narrow_tma ? m.in_dim : 0))) return rc;
+                                     nullptr, a.dx ? a.dx + r0 * TC_H : nullptr, G1, nullptr, acc, s, g16))) return rc;
+            if ((rc = run_wgrad(ns, G1, in, rows, g->W[0], m.in_dim, 0, g->b[0], acc, sc.wg, s, 0, m.in_dim, narrow_tma ? m.in_dim : 0, g16))) return rc;
         }
         return CGNN_OK;
     }
@@ -438,9 +501,19 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         uint32_t* gate1 = cv.take<uint32_t>(chunk * 4); uint32_t* gate2 = cv.take<uint32_t>(chunk * 4);
         float* Ps = cv.take<float>(nn * TC_H); float* Pr = cv.take<float>(n * TC_H);
         float* dPs = cv.take<float>(nn * TC_H); float* dPr = cv.take<float>(n * TC_H);
+        const int n_chunks = (int)((E + chunk - 1) / chunk);
+        int2* ent = cv.take<int2>(scatter_entries(E, nn, chunk));
+        int32_t* ecnt = cv.take<int32_t>(n_chunks + 1); int32_t* eoff = cv.take<int32_t>(n_chunks + 1);
         if ((rc = project_nodes(ns, sc, m, a.h, n, nn, Ps, Pr, s))) return rc;
         // per-node sums of G1 by sender: accumulated chunk by chunk over the sender-sorted transpose (no E-sized buffer)
         CGNN_CUDA(cudaMemsetAsync(dPs, 0, (size_t)nn * TC_H * 4, s));
+        CGNN_CUDA(cudaMemsetAsync(ecnt, 0, (size_t)(n_chunks + 1) * 4, s));
+        sender_chunks_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, ecnt, nullptr, nullptr);
+        CGNN_LAUNCH_CHECK();
+        sender_chunks_offsets_kernel<<<1, 32, 0, s>>>(ecnt, eoff, n_chunks);
+        CGNN_LAUNCH_CHECK();
+        sender_chunks_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, ecnt, eoff, ent);
+        CGNN_LAUNCH_CHECK();
         for (int64_t r0 = 0, c = 0; r0 < E; r0 += chunk, ++c) {
             const int64_t rows = E - r0 < chunk ? E - r0 : chunk;       // chunk is a multiple of 256 and of k unless it is the whole graph
             const float* e_in = a.e_in + r0 * TC_H;
@@ -451,12 +524,17 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             ChainOp r{};
             r.in0 = e_in; r.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 0};
             r.k = a.k; r.k_valid = a.k_valid; r.senders = a.senders + r0; r.Ps = Ps; r.ps_rows = nn; r.Pr = Pr + (r0 / k) * TC_H;
+            const int g16 = grad16(precision, m, rows);
             if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, de_next, a.dagg + (r0 / k) * TC_H, a.k, a.k_valid,
-                                     {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}, de_next, a.de + r0 * TC_H, G1, dPr + (r0 / k) * TC_H, acc, s))) return rc;
+                                     {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}, de_next, a.de + r0 * TC_H, G1, dPr + (r0 / k) * TC_H, acc, s, g16))) return rc;
             // dW1e = G1^T e, db1
-            if ((rc = run_wgrad(ns, G1, e_in, rows, g->W[0], 3 * TC_H, 2 * TC_H, g->b[0], acc, sc.wg, s))) return rc;
-            scatter_chunk_kernel<<<(unsigned)((nn * (TC_H / 4) + 255) / 256), 256, 0, s>>>(
-                reinterpret_cast<const float4*>(G1), (int)r0, (int)(r0 + rows), a.t_rowptr, a.t_perm, nn, reinterpret_cast<float4*>(dPs));
+            if ((rc = run_wgrad(ns, G1, e_in, rows, g->W[0], 3 * TC_H, 2 * TC_H, g->b[0], acc, sc.wg, s, 0, 0, 0, g16))) return rc;
+            // (grid: enough warps to cover the memory latency; every warp strides over the chunk's entries)
+            const unsigned sgrid = (unsigned)(num_sms() * 8);
+            if (g16) scatter_chunk_kernel<true><<<sgrid, SCATTER_WARPS * 32, 0, s>>>(
+                         G1, (int)r0, (int)(r0 + rows), a.t_rowptr, a.t_perm, ent, eoff + c, reinterpret_cast<float4*>(dPs));
+            else scatter_chunk_kernel<false><<<sgrid, SCATTER_WARPS * 32, 0, s>>>(
+                     G1, (int)r0, (int)(r0 + rows), a.t_rowptr, a.t_perm, ent, eoff + c, reinterpret_cast<float4*>(dPs));
             CGNN_LAUNCH_CHECK();
         }
         // (the per-receiver sums dPr came out of the chunks' G1 chains)

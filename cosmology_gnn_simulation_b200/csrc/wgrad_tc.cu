@@ -35,7 +35,9 @@ constexpr int ONES_BYTES = 16 * TR * 2;
 constexpr int PW = 132;                   // floats per partial row: 128 dW columns + db + pad
 constexpr float LN_EPS = 1e-5f;
 
-static_assert(WG_RING % WG_SETS == 0 && (2 * NCW) % WG_SETS == 0, "ring slots and a tile's chunks must keep the set of a chunk");
+// (a ring slot's set is slot % WG_SETS because WG_RING is a multiple of WG_SETS -- whatever the number of chunks per tile: 8, or 6
+//  with a bfloat16 X stream)
+static_assert(WG_RING % WG_SETS == 0, "a ring slot must keep its converter set");
 struct WgSmem {
     static constexpr int ring = 0;
     static constexpr int bars = ring + WG_RING * CW_BYTES;
@@ -52,7 +54,9 @@ struct WgBars {
 };
 
 // MN-major image: element (mn, k) at (mn/8)*MN_STRIDE + (k/8)*128 + (k%8)*16 + (mn%8)*2
-template <int NS>
+// X16: X is a bfloat16 [rows][128] stream (the 2-byte gradient stream): two 64-column chunks per tile whose 16-byte pieces ARE the
+// rows of the image's 8 x 8 core matrices -- no split, no low image, two MMAs per K step instead of three.
+template <int NS, bool X16>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_a,
                 int64_t n_tiles, float* __restrict__ partials) {
@@ -89,13 +93,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             uint32_t seq = 0;
             for (int64_t it = 0; it < n_it; ++it) {
                 const int64_t row0 = (blockIdx.x + it * gridDim.x) * TR;
-                for (int op = 0; op < 2; ++op)
-                    for (int q = 0; q < NCW; ++q, ++seq) {
+                for (int op = 0; op < 2; ++op) {
+                    const int nq = X16 && op == 0 ? NCW / 2 : NCW, qcols = X16 && op == 0 ? 2 * CW : CW;
+                    for (int q = 0; q < nq; ++q, ++seq) {
                         const uint32_t buf = seq % WG_RING, use = seq / WG_RING;
                         mbar_wait_or_trap(&bars->in_empty[buf], (use & 1) ^ 1, 200 + buf);
                         mbar_expect_tx(&bars->in_full[buf], CW_BYTES);
-                        tma_load_2d(smem + WgSmem::ring + buf * CW_BYTES, op == 0 ? &tm_x : &tm_a, q * CW, (int)row0, &bars->in_full[buf]);
+                        tma_load_2d(smem + WgSmem::ring + buf * CW_BYTES, op == 0 ? &tm_x : &tm_a, q * qcols, (int)row0, &bars->in_full[buf]);
                     }
+                }
             }
         }
     } else if (warp == WG_MMA) {
@@ -118,9 +124,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     umma_bf16<1>(tmem + 128, dxh, umma_desc(ones + ks * 256, 128, MN_STRIDE), idesc1, acc);
                     if (NS == 3) {
                         const uint64_t dxl = umma_desc(x_lo + ks * 256, 128, MN_STRIDE);
-                        umma_bf16<1>(tmem, dxl, umma_desc(a_hi + ks * 256, 128, MN_STRIDE), idesc, 1u);
+                        if (!X16) umma_bf16<1>(tmem, dxl, umma_desc(a_hi + ks * 256, 128, MN_STRIDE), idesc, 1u);
                         umma_bf16<1>(tmem, dxh, umma_desc(a_lo + ks * 256, 128, MN_STRIDE), idesc, 1u);
-                        umma_bf16<1>(tmem + 128, dxl, umma_desc(ones + ks * 256, 128, MN_STRIDE), idesc1, 1u);
+                        if (!X16) umma_bf16<1>(tmem + 128, dxl, umma_desc(ones + ks * 256, 128, MN_STRIDE), idesc1, 1u);
                     }
                 }
                 umma_commit<1>(&bars->ops_empty);
@@ -136,11 +142,30 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if (it > 0) mbar_wait_or_trap(&bars->ops_empty, (uint32_t)((it - 1) & 1), 220);      // previous tile's MMAs read the images
             for (int op = 0; op < 2; ++op) {
                 uint8_t* img = op == 0 ? sX : sA;
-                for (int q = 0; q < NCW; ++q, ++seq) {
+                const int nq = X16 && op == 0 ? NCW / 2 : NCW;
+                for (int q = 0; q < nq; ++q, ++seq) {
                     if ((int)(seq & (WG_SETS - 1)) != cset) continue;
                     const uint32_t buf = seq % WG_RING, use = seq / WG_RING;
                     mbar_wait_or_trap(&bars->in_full[buf], use & 1, 230 + buf);
                     const uint8_t* src = smem + WgSmem::ring + buf * CW_BYTES;
+                    if (X16 && op == 0) {
+                        // columns 64q .. 64q+63 of row r: piece j = columns 64q + 8j .. + 7 = the k = r row of mn group 8q + j
+                        uint32_t w[32];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(src + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)));
+                            w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+                        }
+                        // the raw words go to the image first (a real reader of every loaded register), then the slot goes back --
+                        // through an arrival that depends on them (fold_zero, tc_common.cuh)
+                        uint8_t* dst = img + (8 * q) * MN_STRIDE + (r >> 3) * 128 + (r & 7) * 16;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dst + j * MN_STRIDE) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                        const uint32_t fz = fold_zero<32>(w, (uint32_t)((unsigned long long)n_tiles >> 62));
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_local(&bars->in_empty[buf] + fz);
+                        continue;
+                    }
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -289,7 +314,7 @@ constexpr int LNB_BLOCKS = 592;       // 4 per SM
 int64_t wgrad_workspace_bytes() { return align_up((int64_t)148 * 128 * PW * 4, 256); }
 
 int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, int ld, int col0, float* db,
-              int accumulate, void* ws, cudaStream_t stream, int nrows, int ncols, int a_cols) {
+              int accumulate, void* ws, cudaStream_t stream, int nrows, int ncols, int a_cols, int x16) {
     CGNN_CHECK_ARG(X && A && dW && ws && rows >= 1, "tensor-core wgrad: bad arguments");
     const int nsi = ns == 3 ? 2 : 1;
     const int64_t n_tiles = (rows + TR - 1) / TR;
@@ -297,19 +322,16 @@ int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, i
     if (n_tiles < grid) grid = (int)n_tiles;
     CUtensorMap mx, ma;
     int rc;
-    if ((rc = make_row_map32_rows(&mx, X, rows, TR))) return rc;
+    if ((rc = x16 ? make_row_map_bf16(&mx, X, rows, TR) : make_row_map32_rows(&mx, X, rows, TR))) return rc;
     if ((rc = make_row_map32_rows(&ma, A, rows, TR, a_cols > 0 ? a_cols : TC_H))) return rc;
     const size_t smem = (size_t)WgSmem::ops + (size_t)2 * nsi * OP_BYTES;
     float* partials = static_cast<float*>(ws);
-    if (ns == 3) {
-        static bool configured = false;
-        if (!configured) { CGNN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
-        tc_wgrad_kernel<3><<<grid, WG_THREADS, smem, stream>>>(mx, ma, n_tiles, partials);
-    } else {
-        static bool configured = false;
-        if (!configured) { CGNN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
-        tc_wgrad_kernel<1><<<grid, WG_THREADS, smem, stream>>>(mx, ma, n_tiles, partials);
-    }
+    void (*kern)(CUtensorMap, CUtensorMap, int64_t, float*) =
+        ns == 3 ? (x16 ? tc_wgrad_kernel<3, true> : tc_wgrad_kernel<3, false>) : (x16 ? tc_wgrad_kernel<1, true> : tc_wgrad_kernel<1, false>);
+    static bool configured[4] = {false, false, false, false};
+    const int slot = (ns == 3 ? 2 : 0) + (x16 ? 1 : 0);
+    if (!configured[slot]) { CGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[slot] = true; }
+    kern<<<grid, WG_THREADS, smem, stream>>>(mx, ma, n_tiles, partials);
     CGNN_LAUNCH_CHECK();
     wgrad_reduce_kernel<<<(128 * 129 + 63) / 64, 256, 0, stream>>>(partials, grid, dW, ld, col0, db, accumulate,
                                                                      nrows > 0 ? nrows : 128, ncols > 0 ? ncols : 128);

@@ -95,9 +95,13 @@ class _Plan:
     """Static description of one forward call, shared by forward and backward."""
 
     def __init__(self, n_steps, message, precision, k, enc_node, enc_edge, proc_node, proc_edge, dec_acc,
-                 dec_temp, groups, edge_buffers, halo=None, k_valid=0):
+                 dec_temp, groups, edge_buffers, halo=None, k_valid=0, grad_stream="fp32"):
         self.halo = halo                      # slab.HaloPlan of a sharded box, or None
         self.n_steps, self.message, self.precision, self.k = n_steps, message, precision, k
+        # precision of the backward over the EDGE streams (processor edge MLPs, edge encoder): "bf16x3g" keeps the three gradient
+        # intermediates of the long-stream composition as bfloat16 (csrc/tc_model.cu grad16; error study tests/study_grad_stream.py)
+        self.grad_stream = grad_stream
+        self.edge_bwd_precision = "bf16x3g" if precision == "bf16x3" and grad_stream == "bf16" else precision
         self.k_valid = k_valid                # real in-degree when k is the padded power of two (0: k itself)
         self.enc_node, self.enc_edge = enc_node, enc_edge
         self.proc_node, self.proc_edge = proc_node, proc_edge
@@ -122,7 +126,7 @@ class _Plan:
         groups_by_id = {id(mp): first for mp, first in self.groups}
         q = _Plan(self.n_steps, self.message, self.precision, self.k, p(self.enc_node, 0), p(self.enc_edge, 0),
                   [p(m, 2) for m in self.proc_node], [p(m, 3) for m in self.proc_edge], p(self.dec_acc, 1), p(self.dec_temp, 1),
-                  None, self.edge_buffers, self.halo, self.k_valid)
+                  None, self.edge_buffers, self.halo, self.k_valid, self.grad_stream)
         q.groups = [(pad[i], first) for i, first in groups_by_id.items()]
         q.grad_enabled = self.grad_enabled
         return q
@@ -347,7 +351,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
                 de_new = de if de is not None else ctx.lease.bufs[-1]
                 gs = torch.empty_like(e_t) if fp32 else None
                 put(p.proc_edge[t], ops.mp_edge_bwd(p.proc_edge[t], hs[t], e_t, senders, rowptr, perm, k, de, dagg,
-                                                    de_new, dh_new, gs, prec, p.k_valid))
+                                                    de_new, dh_new, gs, p.edge_bwd_precision, p.k_valid))
                 return dh_new, de_new
             ops.scatter_to_senders(dagg, True, rowptr, perm, k, dh_new)
             return dh_new, None
@@ -374,7 +378,7 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         put(p.enc_node, g_en)
         dea = None
         if edge_mode:
-            g_ee, dea = ops.mlp_rows_bwd(p.enc_edge, ctx.edge_attr, de, need_dea, prec)
+            g_ee, dea = ops.mlp_rows_bwd(p.enc_edge, ctx.edge_attr, de, need_dea, p.edge_bwd_precision)
             put(p.enc_edge, g_ee)
         if ctx.lease is not None:
             ctx.lease.release()
@@ -390,19 +394,27 @@ class EncodeProcessDecode(nn.Module):
       message        "sender" (reference-actual, default) | "edge" (intended Interaction Network); env CGNN_MESSAGE
       precision      "fp32" (FP32 SIMT, <= 1e-5 parity, default) | "bf16x3" | "bf16" (tcgen05 tensor cores); env CGNN_PRECISION
       edge_buffers   message="edge" training: copies of the edge stream kept for the backward (0 = from the free memory)
+      grad_stream    precision="bf16x3" only: "bf16" (default) | "fp32"; env CGNN_GRAD_STREAM.  "bf16": the backward of the edge MLPs
+                     over long streams (more rows than one wave of tiles) keeps its gradient intermediates dY / G2 / G1 as bfloat16
+                     in HBM.  Forward values and ReLU gates are unchanged; the rounding averages out in the weight gradients
+                     (tests/study_grad_stream.py: 1.3e-4 at 4 096 particles, shrinking with the square root of the size).
     """
 
     def __init__(self, latent_size: int, mlp_hidden_size: int, mlp_num_hidden_layers: int,
                  num_message_passing_steps: int, output_size: int, *, num_neighbors: Optional[int] = None,
-                 message: Optional[str] = None, precision: Optional[str] = None, edge_buffers: int = 0):
+                 message: Optional[str] = None, precision: Optional[str] = None, edge_buffers: int = 0,
+                 grad_stream: Optional[str] = None):
         super().__init__()
         # the reference's scripts construct the model with its five arguments only: the environment chooses for them
         message = message if message is not None else os.environ.get("CGNN_MESSAGE", "sender")
         precision = precision if precision is not None else os.environ.get("CGNN_PRECISION", "fp32")
         if message not in ("sender", "edge"):
             raise ValueError("message must be 'sender' or 'edge'")
-        if precision not in ops.PREC:
-            raise ValueError(f"precision must be one of {sorted(ops.PREC)}")
+        if precision not in ("fp32", "bf16x3", "bf16"):
+            raise ValueError("precision must be one of 'fp32', 'bf16x3', 'bf16'")
+        grad_stream = grad_stream if grad_stream is not None else os.environ.get("CGNN_GRAD_STREAM", "bf16")
+        if grad_stream not in ("bf16", "fp32"):
+            raise ValueError("grad_stream must be 'bf16' or 'fp32'")
         self._latent_size = latent_size
         self._mlp_hidden_size = mlp_hidden_size
         self._mlp_num_hidden_layers = mlp_num_hidden_layers
@@ -411,6 +423,7 @@ class EncodeProcessDecode(nn.Module):
         self.num_neighbors = num_neighbors
         self.message = message
         self.precision = precision
+        self.grad_stream = grad_stream
         self.edge_buffers = edge_buffers        # message='edge' training: copies of the edge stream to keep (0: from the free memory)
 
         def mlp_ln():
@@ -546,7 +559,7 @@ class EncodeProcessDecode(nn.Module):
             edge_attr = padded.view(n * k, -1)
         plan = _Plan(self._num_message_passing_steps, self.message, self.precision, k, enc_node, enc_edge,
                      proc_node, proc_edge, dec_acc, dec_temp, groups, self.edge_buffers,
-                     halo=halo, k_valid=k_valid)
+                     halo=halo, k_valid=k_valid, grad_stream=getattr(self, "grad_stream", "fp32"))
         acc, temp = _EncodeProcessDecodeFn.apply(plan, senders, transpose, x, edge_attr, *flat)
         if order is not None:
             acc, temp = acc[inv], temp[inv]

@@ -439,3 +439,68 @@ def test_whole_model_training_step_is_reproducible(message):
             ref = cur
         else:
             assert all(torch.equal(a, b) for a, b in zip(cur, ref)), f"repetition {rep} differs"
+
+
+# ---- the 2-byte gradient stream (CGNN_PREC_BF16X3_G16, "bf16x3g") -----------------------------------------------------------
+# On long streams the backward keeps dY / G2 / G1 as bfloat16.  Against the FP32-stream backward of the same precision every
+# element of those intermediates is off by <= 2^-9 relative, with random sign.  On THIS test's data (independent random inputs
+# and upstream gradients) a weight gradient is itself a sum of zero-mean terms, so rounding noise and signal both grow like
+# sqrt(rows) and the distance stays near 2^-9 / sqrt(3) ~ 1e-3 whatever the size: bar 4e-3.  In the model the terms of a weight
+# gradient are coherent and the noise averages out (tests/study_grad_stream.py; tests/test_gpu_benched.py holds 1e-3 there).
+G16_TOL = 4e-3
+
+
+def test_bf16_gradient_stream_edge_backward():
+    from cosmology_gnn_simulation_b200 import ops
+    from cosmology_gnn_simulation_b200.ops import MlpParams
+    d = _dev()
+    gen = torch.Generator(device=d).manual_seed(3)
+    n, k = 6000, 16                                     # 96 000 rows: the layered composition (more than one wave of tiles)
+    ws = [torch.randn(L, i, device=d, generator=gen) / i ** 0.5 for i in (3 * L, L, L)]
+    bs = [torch.randn(L, device=d, generator=gen) * 0.1 for _ in range(3)]
+    p = MlpParams(ws, bs, 1.0 + 0.1 * torch.randn(L, device=d, generator=gen), 0.1 * torch.randn(L, device=d, generator=gen))
+    h = torch.randn(n, L, device=d, generator=gen)
+    e = torch.randn(n * k, L, device=d, generator=gen)
+    senders = torch.randint(0, n, (n * k,), device=d, generator=gen, dtype=torch.int32)
+    rowptr, perm = ops.csr_transpose(senders, n)
+    de0 = torch.randn(n * k, L, device=d, generator=gen)
+    dagg = torch.randn(n, L, device=d, generator=gen)
+    dh0 = torch.randn(n, L, device=d, generator=gen)
+
+    def run(precision):
+        de, dh = de0.clone(), dh0.clone()
+        grads = ops.mp_edge_bwd(p, h, e, senders, rowptr, perm, k, de, dagg, de, dh, None, precision)
+        return [de - de0, dh - dh0] + list(grads)
+
+    ref = run("bf16x3")
+    got = run("bf16x3g")
+    torch.cuda.synchronize()
+    names = ["de", "dh", "W1", "b1", "W2", "b2", "W3", "b3", "gamma", "beta"]
+    errs = {nm: rel_l2(a.cpu(), b.cpu()) for nm, a, b in zip(names, got, ref)}
+    print("bf16 gradient stream vs FP32 stream:", {nm: f"{v:.1e}" for nm, v in errs.items()})
+    assert all(v < G16_TOL for v in errs.values()), errs
+    assert errs["de"] > 1e-5, "the 2-byte stream did not run (results equal the FP32 stream's)"
+    assert errs["gamma"] < 1e-6 and errs["beta"] < 1e-6     # the LayerNorm sums are taken before anything is rounded
+    for rep in range(10):                                   # deterministic, and the race detector of the ring protocol
+        again = run("bf16x3g")
+        assert all(torch.equal(a, b) for a, b in zip(again, got)), f"repetition {rep} differs"
+
+
+def test_bf16_gradient_stream_rows_backward():
+    """The edge encoder's backward (graph_network.py:57: 4 features -> latent, LayerNorm) over a long stream."""
+    from cosmology_gnn_simulation_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    rows = 70000
+    p, ws, bs, gamma, beta = _rows_params(4, L, True, gen)
+    d = _dev()
+    x = torch.randn(rows, 4, generator=gen).to(d)
+    dout = torch.randn(rows, L, generator=gen).to(d)
+    ref, _ = ops.mlp_rows_bwd(p, x, dout, False, "bf16x3")
+    got, _ = ops.mlp_rows_bwd(p, x, dout, False, "bf16x3g")
+    torch.cuda.synchronize()
+    errs = [rel_l2(a.cpu(), b.cpu()) for a, b in zip(got, ref)]
+    print("bf16 gradient stream (rows) vs FP32 stream:", [f"{v:.1e}" for v in errs])
+    assert all(v < G16_TOL for v in errs), errs
+    assert max(errs[:6]) > 1e-6, "the 2-byte stream did not run"
+    again, _ = ops.mlp_rows_bwd(p, x, dout, False, "bf16x3g")
+    assert all(torch.equal(a, b) for a, b in zip(again, got))

@@ -16,6 +16,8 @@ ap.add_argument("--n", type=int, default=3000)
 ap.add_argument("--halo", type=int, default=600)
 ap.add_argument("--k", type=int, default=16)
 ap.add_argument("--reps", type=int, default=30)
+ap.add_argument("--precision", default="bf16x3")
+ap.add_argument("--no-de-next", action="store_true", help="the last processor step: no gradient on the edge output")
 a = ap.parse_args()
 L, d = 128, torch.device("cuda", 0)
 g = torch.Generator(device=d).manual_seed(0)
@@ -35,7 +37,7 @@ bad = 0
 for rep in range(a.reps):
     de = de_next0.clone()
     dh = dh0.clone()
-    grads = ops.mp_edge_bwd(p, h, e, senders, rowptr, perm, k, de, dagg, de, dh, None, "bf16x3")
+    grads = ops.mp_edge_bwd(p, h, e, senders, rowptr, perm, k, None if a.no_de_next else de, dagg, de, dh, None, a.precision)
     torch.cuda.synchronize()
     cur = [de, dh] + list(grads)
     if ref is None:
@@ -45,4 +47,4 @@ for rep in range(a.reps):
         if diff:
             bad += 1
             print(f"rep {rep}: tensors {diff} differ, max abs {[float((cur[i] - ref[i]).abs().max()) for i in diff]}")
-print(f"n={n} halo={a.halo} k={k}: {bad} of {a.reps - 1} repetitions differ from the first")
+print(f"n={n} halo={a.halo} k={k} {a.precision}{' no de_next' if a.no_de_next else ''}: {bad} of {a.reps - 1} repetitions differ from the first")
