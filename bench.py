@@ -422,7 +422,10 @@ def run_gpu(args):
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16 operands, f32 accumulate/storage)", "bf16": "bf16"}[precision],
+        "dtype": {"fp32": "f32", "bf16": "bf16",
+                  "bf16x3": "bf16x3 (split bf16 operands, f32 accumulate, f32 latents in HBM" +
+                            ("; gradient streams of the edge MLPs' backward bf16)" if os.environ.get("CGNN_GRAD_STREAM", "bf16") == "bf16"
+                             else ")")}[precision],
         "data": "synthetic",
         "config": workload_config(args.workload, message, precision, world, args.sharding, args.scaling),
         "clocks": clocks.summary(),

@@ -84,6 +84,8 @@ struct TcParams {
     int in16;                   // the chain input is a bfloat16 [n_rows][128] stream (the 2-byte gradient stream of the long-stream backward):
                                 // two 64-column ring slots per tile, written to the A operand as they are -- no low part, two MMA passes
     int out16;                  // `out` is a bfloat16 [n_rows][128] stream (round to nearest even)
+    int t116;                   // C_T1: the ring-fed epilogue stream (dU rows / residual: the gradient stream de) is bfloat16 -- two
+                                // 64-column slots per tile instead of four 32-column ones
     ChainBlock blk[MAX_BLOCKS]; // weight blocks in FP32 (torch layout): every CTA builds its BF16 images in shared memory itself
     const float* vec_src[5];    // bias of layer 1, 2, 3, gamma, beta (nullable -> zeros / ones for gamma)
     int vec_len[5];             // valid entries (zero padded to 128)
@@ -355,7 +357,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                 }
                 for (int ip = 0; ip < p.n_in + (T1 ? 1 : 0); ++ip) {    // T1: the epilogue stream follows the MMA input(s), map 1
                     // a bfloat16 input has 64 columns per slot (the same 128-byte rows): two slots per tile
-                    const bool in16 = IO16 && p.in16 && ip < p.n_in;
+                    const bool in16 = IO16 && (ip < p.n_in ? p.in16 : p.t116);
                     const int nq = in16 ? NCW / 2 : NCW, qcols = in16 ? 2 * CW : CW;
                     for (int q = 0; q < nq; ++q) {
                         if (lane == 0) {
@@ -449,7 +451,7 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
 
         // ring slot of this group's next tile's first chunk: advanced by the chunks of two tiles (its own and the other group's) per
         // iteration, wrapped by subtraction -- no division in the loops
-        const uint32_t uring = (uint32_t)NRING, tile_chunks = (uint32_t)((IO16 && p.in16 ? NCW / 2 : NCW) * p.n_in + NCW * ((T1 ? 1 : 0) + (G4 ? 1 : 0)));
+        const uint32_t uring = (uint32_t)NRING, tile_chunks = (uint32_t)((IO16 && p.in16 ? NCW / 2 : NCW) * p.n_in + (T1 ? (IO16 && p.t116 ? NCW / 2 : NCW) : 0) + (G4 ? NCW : 0));
         uint32_t ring0 = (uint32_t)g * tile_chunks % uring;
         // sender index of the first tile's row; the next tile's is fetched one tile ahead so its latency never shows
         int32_t snd_next = 0;
@@ -647,6 +649,30 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
             // MMA input; every thread reads its own row of a slot (two 16-column halves) and the slot goes back after the second
             uint32_t tbuf = buf, t1fold = 0u;
             auto t1_load16 = [&](int cc, float* dst) {
+                if (IO16 && p.t116) {
+                    // bfloat16 stream: a slot holds 64 columns of the row (128 bytes); 16 columns are two of its 16-byte pieces
+                    if ((cc & 63) == 0) {
+                        mbar_wait_or_trap(&bars->in_full[g][tbuf], (in_par >> tbuf) & 1u, 190);
+                        in_par ^= 1u << tbuf;
+                    }
+                    const uint8_t* src = sRing + tbuf * CW_BYTES;
+                    const uint4 u0 = *reinterpret_cast<const uint4*>(src + swz128(r, (cc & 63) >> 3));
+                    const uint4 u1 = *reinterpret_cast<const uint4*>(src + swz128(r, ((cc & 63) >> 3) + 1));
+                    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        dst[2 * j] = __uint_as_float(w[j] << 16);
+                        dst[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+                    }
+                    t1fold ^= fold_zero<8>(w, zero_rt);
+                    if ((cc & 63) == 48) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_local(&bars->in_empty[tbuf] + t1fold);
+                        t1fold = 0u;
+                        tbuf = tbuf + 1 == uring ? 0 : tbuf + 1;
+                    }
+                    return;
+                }
                 if ((cc & 31) == 0) {
                     mbar_wait_or_trap(&bars->in_full[g][tbuf], (in_par >> tbuf) & 1u, 190);
                     in_par ^= 1u << tbuf;
@@ -887,7 +913,10 @@ tc_chain_fwd(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__
                             t1_load16(cc, t1v);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) t1v[j] += v[j];
-                            if (vout) st16(outp + cc, t1v);
+                            if (vout) {
+                                if (IO16 && p.out16) st16h(outh + cc, t1v);
+                                else st16(outp + cc, t1v);
+                            }
                         } else if (!lnb && pb) {
                             // residual: the sum goes out from the stream's own registers, v stays free for the per-receiver sum
 #pragma unroll
@@ -999,8 +1028,8 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     p.in16 = op.in16 != 0; p.out16 = op.out16 != 0;
     CGNN_CHECK_ARG(!op.in16 || (op.n_layers == 1 && !op.in1 && !gather && op.in0_cols == 0 && op.residual != op.in0),
                    "tensor-core chain: a bfloat16 input stream feeds one-layer chains with a single input");
-    CGNN_CHECK_ARG(!op.out16 || (op.out && !op.residual && op.n_layers == 1 && !gather),
-                   "tensor-core chain: a bfloat16 output stream belongs to one-layer chains without gather or residual");
+    CGNN_CHECK_ARG(!op.out16 || (op.out && op.n_layers == 1 && !gather),
+                   "tensor-core chain: a bfloat16 output stream belongs to one-layer chains without gather");
     for (int b = 0; b < n_blocks; ++b) p.blk[b] = op.blk[b];
     if (op.n_layers == 1) {
         p.vec_src[0] = op.bias[0];
@@ -1035,13 +1064,20 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
     // one-layer chains: the dU rows / the residual ride the TMA ring (CGNN_NO_T1=1: thread = row global loads, as measured before)
     // The residual chains take it by default.  The LayerNorm-backward chain does NOT: with its dU rows on the ring the edge backward
     // stopped being reproducible (tools/stress_edge_bwd.py: 17 of 39 repetitions differed, 0 of 39 without) -- a race not yet
-    // found; CGNN_T1_LNB=1 switches it on for that investigation.
+    // found.  FOUND (round 2, second session): the hand-back of a ring slot whose loaded registers are passed on raw did not wait for
+    // the loads (fold_zero, tc_common.cuh); with the arrival depending on them 0 of 39 / 29 / 39 repetitions differ, and the
+    // LayerNorm-backward chain takes its dU rows through the ring by default again (CGNN_T1_LNB=0: thread = row loads).
     static const bool t1_off = getenv("CGNN_NO_T1") != nullptr && atoi(getenv("CGNN_NO_T1")) != 0;
-    static const bool t1_lnb = getenv("CGNN_T1_LNB") != nullptr && atoi(getenv("CGNN_T1_LNB")) != 0;
+    static const bool t1_lnb = getenv("CGNN_T1_LNB") == nullptr || atoi(getenv("CGNN_T1_LNB")) != 0;
     const float* t1_src = t1_off || op.n_layers != 1 || op.in1 || gather ? nullptr
                           : op.ln_bwd ? (t1_lnb ? op.du_rows : nullptr)
                           : (op.residual != op.in0 && !op.mask_src ? op.residual : nullptr);
     const bool t1 = t1_src != nullptr;
+    // a bfloat16 gradient stream (dU rows / residual) only travels through the ring
+    CGNN_CHECK_ARG(!(op.du16 && op.du_rows) || (op.ln_bwd && t1), "tensor-core chain: bfloat16 dU rows need the ring-fed LayerNorm-backward chain");
+    CGNN_CHECK_ARG(!(op.res16 && op.residual) || (!op.ln_bwd && t1), "tensor-core chain: a bfloat16 residual needs the ring-fed one-layer chain");
+    CGNN_CHECK_ARG(!op.out16 || !op.residual || t1, "tensor-core chain: a bfloat16 output with a residual needs the ring-fed one-layer chain");
+    p.t116 = t1 && (op.ln_bwd ? op.du16 : op.res16);
     // gather chains whose ring and second tensor map are free can take the P_s rows by tile::gather4 (CGNN_GATHER4=1).  Measured
     // slower than the thread = row loads (128 four-row gathers per tile: 25.2 k vs 20.4 k cycles per tile of the A1 chain), so opt-in.
     static const bool g4_allowed = getenv("CGNN_GATHER4") != nullptr && atoi(getenv("CGNN_GATHER4")) != 0;
@@ -1063,7 +1099,9 @@ int run_chain_t(const ChainOp& op, cudaStream_t stream) {
         // (the node table's row count is not part of the op; the gather only ever names valid sender rows, so the map's extent is
         //  set to the int32 index range the senders can express)
         if ((rc = make_gather_map32(&m1, op.Ps, op.ps_rows))) return rc;
-    } else if ((rc = make_row_map32(&m1, t1 ? t1_src : (op.in1 ? op.in1 : op.in0), op.rows))) return rc;
+    } else if (p.t116) {
+        if ((rc = make_row_map_bf16(&m1, t1_src, op.rows, 128))) return rc;
+    } else if ((rc = make_row_map32(&m1, t1 ? t1_src : (op.in1 ? op.in1 : op.in0), op.rows))) return rc;       // (unused map when there is no second stream)
     void (*kern)(CUtensorMap, CUtensorMap, TcParams) = nullptr;
     int slot = -1;
 #define CGNN_CHAIN_CFG(i, c) else if (cfg == (c)) { kern = tc_chain_fwd<NS, (c)>; slot = (i); }

@@ -102,6 +102,9 @@ struct ChainOp {
     // the 2-byte gradient stream of the long-stream backward: in0 / out are bfloat16 [rows][128] arrays behind the float pointers
     // (one-layer chains; in16: single input, no gather; out16: no residual)
     int in16; int out16;
+    // ... and the gradient stream de that is carried from processor step to processor step: du_rows (LayerNorm backward) / residual
+    // are bfloat16 [rows][128]; both only through the ring-fed one-layer chains (C_T1)
+    int du16; int res16;
 };
 int run_chain(const ChainOp& op, cudaStream_t stream);
 

@@ -312,14 +312,19 @@ static int bwd_mode(int64_t rows) {
     return pair_tiles <= 2 * clusters ? 1 : 0;
 }
 
-// The 2-byte gradient stream (CGNN_PREC_BF16X3_G16): on long row streams of an MLP with LayerNorm the three gradient
-// intermediates dY, G2, G1 are bfloat16 in HBM -- 10 of the 21 row-stream passes of a processor step become half passes.
-// Forward values (the activations that decide the ReLU gates) are untouched; what the rounding does to the parameter gradients
-// is measured on the oracle by tests/study_grad_stream.py (2.6e-4 at 1 024 particles, 1.3e-4 at 4 096: it averages out over the
-// rows a weight gradient sums).  Short streams (the fused chains) keep FP32 intermediates.
-static bool grad16(int precision, const MlpDev& m, int64_t rows) {
-    return precision == CGNN_PREC_BF16X3_G16 && m.gamma != nullptr && bwd_mode(rows) == 0;
+// The 2-byte gradient stream (CGNN_PREC_BF16X3_G16), for the backward of an MLP with LayerNorm over a long row stream: the three
+// gradient intermediates dY, G2, G1 AND the gradient stream the caller carries from step to step (de_next / de of
+// cgnn_mp_edge_bwd, dout of cgnn_mlp_rows_bwd) are bfloat16 in HBM -- 13 of the 21 row-stream passes of a processor step become
+// half passes.  Forward values (the activations that decide the ReLU gates) are untouched; what the rounding does to the parameter
+// gradients is measured on the oracle by tests/study_grad_stream.py (2.9e-4 at 1 024 particles, halving with every fourfold size:
+// it averages out over the rows a weight gradient sums).  The call runs the layered composition whatever its size (the caller
+// picks this precision for long streams only).
+static bool grad16(int precision, const MlpDev& m) { return precision == CGNN_PREC_BF16X3_G16 && m.gamma != nullptr; }
+// row r0 of a [rows][128] stream of 4- or 2-byte elements
+static const float* row_at(const float* base, int64_t r0, int half) {
+    return base == nullptr ? nullptr : half ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(base) + r0 * TC_H) : base + r0 * TC_H;
 }
+static float* row_at(float* base, int64_t r0, int half) { return const_cast<float*>(row_at(static_cast<const float*>(base), r0, half)); }
 
 // Backward of one 3-layer MLP (+ LayerNorm) over a row range as TWO fused chains plus the weight gradients:
 //   R  recompute:  in -> A1 -> A2 -> Y, LayerNorm backward of (Y, dU) in the final epilogue -> dY (T);
@@ -334,12 +339,13 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
                           float* A1, float* A2, float* T, float* G2, uint32_t* gate1, uint32_t* gate2,
                           const float* du_rows, const float* du_recv, int k, int k_valid,
                           ChainBlock last, const float* residual, float* d_in, float* g1_out, float* g1_agg,
-                          int accumulate, cudaStream_t s, int g16 = 0) {
+                          int accumulate, cudaStream_t s, int g16 = 0, int de16 = 0) {
     int rc;
     const int n_in = r.in1 ? 2 : 1;
     // g16 (see grad16()): T, G2 and g1_out hold bfloat16 rows -- written rounded to nearest even by the chain that produces them,
-    // read as they are by the next dgrad chain, the weight gradient and the caller (sender scatter, dW1)
-    if (bwd_mode(rows) == 0) {
+    // read as they are by the next dgrad chain, the weight gradient and the caller (sender scatter, dW1); du_rows is bfloat16 too,
+    // and with de16 so are residual and d_in (the edge phase's gradient stream)
+    if (g16 || bwd_mode(rows) == 0) {
         // A1 = relu(layer 1), A2 = relu(A1 W2^T + b2)
         r.ns = ns; r.rows = rows; r.n_layers = 1;
         r.relu_out = 1; r.out = A1; r.bits_out = gate1;          // the ReLU gates go out as 16 B per row for the dgrad chains
@@ -354,7 +360,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
             op.in0 = A2; op.blk[0] = {m.W[2], TC_H, 0, 0, 0}; op.bias[0] = m.b[2];
             op.gamma = m.gamma; op.beta = m.beta; op.ln_n = m.ln_dim; op.ln_bwd = 1; op.k = k; op.k_valid = k_valid;
             op.du_rows = du_rows; op.du_recv = du_recv; op.dgamma = g->ln_gamma; op.dbeta = g->ln_beta; op.accumulate = accumulate; op.ln_ws = sc.lnb;
-            op.out = T; op.out16 = g16;
+            op.out = T; op.out16 = g16; op.du16 = g16;
             if ((rc = run_chain(op, s))) return rc;
         }
         if ((rc = run_wgrad(ns, T, A2, rows, g->W[2], TC_H, 0, g->b[2], accumulate, sc.wg, s, m.out_dim, 0, 0, g16))) return rc;
@@ -375,6 +381,7 @@ static int fused_backward(int ns, const Scratch& sc, const MlpDev& m, const cgnn
         if (d_in != nullptr) {   // d_in = G1 last^T (+ residual)
             ChainOp op = base_op(ns, sc, rows);
             op.in0 = g1_out; op.blk[0] = last; op.residual = residual; op.out = d_in; op.in16 = g16;
+            op.res16 = de16; op.out16 = de16;
             if ((rc = run_chain(op, s))) return rc;
         }
         return CGNN_OK;
@@ -439,7 +446,8 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
                 if ((rc = pad_rows(in, m.in_dim, rows, Xp, s))) return rc;
                 in = Xp;
             }
-            const float* dU = a.dout + r0 * m.out_dim;
+            const int g16 = grad16(precision, m);            // (LayerNorm MLPs have out_dim == 128)
+            const float* dU = g16 ? row_at(a.dout, r0, 1) : a.dout + r0 * m.out_dim;
             if (m.gamma == nullptr) {                       // no LayerNorm: dY = dout, zero padded
                 if (m.out_dim < TC_H) { if ((rc = pad_rows(dU, m.out_dim, rows, T, s))) return rc; }
                 else CGNN_CUDA(cudaMemcpyAsync(T, dU, (size_t)rows * TC_H * 4, cudaMemcpyDeviceToDevice, s));
@@ -447,7 +455,6 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
             ChainOp r{};
             r.in0 = in; r.in0_cols = narrow_tma ? m.in_dim : 0; r.blk[0] = {m.W[0], m.in_dim, 0, 0, 0, 0, m.in_dim}; r.bias[0] = m.b[0];
             // dx = G1 W1 (in_dim == 128) comes out of the dgrad chain's last layer
-            const int g16 = grad16(precision, m, rows);
             if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, dU, nullptr, 1, 0, {m.W[0], m.in_dim, 0, 0, 1, m.in_dim, 0},
                                      nullptr, a.dx ? a.dx + r0 * TC_H : nullptr, G1, nullptr, acc, s, g16))) return rc;
             if ((rc = run_wgrad(ns, G1, in, rows, g->W[0], m.in_dim, 0, g->b[0], acc, sc.wg, s, 0, m.in_dim, narrow_tma ? m.in_dim : 0, g16))) return rc;
@@ -517,16 +524,16 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         for (int64_t r0 = 0, c = 0; r0 < E; r0 += chunk, ++c) {
             const int64_t rows = E - r0 < chunk ? E - r0 : chunk;       // chunk is a multiple of 256 and of k unless it is the whole graph
             const float* e_in = a.e_in + r0 * TC_H;
-            const float* de_next = a.de_next ? a.de_next + r0 * TC_H : nullptr;
+            const int g16 = grad16(precision, m);
+            const float* de_next = row_at(a.de_next, r0, g16);
             const int acc = c > 0;
             // recompute with e W1e^T + Ps[sender] + Pr[receiver] as layer 1; dU = de_next + dagg[receiver];
             // de = de_next + G1 W1e is the dgrad chain's last layer, the per-receiver sum of G1 is d P_r
             ChainOp r{};
             r.in0 = e_in; r.blk[0] = {m.W[0], 3 * TC_H, 0, 2 * TC_H, 0};
             r.k = a.k; r.k_valid = a.k_valid; r.senders = a.senders + r0; r.Ps = Ps; r.ps_rows = nn; r.Pr = Pr + (r0 / k) * TC_H;
-            const int g16 = grad16(precision, m, rows);
             if ((rc = fused_backward(ns, sc, m, g, rows, r, A1, A2, T, G2, gate1, gate2, de_next, a.dagg + (r0 / k) * TC_H, a.k, a.k_valid,
-                                     {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}, de_next, a.de + r0 * TC_H, G1, dPr + (r0 / k) * TC_H, acc, s, g16))) return rc;
+                                     {m.W[0], 3 * TC_H, 0, 2 * TC_H, 1}, de_next, row_at(a.de, r0, g16), G1, dPr + (r0 / k) * TC_H, acc, s, g16, g16))) return rc;
             // dW1e = G1^T e, db1
             if ((rc = run_wgrad(ns, G1, e_in, rows, g->W[0], 3 * TC_H, 2 * TC_H, g->b[0], acc, sc.wg, s, 0, 0, 0, g16))) return rc;
             // (grid: enough warps to cover the memory latency; every warp strides over the chunk's entries)

@@ -70,6 +70,8 @@ def _mlp_params(seq: nn.Sequential, norm: Optional[nn.LayerNorm]) -> MlpParams:
                      None if norm is None else norm.weight, None if norm is None else norm.bias)
 
 
+GRAD16_MIN_ROWS = 1 << 16         # edge rows from which the bfloat16 gradient stream is used (more than one wave of tiles: the
+                                  # backward of shorter streams runs the fused chains, csrc/tc_model.cu bwd_mode)
 REORDER_MIN_NODES = 1 << 17       # below this the per-node tables the edges gather from live in L2 whatever the numbering
 
 
@@ -101,7 +103,6 @@ class _Plan:
         # precision of the backward over the EDGE streams (processor edge MLPs, edge encoder): "bf16x3g" keeps the three gradient
         # intermediates of the long-stream composition as bfloat16 (csrc/tc_model.cu grad16; error study tests/study_grad_stream.py)
         self.grad_stream = grad_stream
-        self.edge_bwd_precision = "bf16x3g" if precision == "bf16x3" and grad_stream == "bf16" else precision
         self.k_valid = k_valid                # real in-degree when k is the padded power of two (0: k itself)
         self.enc_node, self.enc_edge = enc_node, enc_edge
         self.proc_node, self.proc_edge = proc_node, proc_edge
@@ -109,6 +110,13 @@ class _Plan:
         self.groups = groups                  # [(MlpParams, first index into the flat parameter list)]
         self.edge_buffers = edge_buffers      # forced number of edge-stream buffers (0: from the free memory)
         self.grad_enabled = torch.is_grad_enabled()      # sampled where the module is called (autograd runs Function.forward in no-grad mode)
+
+    def edge_bwd_precision(self, n_edges: int) -> str:
+        """"bf16x3g" (CGNN_PREC_BF16X3_G16) for edge streams long enough for the layered backward composition, where it pays and where
+        the rounding of the gradient stream averages out; the model's own precision otherwise."""
+        if self.precision == "bf16x3" and self.grad_stream == "bf16" and n_edges >= GRAD16_MIN_ROWS:
+            return "bf16x3g"
+        return self.precision
 
     def padded_for_tensor_cores(self):
         """The same plan over zero-padded copies of the parameters (ops.PaddedMlp) when the tensor-core precisions meet a
@@ -336,6 +344,8 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         de = None
         rowptr, perm = ctx.transpose_fn()
         fp32 = prec == "fp32"
+        prec_e = p.edge_bwd_precision(ctx.edge_attr.shape[0]) if edge_mode else prec
+        de_dtype = ops.grad_stream_dtype(prec_e)
 
         def step_backward(t, e_t, dh, de):
             if halo is not None:
@@ -348,10 +358,13 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
             if edge_mode:
                 # the gradient stream is updated in place (de^t over de^{t+1}); only the FP32 kernels need the per-edge
                 # scratch gs, the tensor-core path accumulates the sender sums chunk by chunk in its workspace
-                de_new = de if de is not None else ctx.lease.bufs[-1]
+                de_new = de
+                if de_new is None:                   # (a bfloat16 gradient stream uses the first half of its buffer)
+                    buf = ctx.lease.bufs[-1]
+                    de_new = buf if de_dtype == buf.dtype else buf.view(-1).view(de_dtype)[:buf.numel()].view(buf.shape)
                 gs = torch.empty_like(e_t) if fp32 else None
                 put(p.proc_edge[t], ops.mp_edge_bwd(p.proc_edge[t], hs[t], e_t, senders, rowptr, perm, k, de, dagg,
-                                                    de_new, dh_new, gs, p.edge_bwd_precision, p.k_valid))
+                                                    de_new, dh_new, gs, prec_e, p.k_valid))
                 return dh_new, de_new
             ops.scatter_to_senders(dagg, True, rowptr, perm, k, dh_new)
             return dh_new, None
@@ -378,7 +391,9 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         put(p.enc_node, g_en)
         dea = None
         if edge_mode:
-            g_ee, dea = ops.mlp_rows_bwd(p.enc_edge, ctx.edge_attr, de, need_dea, p.edge_bwd_precision)
+            if need_dea and de.dtype != torch.float32:     # (an input gradient narrower than 128 columns comes from the FP32 kernels)
+                de, prec_e = de.float(), prec
+            g_ee, dea = ops.mlp_rows_bwd(p.enc_edge, ctx.edge_attr, de, need_dea, prec_e)
             put(p.enc_edge, g_ee)
         if ctx.lease is not None:
             ctx.lease.release()

@@ -241,8 +241,14 @@ def mlp_rows_fwd(p: MlpParams, x: torch.Tensor, precision: str = "fp32", out: Op
     return out
 
 
+def grad_stream_dtype(precision: str):
+    """Element type of the gradient stream an entry point exchanges with its caller (`de_next` / `de` of the edge phase, `dout` of
+    an MLP with LayerNorm): bfloat16 with "bf16x3g" (CGNN_PREC_BF16X3_G16), float32 otherwise."""
+    return torch.bfloat16 if precision == "bf16x3g" else torch.float32
+
+
 def mlp_rows_bwd(p: MlpParams, x: torch.Tensor, dout: torch.Tensor, need_dx: bool, precision: str = "fp32"):
-    require_cuda(dout, "dout", torch.float32)
+    require_cuda(dout, "dout", grad_stream_dtype(precision) if p.gamma is not None else torch.float32)
     m = p.c_struct()
     g, grads = p.new_grads()
     dx = torch.empty_like(x) if need_dx else None
@@ -335,6 +341,9 @@ def mp_edge_bwd(p: MlpParams, h, e_in, senders, rowptr, perm, k: int, de_next, d
     """Edge-phase backward including the deterministic scatter of the sender gradients into `dh`
     (`rowptr`, `perm`: sender-sorted transpose from `csr_transpose`).  `de` may be `de_next` (in place); `gs` [E,L] is
     the scratch of the FP32 kernels (None for the tensor-core precisions)."""
+    for name, t in (("de_next", de_next), ("de", de)):
+        if t is not None:
+            require_cuda(t, name, grad_stream_dtype(precision))
     m = p.c_struct()
     g, grads = p.new_grads()
     n_recv = e_in.shape[0] // k

@@ -63,11 +63,15 @@ typedef enum {
     CGNN_PREC_FP32 = 0,        /* FP32 SIMT FMA everywhere (<= 1e-5 parity mode) */
     CGNN_PREC_BF16X3 = 1,      /* tcgen05 tensor cores, bf16 hi/lo split operands (3 MMAs), FP32 accum/storage */
     CGNN_PREC_BF16 = 2,        /* tcgen05, single bf16 pass (fastest; ~1e-2, outside the parity bar) */
-    CGNN_PREC_BF16X3_G16 = 3   /* CGNN_PREC_BF16X3 whose backward over LONG row streams (cgnn_mp_edge_bwd, cgnn_mlp_rows_bwd of an MLP with
-                                * LayerNorm; more rows than one wave of tiles) keeps its three gradient intermediates dY, G2, G1 as bfloat16
-                                * in HBM: forward values and ReLU gates are those of CGNN_PREC_BF16X3, the rounding of the gradient stream
-                                * averages out in the weight gradients (tests/study_grad_stream.py).  Every other entry point treats it as
-                                * CGNN_PREC_BF16X3. */
+    CGNN_PREC_BF16X3_G16 = 3   /* CGNN_PREC_BF16X3 with a 2-byte gradient stream, meant for LONG row streams (the edges of a large graph): in
+                                * cgnn_mp_edge_bwd and in cgnn_mlp_rows_bwd of an MLP with LayerNorm
+                                *   - `de_next` / `de` (edge phase) and `dout` (rows) are bfloat16 [rows][128] arrays behind the float pointers
+                                *     (round to nearest even; `de` may still alias `de_next`),
+                                *   - the three gradient intermediates dY, G2, G1 of the workspace are bfloat16 as well,
+                                *   - the call always runs the layered one-launch-per-GEMM composition.
+                                * Forward values and ReLU gates are those of CGNN_PREC_BF16X3; the rounding of the gradient stream averages
+                                * out in the weight gradients (error study on the oracle: tests/study_grad_stream.py).  MLPs without
+                                * LayerNorm and every other entry point treat it as CGNN_PREC_BF16X3. */
     /* The tensor-core modes cover the processor phases (cgnn_mp_edge_* / cgnn_mp_node_*) for
      * latent = hidden = 128 with 2 hidden layers and k a power of two <= 32; other shapes return
      * CGNN_ERR_UNSUPPORTED.  The row-wise encoder / decoder entry points use the tensor cores for 3-layer

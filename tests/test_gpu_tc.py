@@ -442,8 +442,8 @@ def test_whole_model_training_step_is_reproducible(message):
 
 
 # ---- the 2-byte gradient stream (CGNN_PREC_BF16X3_G16, "bf16x3g") -----------------------------------------------------------
-# On long streams the backward keeps dY / G2 / G1 as bfloat16.  Against the FP32-stream backward of the same precision every
-# element of those intermediates is off by <= 2^-9 relative, with random sign.  On THIS test's data (independent random inputs
+# The backward keeps dY / G2 / G1 and the gradient stream it exchanges with its caller (de_next / de, dout) as bfloat16.  Against the
+# FP32-stream backward of the same precision every element of those streams is off by <= 2^-9 relative, with random sign.  On THIS test's data (independent random inputs
 # and upstream gradients) a weight gradient is itself a sum of zero-mean terms, so rounding noise and signal both grow like
 # sqrt(rows) and the distance stays near 2^-9 / sqrt(3) ~ 1e-3 whatever the size: bar 4e-3.  In the model the terms of a weight
 # gradient are coherent and the noise averages out (tests/study_grad_stream.py; tests/test_gpu_benched.py holds 1e-3 there).
@@ -463,14 +463,14 @@ def test_bf16_gradient_stream_edge_backward():
     e = torch.randn(n * k, L, device=d, generator=gen)
     senders = torch.randint(0, n, (n * k,), device=d, generator=gen, dtype=torch.int32)
     rowptr, perm = ops.csr_transpose(senders, n)
-    de0 = torch.randn(n * k, L, device=d, generator=gen)
+    de0 = torch.randn(n * k, L, device=d, generator=gen).bfloat16().float()      # (both runs see the same upstream gradient)
     dagg = torch.randn(n, L, device=d, generator=gen)
     dh0 = torch.randn(n, L, device=d, generator=gen)
 
     def run(precision):
-        de, dh = de0.clone(), dh0.clone()
+        de, dh = de0.clone().to(ops.grad_stream_dtype(precision)), dh0.clone()       # in place: de^t over de^{t+1}
         grads = ops.mp_edge_bwd(p, h, e, senders, rowptr, perm, k, de, dagg, de, dh, None, precision)
-        return [de - de0, dh - dh0] + list(grads)
+        return [de.float(), dh - dh0] + list(grads)
 
     ref = run("bf16x3")
     got = run("bf16x3g")
@@ -494,8 +494,8 @@ def test_bf16_gradient_stream_rows_backward():
     p, ws, bs, gamma, beta = _rows_params(4, L, True, gen)
     d = _dev()
     x = torch.randn(rows, 4, generator=gen).to(d)
-    dout = torch.randn(rows, L, generator=gen).to(d)
-    ref, _ = ops.mlp_rows_bwd(p, x, dout, False, "bf16x3")
+    dout = torch.randn(rows, L, generator=gen).to(d).bfloat16()
+    ref, _ = ops.mlp_rows_bwd(p, x, dout.float(), False, "bf16x3")
     got, _ = ops.mlp_rows_bwd(p, x, dout, False, "bf16x3g")
     torch.cuda.synchronize()
     errs = [rel_l2(a.cpu(), b.cpu()) for a, b in zip(got, ref)]
@@ -503,4 +503,36 @@ def test_bf16_gradient_stream_rows_backward():
     assert all(v < G16_TOL for v in errs), errs
     assert max(errs[:6]) > 1e-6, "the 2-byte stream did not run"
     again, _ = ops.mlp_rows_bwd(p, x, dout, False, "bf16x3g")
+    assert all(torch.equal(a, b) for a, b in zip(again, got))
+
+
+def test_bf16_gradient_stream_last_step_and_multiple_chunks():
+    """No gradient on the edge output (the last processor step: de is written, nothing is read), and a stream longer than one
+    backward chunk (2 Mi rows) whose last chunk is short: same results as the FP32 stream within the bar, bit-reproducible."""
+    from cosmology_gnn_simulation_b200 import ops
+    from cosmology_gnn_simulation_b200.ops import MlpParams
+    d = _dev()
+    gen = torch.Generator(device=d).manual_seed(5)
+    n, k = 70000, 32                                    # 2 240 000 rows = one full chunk + 142 848
+    ws = [torch.randn(L, i, device=d, generator=gen) / i ** 0.5 for i in (3 * L, L, L)]
+    bs = [torch.randn(L, device=d, generator=gen) * 0.1 for _ in range(3)]
+    p = MlpParams(ws, bs, torch.ones(L, device=d), torch.zeros(L, device=d))
+    h = torch.randn(n, L, device=d, generator=gen)
+    e = torch.randn(n * k, L, device=d, generator=gen)
+    senders = torch.randint(0, n, (n * k,), device=d, generator=gen, dtype=torch.int32)
+    rowptr, perm = ops.csr_transpose(senders, n)
+    dagg = torch.randn(n, L, device=d, generator=gen)
+
+    def run(precision):
+        de = torch.full((n * k, L), 7.0, device=d, dtype=ops.grad_stream_dtype(precision))
+        dh = torch.zeros(n, L, device=d)
+        grads = ops.mp_edge_bwd(p, h, e, senders, rowptr, perm, k, None, dagg, de, dh, None, precision)
+        return [de.float(), dh] + list(grads)
+
+    ref, got, again = run("bf16x3"), run("bf16x3g"), run("bf16x3g")
+    torch.cuda.synchronize()
+    names = ["de", "dh", "W1", "b1", "W2", "b2", "W3", "b3", "gamma", "beta"]
+    errs = {nm: rel_l2(a.cpu(), b.cpu()) for nm, a, b in zip(names, got, ref)}
+    print("bf16 gradient stream, last step, 2 chunks:", {nm: f"{v:.1e}" for nm, v in errs.items()})
+    assert all(v < G16_TOL for v in errs.values()), errs
     assert all(torch.equal(a, b) for a, b in zip(again, got))

@@ -139,3 +139,23 @@ def test_edge_stream_schedule_is_valid_and_minimal():
                 assert ckpt_plan.recomputed_phases(acts) == 0.0
     assert ckpt_plan.recomputed_phases(ckpt_plan.schedule(10, 2)) == 12.5
     assert ckpt_plan.recomputed_phases(ckpt_plan.schedule(10, 3)) == 7.0
+
+
+def test_model_plan_is_built_on_cpu_and_the_kernels_refuse_cpu_tensors():
+    """Everything above the C ABI (plan, parameter groups, precision of the edge-stream backward) runs without a GPU; the first
+    kernel entry point then refuses the CPU tensors -- there is no CPU path."""
+    import pytest
+    from cosmology_gnn_simulation_b200.graph import Data
+    from cosmology_gnn_simulation_b200.graph_network import EncodeProcessDecode, GRAD16_MIN_ROWS, _Plan
+    n, k = 64, 4
+    g = Data(x=torch.randn(n, 17), edge_index=torch.stack([torch.randint(0, n, (n * k,)), torch.arange(n).repeat_interleave(k)]),
+             edge_attr=torch.randn(n * k, 4))
+    for precision in ("fp32", "bf16x3"):
+        model = EncodeProcessDecode(128, 128, 2, 2, 3, message="edge", precision=precision)
+        with pytest.raises((RuntimeError, TypeError, ValueError)) as err:
+            model(g)
+        assert "CUDA" in str(err.value) or "cuda" in str(err.value), err.value
+    plan = _Plan(2, "edge", "bf16x3", k, None, None, [], [], None, None, [], 0, grad_stream="bf16")
+    assert plan.edge_bwd_precision(GRAD16_MIN_ROWS) == "bf16x3g" and plan.edge_bwd_precision(GRAD16_MIN_ROWS - 1) == "bf16x3"
+    assert _Plan(2, "edge", "bf16x3", k, None, None, [], [], None, None, [], 0, grad_stream="fp32").edge_bwd_precision(1 << 30) == "bf16x3"
+    assert _Plan(2, "edge", "fp32", k, None, None, [], [], None, None, [], 0, grad_stream="bf16").edge_bwd_precision(1 << 30) == "fp32"
