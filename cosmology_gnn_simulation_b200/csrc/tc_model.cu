@@ -96,15 +96,22 @@ int slice_rows(const float* src, int w, int64_t rows, float* dst, cudaStream_t s
 // the sums do not depend on it), and a chunk's kernel visits its own entries only, a warp per entry.
 __global__ void sender_chunks_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, int64_t n, int chunk,
                                      int32_t* __restrict__ cnt, const int32_t* __restrict__ off, int2* __restrict__ ent) {
-    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // a warp per node, 32 list positions at a time (coalesced reads of perm): a position opens an entry when its chunk differs from
+    // its predecessor's
+    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (j >= n) return;
-    int prev = -1;
-    for (int p = rowptr[j], b = rowptr[j + 1]; p < b; ++p) {
-        const int c = perm[p] / chunk;
-        if (c == prev) continue;
-        prev = c;
-        const int slot = atomicAdd(cnt + c, 1);
-        if (ent != nullptr) ent[off[c] + slot] = make_int2((int)j, p);      // second pass: fill
+    int last = -1;                                        // chunk of the position before this batch
+    for (int base = rowptr[j], b = rowptr[j + 1]; base < b; base += 32) {
+        const int p = base + lane;
+        const int c = p < b ? perm[p] / chunk : -2;
+        int before = __shfl_up_sync(0xFFFFFFFFu, c, 1);
+        if (lane == 0) before = last;
+        if (p < b && c != before) {
+            const int slot = atomicAdd(cnt + c, 1);
+            if (ent != nullptr) ent[off[c] + slot] = make_int2((int)j, p);      // second pass: fill
+        }
+        last = __shfl_sync(0xFFFFFFFFu, c, 31);
     }
 }
 // off[c] = entries of the chunks before c (exclusive scan; at most a few thousand chunks), counters back to zero for the fill pass
@@ -515,11 +522,11 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         // per-node sums of G1 by sender: accumulated chunk by chunk over the sender-sorted transpose (no E-sized buffer)
         CGNN_CUDA(cudaMemsetAsync(dPs, 0, (size_t)nn * TC_H * 4, s));
         CGNN_CUDA(cudaMemsetAsync(ecnt, 0, (size_t)(n_chunks + 1) * 4, s));
-        sender_chunks_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, ecnt, nullptr, nullptr);
+        sender_chunks_kernel<<<(unsigned)((nn * 32 + 255) / 256), 256, 0, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, ecnt, nullptr, nullptr);
         CGNN_LAUNCH_CHECK();
         sender_chunks_offsets_kernel<<<1, 32, 0, s>>>(ecnt, eoff, n_chunks);
         CGNN_LAUNCH_CHECK();
-        sender_chunks_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, ecnt, eoff, ent);
+        sender_chunks_kernel<<<(unsigned)((nn * 32 + 255) / 256), 256, 0, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, ecnt, eoff, ent);
         CGNN_LAUNCH_CHECK();
         for (int64_t r0 = 0, c = 0; r0 < E; r0 += chunk, ++c) {
             const int64_t rows = E - r0 < chunk ? E - r0 : chunk;       // chunk is a multiple of 256 and of k unless it is the whole graph

@@ -25,9 +25,10 @@ constexpr int TR = 64;                    // rows per tile (the K extent of one 
                                           // warps waiting for TMA data in 46 % of their samples.  64-row tiles halve the images, the freed
                                           // shared memory goes to the ring: two tiles of input in flight per SM.
 constexpr int WG_SETS = 4;
-constexpr int WG_RING = 16;               // input ring: TR rows x 32 columns (128-byte rows, SWIZZLE_128B) per chunk.  A multiple of WG_SETS,
+constexpr int WG_RING = 12;               // input ring: TR rows x 32 columns (128-byte rows, SWIZZLE_128B) per chunk.  A multiple of WG_SETS,
                                           // so that a ring slot is always consumed by the same converter set and the phase parity a set
-                                          // waits on can never alias a phase that belongs to another set
+                                          // waits on can never alias a phase that belongs to another set.  (16 slots until the operand
+                                          // images were double-buffered: 96 KB in flight per SM still cover the memory latency.)
 constexpr int CW = 32, NCW = TC_H / CW, CW_BYTES = TR * CW * 4;
 constexpr int OP_BYTES = 128 * TR * 2;    // one BF16 operand image (128 mn x TR k)
 constexpr int MN_STRIDE = (TR / 8) * 128; // bytes between groups of 8 mn in an MN-major image
@@ -42,18 +43,21 @@ struct WgSmem {
     static constexpr int ring = 0;
     static constexpr int bars = ring + WG_RING * CW_BYTES;
     static constexpr int ones = bars + 512;
-    static constexpr int ops = ones + ONES_BYTES;          // X images (NSI), then A images (NSI)
+    static constexpr int ops = ones + ONES_BYTES;          // two sets of {X images (NSI), A images (NSI)}: tile it uses set it & 1
 };
 static_assert(WgSmem::ops % 128 == 0, "operand images need 128-byte alignment");
 
 struct WgBars {
     uint64_t in_full[WG_RING], in_empty[WG_RING];
-    uint64_t ops_full;       // 8 converter warps
-    uint64_t ops_empty;      // tcgen05.commit
+    uint64_t ops_full[2];    // per image set: 8 converter warps
+    uint64_t ops_empty[2];   // per image set: tcgen05.commit of the tile that read it
     uint32_t tmem_base;
 };
 
 // MN-major image: element (mn, k) at (mn/8)*MN_STRIDE + (k/8)*128 + (k%8)*16 + (mn%8)*2
+// The operand images are double-buffered (round 2, second session): with one set the converters of tile i + 1 waited for the MMAs of
+// tile i, and convert -> publish -> MMA -> commit ran as one serial chain per 64-row tile (~3.1 k cycles per tile, 4.4 TB/s on the
+// bfloat16 X stream: latency-, not memory-bound).
 // X16: X is a bfloat16 [rows][128] stream (the 2-byte gradient stream): two 64-column chunks per tile whose 16-byte pieces ARE the
 // rows of the image's 8 x 8 core matrices -- no split, no low image, two MMAs per K step instead of three.
 template <int NS, bool X16>
@@ -64,15 +68,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem[];
     WgBars* bars = reinterpret_cast<WgBars*>(smem + WgSmem::bars);
     uint8_t* sOnes = smem + WgSmem::ones;
-    uint8_t* sX = smem + WgSmem::ops;
-    uint8_t* sA = sX + NSI * OP_BYTES;
+    constexpr int SET_BYTES = 2 * NSI * OP_BYTES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_it = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid == 0) {
         for (int i = 0; i < WG_RING; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 2); }
-        mbar_init(&bars->ops_full, 8);
-        mbar_init(&bars->ops_empty, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->ops_full[b], 8); mbar_init(&bars->ops_empty[b], 1); }
         fence_mbar_init();
     }
     for (int i = tid; i < ONES_BYTES / 4; i += WG_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0u;
@@ -109,11 +111,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16_major(128, TC_H, 1, 1);
             const uint32_t idesc1 = umma_idesc_bf16_major(128, 16, 1, 1);
-            const uint32_t x_hi = smem_u32(sX), x_lo = x_hi + OP_BYTES;
-            const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + OP_BYTES;
             const uint32_t ones = smem_u32(sOnes);
             for (int64_t it = 0; it < n_it; ++it) {
-                mbar_wait_or_trap(&bars->ops_full, (uint32_t)(it & 1), 210);
+                const int b = (int)(it & 1);
+                const uint32_t x_hi = smem_u32(smem + WgSmem::ops + b * SET_BYTES), x_lo = x_hi + OP_BYTES;
+                const uint32_t a_hi = x_hi + NSI * OP_BYTES, a_lo = a_hi + OP_BYTES;
+                mbar_wait_or_trap(&bars->ops_full[b], (uint32_t)((it >> 1) & 1), 210);
                 tc_fence_after_sync();
                 const uint32_t first = it == 0 ? 0u : 1u;
 #pragma unroll
@@ -129,7 +132,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                         if (!X16) umma_bf16<1>(tmem + 128, dxl, umma_desc(ones + ks * 256, 128, MN_STRIDE), idesc1, 1u);
                     }
                 }
-                umma_commit<1>(&bars->ops_empty);
+                umma_commit<1>(&bars->ops_empty[b]);
             }
         }
     } else {
@@ -139,7 +142,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int cset = tid >> 6;
         uint32_t seq = 0;
         for (int64_t it = 0; it < n_it; ++it) {
-            if (it > 0) mbar_wait_or_trap(&bars->ops_empty, (uint32_t)((it - 1) & 1), 220);      // previous tile's MMAs read the images
+            const int b = (int)(it & 1);
+            if (it >= 2) mbar_wait_or_trap(&bars->ops_empty[b], (uint32_t)(((it >> 1) - 1) & 1), 220);   // the MMAs of tile it - 2 read this set
+            uint8_t* sX = smem + WgSmem::ops + b * SET_BYTES;
+            uint8_t* sA = sX + NSI * OP_BYTES;
             for (int op = 0; op < 2; ++op) {
                 uint8_t* img = op == 0 ? sX : sA;
                 const int nq = X16 && op == 0 ? NCW / 2 : NCW;
@@ -187,11 +193,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive_local(&bars->ops_full);
+            if (lane == 0) mbar_arrive_local(&bars->ops_full[b]);
         }
         // ---- write this CTA's partial block -----------------------------------------------------------------
-        if (n_it > 0) {
-            mbar_wait_or_trap(&bars->ops_empty, (uint32_t)((n_it - 1) & 1), 240);
+        if (n_it > 0) {       // (a commit covers every MMA issued before it: the last tile's is enough)
+            mbar_wait_or_trap(&bars->ops_empty[(n_it - 1) & 1], (uint32_t)(((n_it - 1) >> 1) & 1), 240);
             tc_fence_after_sync();
         }
         // accumulator row = TMEM lane: warp w reads lane quarter w & 3; the two warps of a quarter alternate 16-column blocks
@@ -324,7 +330,7 @@ int run_wgrad(int ns, const float* X, const float* A, int64_t rows, float* dW, i
     int rc;
     if ((rc = x16 ? make_row_map_bf16(&mx, X, rows, TR) : make_row_map32_rows(&mx, X, rows, TR))) return rc;
     if ((rc = make_row_map32_rows(&ma, A, rows, TR, a_cols > 0 ? a_cols : TC_H))) return rc;
-    const size_t smem = (size_t)WgSmem::ops + (size_t)2 * nsi * OP_BYTES;
+    const size_t smem = (size_t)WgSmem::ops + (size_t)2 * 2 * nsi * OP_BYTES;           // two image sets
     float* partials = static_cast<float*>(ws);
     void (*kern)(CUtensorMap, CUtensorMap, int64_t, float*) =
         ns == 3 ? (x16 ? tc_wgrad_kernel<3, true> : tc_wgrad_kernel<3, false>) : (x16 ? tc_wgrad_kernel<1, true> : tc_wgrad_kernel<1, false>);
