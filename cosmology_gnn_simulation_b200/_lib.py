@@ -59,6 +59,8 @@ SIGNATURES = {
     "cgnn_mp_edge_fwd": (c_int, [POINTER(CgnnMlp), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                  c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "cgnn_aggregate_senders": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "cgnn_halo_pack": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "cgnn_halo_unpack_add": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "cgnn_mp_node_fwd_workspace_bytes": (c_int64, [POINTER(CgnnMlp), c_int64, c_int32]),
     "cgnn_mp_node_fwd": (c_int, [POINTER(CgnnMlp), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32,
                                  c_void_p]),

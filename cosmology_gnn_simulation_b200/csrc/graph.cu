@@ -147,3 +147,48 @@ extern "C" int cgnn_csr_transpose(const int32_t* senders, int64_t n, int64_t n_e
     }
     return CGNN_OK;
 }
+
+// ---- halo exchange of a slab-sharded box: the row copies either side of the transport -------------------------------
+namespace cgnn {
+namespace {
+// a warp per row, lane <-> float4 columns
+template <bool ADD>
+__global__ void halo_rows_kernel(const float4* __restrict__ src, const int64_t* __restrict__ idx, int64_t n_idx, int l4,
+                                 float4* __restrict__ dst) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_idx) return;
+    const int64_t row = idx[i];
+    for (int c = lane; c < l4; c += 32) {
+        if (ADD) {                                   // unique targets: no two warps touch the same row
+            float4 d = dst[row * l4 + c];
+            const float4 v = src[i * l4 + c];
+            d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
+            dst[row * l4 + c] = d;
+        } else {
+            dst[i * l4 + c] = src[row * l4 + c];
+        }
+    }
+}
+}  // namespace
+}  // namespace cgnn
+
+extern "C" int cgnn_halo_pack(const float* src, const int64_t* idx, int64_t n_idx, int32_t latent, float* dst, cgnn_stream stream_) {
+    using namespace cgnn;
+    CGNN_CHECK_ARG(src && idx && dst && n_idx >= 0 && latent >= 4 && latent % 4 == 0, "cgnn_halo_pack: bad arguments");
+    if (n_idx == 0) return CGNN_OK;
+    halo_rows_kernel<false><<<(unsigned)((n_idx * 32 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        reinterpret_cast<const float4*>(src), idx, n_idx, latent / 4, reinterpret_cast<float4*>(dst));
+    CGNN_LAUNCH_CHECK();
+    return CGNN_OK;
+}
+
+extern "C" int cgnn_halo_unpack_add(const float* src, const int64_t* idx, int64_t n_idx, int32_t latent, float* dst, cgnn_stream stream_) {
+    using namespace cgnn;
+    CGNN_CHECK_ARG(src && idx && dst && n_idx >= 0 && latent >= 4 && latent % 4 == 0, "cgnn_halo_unpack_add: bad arguments");
+    if (n_idx == 0) return CGNN_OK;
+    halo_rows_kernel<true><<<(unsigned)((n_idx * 32 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        reinterpret_cast<const float4*>(src), idx, n_idx, latent / 4, reinterpret_cast<float4*>(dst));
+    CGNN_LAUNCH_CHECK();
+    return CGNN_OK;
+}

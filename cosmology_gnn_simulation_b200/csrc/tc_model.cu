@@ -94,24 +94,47 @@ int slice_rows(const float* src, int w, int64_t rows, float* dst, cudaStream_t s
 // list is ascending, so one walk over it yields its (chunk, first position) pairs; they are counted, offset and filled into
 // per-chunk entry lists (the order of the entries inside a list is whatever the atomics give -- every entry owns its dPs row, so
 // the sums do not depend on it), and a chunk's kernel visits its own entries only, a warp per entry.
-__global__ void sender_chunks_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, int64_t n, int chunk,
-                                     int32_t* __restrict__ cnt, const int32_t* __restrict__ off, int2* __restrict__ ent) {
-    // a warp per node, 32 list positions at a time (coalesced reads of perm): a position opens an entry when its chunk differs from
-    // its predecessor's
-    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (j >= n) return;
-    int last = -1;                                        // chunk of the position before this batch
-    for (int base = rowptr[j], b = rowptr[j + 1]; base < b; base += 32) {
-        const int p = base + lane;
-        const int c = p < b ? perm[p] / chunk : -2;
-        int before = __shfl_up_sync(0xFFFFFFFFu, c, 1);
-        if (lane == 0) before = last;
-        if (p < b && c != before) {
-            const int slot = atomicAdd(cnt + c, 1);
-            if (ent != nullptr) ent[off[c] + slot] = make_int2((int)j, p);      // second pass: fill
+constexpr int SC_WARPS = 8, SC_NODES = 64;          // a block of 8 warps walks 64 consecutive nodes
+// Counts (ent == nullptr) or fills the per-chunk entry lists.  The block first counts its own entries per chunk in shared memory and
+// reserves them with ONE global atomic per chunk it touches (consecutive nodes send into the same one or two chunks; a global
+// atomic per entry -- four million on 32 counters at 2.1 M particles -- took 1.6 ms per pass), then walks again to place them.
+__global__ void __launch_bounds__(SC_WARPS * 32)
+sender_chunks_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, int64_t n, int chunk, int n_chunks,
+                     int32_t* __restrict__ cnt, const int32_t* __restrict__ off, int2* __restrict__ ent) {
+    extern __shared__ int32_t sc_sh[];
+    int32_t* lc = sc_sh;                  // entries of this block per chunk
+    int32_t* lbase = sc_sh + n_chunks;    // where they start inside the chunk's global range
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < n_chunks; i += blockDim.x) lc[i] = 0;
+    __syncthreads();
+    for (int pass = 0; pass < (ent != nullptr ? 2 : 1); ++pass) {
+        for (int q = warp; q < SC_NODES; q += SC_WARPS) {
+            // a warp per node, 32 list positions at a time (coalesced reads of perm): a position opens an entry when its chunk
+            // differs from its predecessor's
+            const int64_t j = (int64_t)blockIdx.x * SC_NODES + q;
+            if (j >= n) break;
+            int last = -1;                                    // chunk of the position before this batch
+            for (int base = rowptr[j], b = rowptr[j + 1]; base < b; base += 32) {
+                const int p = base + lane;
+                const int c = p < b ? perm[p] / chunk : -2;
+                int before = __shfl_up_sync(0xFFFFFFFFu, c, 1);
+                if (lane == 0) before = last;
+                if (p < b && c != before) {
+                    const int local = atomicAdd(lc + c, 1);
+                    if (pass == 1) ent[off[c] + lbase[c] + local] = make_int2((int)j, p);
+                }
+                last = __shfl_sync(0xFFFFFFFFu, c, 31);
+            }
         }
-        last = __shfl_sync(0xFFFFFFFFu, c, 31);
+        __syncthreads();
+        if (pass == 0) {
+            for (int i = threadIdx.x; i < n_chunks; i += blockDim.x) {
+                const int m = lc[i];
+                if (m > 0) lbase[i] = atomicAdd(cnt + i, m);
+                lc[i] = 0;
+            }
+            __syncthreads();
+        }
     }
 }
 // off[c] = entries of the chunks before c (exclusive scan; at most a few thousand chunks), counters back to zero for the fill pass
@@ -522,11 +545,14 @@ int tc_mlp_bwd(MlpTask& a, const cgnn_mlp_grad* g, void* ws, int64_t wsb, int pr
         // per-node sums of G1 by sender: accumulated chunk by chunk over the sender-sorted transpose (no E-sized buffer)
         CGNN_CUDA(cudaMemsetAsync(dPs, 0, (size_t)nn * TC_H * 4, s));
         CGNN_CUDA(cudaMemsetAsync(ecnt, 0, (size_t)(n_chunks + 1) * 4, s));
-        sender_chunks_kernel<<<(unsigned)((nn * 32 + 255) / 256), 256, 0, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, ecnt, nullptr, nullptr);
+        const unsigned scgrid = (unsigned)((nn + SC_NODES - 1) / SC_NODES);
+        const size_t scsmem = (size_t)2 * n_chunks * sizeof(int32_t);
+        CGNN_CHECK_ARG(scsmem <= 48 * 1024, "cgnn_mp_edge_bwd: too many backward chunks (%d)", n_chunks);
+        sender_chunks_kernel<<<scgrid, SC_WARPS * 32, scsmem, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, n_chunks, ecnt, nullptr, nullptr);
         CGNN_LAUNCH_CHECK();
         sender_chunks_offsets_kernel<<<1, 32, 0, s>>>(ecnt, eoff, n_chunks);
         CGNN_LAUNCH_CHECK();
-        sender_chunks_kernel<<<(unsigned)((nn * 32 + 255) / 256), 256, 0, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, ecnt, eoff, ent);
+        sender_chunks_kernel<<<scgrid, SC_WARPS * 32, scsmem, s>>>(a.t_rowptr, a.t_perm, nn, (int)chunk, n_chunks, ecnt, eoff, ent);
         CGNN_LAUNCH_CHECK();
         for (int64_t r0 = 0, c = 0; r0 < E; r0 += chunk, ++c) {
             const int64_t rows = E - r0 < chunk ? E - r0 : chunk;       // chunk is a multiple of 256 and of k unless it is the whole graph

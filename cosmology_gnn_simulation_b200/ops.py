@@ -355,6 +355,26 @@ def mp_edge_bwd(p: MlpParams, h, e_in, senders, rowptr, perm, k: int, de_next, d
     return grads
 
 
+def halo_pack(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """src[idx] as a fresh contiguous send buffer (slab.HaloPlan.exchange); idx int64."""
+    require_cuda(src, "src", torch.float32)
+    require_cuda(idx, "idx", torch.int64)
+    out = torch.empty((idx.numel(), src.shape[1]), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib().cgnn_halo_pack(ptr(src), ptr(idx), idx.numel(), src.shape[1], ptr(out), stream_ptr(src.device)), "cgnn_halo_pack")
+    return out
+
+
+def halo_unpack_add(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[idx] += src for unique idx (slab.HaloPlan.reduce_grad)."""
+    require_cuda(src, "src", torch.float32)
+    require_cuda(idx, "idx", torch.int64)
+    require_cuda(dst, "dst", torch.float32)
+    with torch.cuda.device(dst.device):
+        check(lib().cgnn_halo_unpack_add(ptr(src), ptr(idx), idx.numel(), dst.shape[1], ptr(dst), stream_ptr(dst.device)),
+              "cgnn_halo_unpack_add")
+
+
 def scatter_to_senders(src, per_receiver: bool, rowptr, perm, k: int, dh):
     with torch.cuda.device(dh.device):
         check(lib().cgnn_scatter_to_senders(ptr(src), int(per_receiver), ptr(rowptr), ptr(perm), dh.shape[0], k,

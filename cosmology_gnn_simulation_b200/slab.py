@@ -24,6 +24,19 @@ import torch
 import torch.distributed as dist
 
 
+def _native(t: torch.Tensor) -> bool:
+    """The row copies of the exchange run as libcgnn kernels for what the model hands over (float32 latent rows on the GPU, width a
+    multiple of 4); the gloo tests of the index logic (CPU tensors) keep the torch expressions."""
+    return t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] % 4 == 0 and t.is_contiguous()
+
+
+def _rows(t: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    if _native(t):
+        from . import ops
+        return ops.halo_pack(t, idx)                                         # cgnn_halo_pack
+    return t[idx].contiguous()
+
+
 def slab_bounds(n: int, world: int) -> List[int]:
     """Equal-count ownership ranges of the x-sorted particles: rank p owns [b[p], b[p+1])."""
     return [(p * n) // world for p in range(world + 1)]
@@ -63,7 +76,7 @@ class HaloPlan:
             if h_loc.shape[0] != self.n_loc:
                 raise ValueError(f"halo exchange: expected {self.n_loc} rows, got {h_loc.shape[0]}")
             return
-        sends = {q: h_loc[idx].contiguous() for q, idx in enumerate(self.send_idx) if q != self.rank and idx.numel()}
+        sends = {q: _rows(h_loc, idx) for q, idx in enumerate(self.send_idx) if q != self.rank and idx.numel()}
         recvs = {q: h_loc[self.n_own + self.recv_off[q]: self.n_own + self.recv_off[q + 1]]
                  for q in range(self.world) if q != self.rank and self.recv_counts[q]}
         self._p2p(sends, recvs)
@@ -80,7 +93,11 @@ class HaloPlan:
         self._p2p(sends, recvs)
         for q in sorted(recvs):
             # the ids a peer asks for are unique, so index_add_ has no duplicate targets and is deterministic
-            dh_loc.index_add_(0, self.send_idx[q], recvs[q])
+            if _native(dh_loc):
+                from . import ops
+                ops.halo_unpack_add(recvs[q], self.send_idx[q], dh_loc)        # cgnn_halo_unpack_add
+            else:
+                dh_loc.index_add_(0, self.send_idx[q], recvs[q])
         if self.n_halo:
             dh_loc[self.n_own:].zero_()
 

@@ -184,6 +184,15 @@ int cgnn_mp_edge_fwd(const cgnn_mlp* edge_mlp, const float* h, const float* e_in
                      cgnn_stream stream);
 int cgnn_aggregate_senders(const float* h, const int32_t* senders, int64_t n, int32_t k,
                            int32_t latent, float* agg, cgnn_stream stream);
+/* Halo exchange of a slab-sharded box (the reference has no distributed code): the row copies either side of the
+ * transport (NCCL point-to-point between the ranks of one node).
+ *   cgnn_halo_pack:        dst[i] = src[idx[i]]      the owned rows one peer holds as halo, gathered into the send buffer
+ *   cgnn_halo_unpack_add:  dst[idx[i]] += src[i]     the gradients a peer accumulated on those copies, added on the owner;
+ *                                                    idx holds no duplicates, peers are applied in ascending rank order by
+ *                                                    the caller: deterministic
+ * Rows are `latent` floats (a multiple of 4), idx are int64 local row ids. */
+int cgnn_halo_pack(const float* src, const int64_t* idx, int64_t n_idx, int32_t latent, float* dst, cgnn_stream stream);
+int cgnn_halo_unpack_add(const float* src, const int64_t* idx, int64_t n_idx, int32_t latent, float* dst, cgnn_stream stream);
 int64_t cgnn_mp_node_fwd_workspace_bytes(const cgnn_mlp* node_mlp, int64_t n, int32_t precision);
 int cgnn_mp_node_fwd(const cgnn_mlp* node_mlp, const float* h, const float* agg, int64_t n,
                      float* h_out, void* workspace, int64_t workspace_bytes, int32_t precision,

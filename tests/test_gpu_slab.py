@@ -176,3 +176,18 @@ def test_sharded_rollout_world2_equals_single_gpu(tmp_path):
     d = torch.minimum(d, md["box_size"] - d)
     assert float(d.max()) < 1e-4 * md["box_size"]
     assert rel_l2(r0["InternalEnergy"], ref["InternalEnergy"].cpu()) < 1e-4
+
+
+def test_halo_row_copies_match_torch_indexing():
+    """cgnn_halo_pack / cgnn_halo_unpack_add: the row copies either side of the halo transport (slab.HaloPlan)."""
+    from cosmology_gnn_simulation_b200 import ops
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    for rows, L, m in ((1000, 128, 333), (50, 64, 50), (7, 4, 1), (10, 128, 0)):
+        src = torch.randn(rows, L, device=dev, generator=gen)
+        idx = torch.randperm(rows, device=dev, generator=gen)[:m].contiguous()
+        assert torch.equal(ops.halo_pack(src, idx), src[idx])
+        dst = torch.randn(rows, L, device=dev, generator=gen)
+        want = dst.clone().index_add_(0, idx, src[:m])
+        ops.halo_unpack_add(src[:m].contiguous(), idx, dst)
+        assert torch.equal(dst, want)
