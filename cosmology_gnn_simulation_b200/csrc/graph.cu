@@ -175,8 +175,8 @@ __global__ void halo_rows_kernel(const float4* __restrict__ src, const int64_t* 
 
 extern "C" int cgnn_halo_pack(const float* src, const int64_t* idx, int64_t n_idx, int32_t latent, float* dst, cgnn_stream stream_) {
     using namespace cgnn;
-    CGNN_CHECK_ARG(src && idx && dst && n_idx >= 0 && latent >= 4 && latent % 4 == 0, "cgnn_halo_pack: bad arguments");
     if (n_idx == 0) return CGNN_OK;
+    CGNN_CHECK_ARG(src && idx && dst && n_idx > 0 && latent >= 4 && latent % 4 == 0, "cgnn_halo_pack: bad arguments");
     halo_rows_kernel<false><<<(unsigned)((n_idx * 32 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
         reinterpret_cast<const float4*>(src), idx, n_idx, latent / 4, reinterpret_cast<float4*>(dst));
     CGNN_LAUNCH_CHECK();
@@ -185,8 +185,8 @@ extern "C" int cgnn_halo_pack(const float* src, const int64_t* idx, int64_t n_id
 
 extern "C" int cgnn_halo_unpack_add(const float* src, const int64_t* idx, int64_t n_idx, int32_t latent, float* dst, cgnn_stream stream_) {
     using namespace cgnn;
-    CGNN_CHECK_ARG(src && idx && dst && n_idx >= 0 && latent >= 4 && latent % 4 == 0, "cgnn_halo_unpack_add: bad arguments");
     if (n_idx == 0) return CGNN_OK;
+    CGNN_CHECK_ARG(src && idx && dst && n_idx > 0 && latent >= 4 && latent % 4 == 0, "cgnn_halo_unpack_add: bad arguments");
     halo_rows_kernel<true><<<(unsigned)((n_idx * 32 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
         reinterpret_cast<const float4*>(src), idx, n_idx, latent / 4, reinterpret_cast<float4*>(dst));
     CGNN_LAUNCH_CHECK();

@@ -410,9 +410,10 @@ class EncodeProcessDecode(nn.Module):
       precision      "fp32" (FP32 SIMT, <= 1e-5 parity, default) | "bf16x3" | "bf16" (tcgen05 tensor cores); env CGNN_PRECISION
       edge_buffers   message="edge" training: copies of the edge stream kept for the backward (0 = from the free memory)
       grad_stream    precision="bf16x3" only: "bf16" (default) | "fp32"; env CGNN_GRAD_STREAM.  "bf16": the backward of the edge MLPs
-                     over long streams (more rows than one wave of tiles) keeps its gradient intermediates dY / G2 / G1 as bfloat16
-                     in HBM.  Forward values and ReLU gates are unchanged; the rounding averages out in the weight gradients
-                     (tests/study_grad_stream.py: 1.3e-4 at 4 096 particles, shrinking with the square root of the size).
+                     over long streams (GRAD16_MIN_ROWS edge rows or more) keeps the gradient stream de^t it carries from step to
+                     step and its gradient intermediates dY / G2 / G1 as bfloat16 in HBM.  Forward values and ReLU gates are
+                     unchanged; the rounding averages out in the weight gradients (tests/study_grad_stream.py: 1.3e-4 at 4 096
+                     particles, shrinking with the square root of the size).
     """
 
     def __init__(self, latent_size: int, mlp_hidden_size: int, mlp_num_hidden_layers: int,

@@ -25,6 +25,7 @@ ap.add_argument("--workload", default="config2", choices=sorted(bench.WORKLOADS)
 ap.add_argument("--phase", default="step", choices=["step", "edge_fwd", "edge_bwd", "knn"])
 ap.add_argument("--message", default="edge")
 ap.add_argument("--precision", default="bf16x3")
+ap.add_argument("--grad-stream", default="bf16", choices=["bf16", "fp32"])
 a = ap.parse_args()
 n, k, L, M, kind = bench.WORKLOADS[a.workload]
 dev = torch.device("cuda", 0)
@@ -33,7 +34,8 @@ md = box["metadata"]
 g = preprocess(box["Coordinates"][:5], box["InternalEnergy"][:5], md, box["Coordinates"][5:6], box["InternalEnergy"][5:6],
                num_neighbors=k, dt=md["dt"], box_size=md["box_size"], device=dev)
 torch.manual_seed(0)
-model = EncodeProcessDecode(L, L, 2, M if a.phase == "step" else 1, 3, message=a.message, precision=a.precision).to(dev)
+model = EncodeProcessDecode(L, L, 2, M if a.phase == "step" else 1, 3, message=a.message, precision=a.precision,
+                            grad_stream=a.grad_stream).to(dev)
 
 
 def step():
@@ -67,8 +69,12 @@ else:
         run = lambda: ops.mp_edge_fwd(p, h, e, senders, k, e_out, agg, a.precision)  # noqa: E731
     else:
         rowptr, perm = ops.csr_transpose(senders, n)
-        de_next, dagg, dh = torch.randn_like(e), torch.randn_like(h), torch.zeros_like(h)
-        run = lambda: ops.mp_edge_bwd(p, h, e, senders, rowptr, perm, k, de_next, dagg, de_next, dh, None, a.precision)  # noqa: E731
+        # the precision the model itself picks for this stream length (bfloat16 gradient streams for long edge streams)
+        from cosmology_gnn_simulation_b200.graph_network import GRAD16_MIN_ROWS
+        prec_e = "bf16x3g" if a.precision == "bf16x3" and a.grad_stream == "bf16" and n * k >= GRAD16_MIN_ROWS else a.precision
+        de_next = torch.randn_like(e).to(ops.grad_stream_dtype(prec_e))
+        dagg, dh = torch.randn_like(h), torch.zeros_like(h)
+        run = lambda: ops.mp_edge_bwd(p, h, e, senders, rowptr, perm, k, de_next, dagg, de_next, dh, None, prec_e)  # noqa: E731
 for _ in range(2):
     run()
 torch.cuda.synchronize()
