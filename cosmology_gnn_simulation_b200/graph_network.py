@@ -153,23 +153,31 @@ class _StreamLease:
     loop does that) falls back to private tensors."""
     _busy = set()
 
-    def __init__(self, device, n_buffers: int, e_count: int, latent: int):
+    def __init__(self, device, n_buffers: int, e_count: int, latent: int, grad_dtype=None):
+        """n_buffers FP32 copies of the edge stream in `bufs`; with `grad_dtype` also the gradient stream `grad` in that element
+        type (bfloat16 for long streams, DESIGN.md section 3: half the size of a copy)."""
         from ._lib import workspace
         self.key = (str(device), id(workspace._bufs))
         self.shared = self.key not in _StreamLease._busy
         nbytes = e_count * latent * 4
+        self.grad = None
         if self.shared:
             _StreamLease._busy.add(self.key)
             self.bufs = [workspace.get(device, f"edge_stream_{i}", nbytes)[:nbytes].view(torch.float32).view(e_count, latent)
                          for i in range(n_buffers)]
+            if grad_dtype is not None:
+                gbytes = e_count * latent * torch.empty((), dtype=grad_dtype).element_size()
+                self.grad = workspace.get(device, "edge_stream_grad", gbytes)[:gbytes].view(grad_dtype).view(e_count, latent)
         else:
             self.bufs = [torch.empty((e_count, latent), dtype=torch.float32, device=device) for _ in range(n_buffers)]
+            if grad_dtype is not None:
+                self.grad = torch.empty((e_count, latent), dtype=grad_dtype, device=device)
 
     def release(self):
         if self.shared:
             _StreamLease._busy.discard(self.key)
             self.shared = False
-        self.bufs = None
+        self.bufs = self.grad = None
 
     def __del__(self):
         self.release()
@@ -184,7 +192,8 @@ def _edge_stream_buffers(plan: _Plan, n: int, n_loc: int, e_count: int, L: int, 
     forced = plan.edge_buffers or int(os.environ.get("CGNN_EDGE_BUFFERS", "0"))
     if forced:
         return min(int(forced), M)
-    key = (M, n, n_loc, e_count, L, plan.precision, str(device))
+    grad_copy = e_count * L * torch.empty((), dtype=ops.grad_stream_dtype(plan.edge_bwd_precision(e_count))).element_size()
+    key = (M, n, n_loc, e_count, L, plan.precision, grad_copy, str(device))
     nbuf = _STREAM_PLANS.get(key)
     if nbuf is not None:
         return nbuf
@@ -199,7 +208,7 @@ def _edge_stream_buffers(plan: _Plan, n: int, n_loc: int, e_count: int, L: int, 
     # still to come besides the stream copies: h^t (M+1) and agg^t (M) for every step, six node-sized temporaries of the
     # backward, the sender-sorted transpose, 1 GiB of small tensors -- and 3 % of the device is left untouched
     other = (2 * M + 7) * n_loc * L * 4 + 6 * e_count + (1 << 30) + (total * 3) // 100
-    nbuf = min(M, (free - other) // copy - 1)                  # - 1: the gradient stream de
+    nbuf = min(M, (free - other - grad_copy) // copy)           # next to the gradient stream de (half a copy as bfloat16)
     if nbuf < 1:
         raise RuntimeError(
             f"cgnn: the edge latent stream does not fit: {copy / 2**30:.1f} GiB per copy, two copies needed, "
@@ -267,8 +276,9 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
         else:
             nbuf = _edge_stream_buffers(p, n, n_loc, e_count, L, dev)
             acts = ckpt_plan.schedule(M, nbuf)
-            lease = _StreamLease(dev, nbuf + 1, e_count, L)           # nbuf copies of e^t + the gradient stream
-            bufs = lease.bufs[:nbuf]
+            lease = _StreamLease(dev, nbuf, e_count, L,               # nbuf copies of e^t + the gradient stream
+                                 grad_dtype=ops.grad_stream_dtype(p.edge_bwd_precision(e_count)))
+            bufs = lease.bufs
             last = None
             for pos, act in enumerate(acts):
                 if act[0] == "bwd":
@@ -358,10 +368,8 @@ class _EncodeProcessDecodeFn(torch.autograd.Function):
             if edge_mode:
                 # the gradient stream is updated in place (de^t over de^{t+1}); only the FP32 kernels need the per-edge
                 # scratch gs, the tensor-core path accumulates the sender sums chunk by chunk in its workspace
-                de_new = de
-                if de_new is None:                   # (a bfloat16 gradient stream uses the first half of its buffer)
-                    buf = ctx.lease.bufs[-1]
-                    de_new = buf if de_dtype == buf.dtype else buf.view(-1).view(de_dtype)[:buf.numel()].view(buf.shape)
+                de_new = de if de is not None else ctx.lease.grad
+                assert de_new.dtype == de_dtype
                 gs = torch.empty_like(e_t) if fp32 else None
                 put(p.proc_edge[t], ops.mp_edge_bwd(p.proc_edge[t], hs[t], e_t, senders, rowptr, perm, k, de, dagg,
                                                     de_new, dh_new, gs, prec_e, p.k_valid))
