@@ -263,6 +263,8 @@ def run_gpu(args):
     coords_host = box["Coordinates"].pin_memory()
     energy_host = box["InternalEnergy"].pin_memory()
     h2d_bytes = coords_host.numel() * 4 + energy_host.numel() * 4
+    if slab and world > 1:
+        h2d_bytes = (h2d_bytes + world - 1) // world      # per rank: its own share of the box (the rest arrives over NVLink)
 
     torch.manual_seed(0)
     model = EncodeProcessDecode(L, L, 2, M, 3, message=message, precision=precision).to(dev)
@@ -380,8 +382,13 @@ def run_gpu(args):
 
     # ---- end to end through the public API with host buffers (`e2e`) ---------------------------
     def e2e_step():
-        c = coords_host.to(dev, non_blocking=True)
-        u = energy_host.to(dev, non_blocking=True)
+        if slab and world > 1:
+            # host tensors go to preprocess_slab as they are: every rank copies its own share of the particles over PCIe, the
+            # shares travel between the GPUs over NVLink (slab.sharded_to_device)
+            c, u = coords_host, energy_host
+        else:
+            c = coords_host.to(dev, non_blocking=True)
+            u = energy_host.to(dev, non_blocking=True)
         g = build_graph(c, u)
         ls = run_step(g)
         return torch.stack([ls["loss"].detach(), ls["acc_loss"], ls["temp_rate_loss"], ls["momentum_loss"]]).cpu()

@@ -202,6 +202,22 @@ def preprocess_slab(position_seq, temperature_seq, metadata, target_position=Non
     dt = float(dt)
     box_size = float(box_size)
     dev = _cuda_device(device if device is not None else (position_seq.device if position_seq.is_cuda else None))
+    if world > 1 and float(noise_std) == 0.0 and not position_seq.is_cuda and position_seq.dim() == 3:
+        # host inputs: every rank copies only its share of the particles over PCIe, the shares travel between the GPUs over
+        # NVLink (slab.sharded_to_device) -- host-to-device bytes per rank do not grow with the number of ranks.  (With noise
+        # the reference draws it on the INPUT's device, data_utils.py:36-70: host inputs then stay on the host until after.)
+        w_, n_ = position_seq.shape[0], position_seq.shape[1]
+
+        def up(t, pdim):
+            return _slab.sharded_to_device(t.float(), pdim, rank, world, dev, group)
+
+        position_seq = up(position_seq, 1)
+        if not temperature_seq.is_cuda:
+            temperature_seq = up(temperature_seq, 1 if (temperature_seq.shape[0] == w_ and temperature_seq.shape[1] == n_) else 0)
+        if target_position is not None and not target_position.is_cuda:
+            target_position = up(target_position, 1 if target_position.dim() == 3 else 0)
+        if target_temperature is not None and not target_temperature.is_cuda:
+            target_temperature = up(target_temperature, 1 if target_temperature.dim() == 3 else 0)
     recent_pos, x, y_acc, y_temp = _features_and_targets(position_seq, temperature_seq, metadata, target_position,
                                                          target_temperature, noise_std, dt, box_size, dev)
     n = recent_pos.shape[0]

@@ -114,6 +114,41 @@ class HaloPlan:
         return other
 
 
+def sharded_to_device(t: torch.Tensor, particle_dim: int, rank: int, world: int, device, group=None) -> torch.Tensor:
+    """A host tensor that every rank holds in full, as a device tensor on every rank -- with each rank copying only ITS share
+    of the particles over PCIe (the range slab_bounds gives it along `particle_dim`) and the ranks handing their shares to one
+    another over NVLink (`share_over_ranks`).  Host-to-device bytes per rank are 1 / world of the tensor instead of all of it.
+    Tensors already on the device, and single-rank runs, pass through."""
+    if t is None:
+        return None
+    device = torch.device(device)
+    if t.device == device:
+        return t
+    if world == 1 or not dist.is_initialized():
+        return t.to(device, non_blocking=True)
+    b = slab_bounds(t.shape[particle_dim], world)
+    out = torch.empty(t.shape, dtype=t.dtype, device=device)
+    mine = tuple([slice(None)] * particle_dim + [slice(b[rank], b[rank + 1])])
+    out[mine].copy_(t[mine], non_blocking=True)
+    share_over_ranks(out, particle_dim, world, group)
+    return out
+
+
+def share_over_ranks(out: torch.Tensor, particle_dim: int, world: int, group=None) -> None:
+    """`out` holds, on every rank, that rank's own share [b[rank], b[rank+1]) along `particle_dim` (b = slab_bounds); on return
+    every rank holds all of it.  One broadcast per owner and contiguous block (a [W, N, 3] sequence has one block per frame), so
+    the shares need not be equal in size."""
+    import itertools
+    b = slab_bounds(out.shape[particle_dim], world)
+    lead = list(itertools.product(*[range(s) for s in out.shape[:particle_dim]]))
+    for q in range(world):
+        if b[q + 1] == b[q]:
+            continue
+        src = dist.get_global_rank(group, q) if group is not None else q
+        for idx in lead:
+            dist.broadcast(out[idx + (slice(b[q], b[q + 1]),)], src=src, group=group)
+
+
 def plan_from_global_senders(senders_global: torch.Tensor, bounds: Sequence[int], rank: int, world: int, group=None):
     """Builds the halo plan and the local sender table of one rank.
 

@@ -536,3 +536,16 @@ def test_bf16_gradient_stream_last_step_and_multiple_chunks():
     print("bf16 gradient stream, last step, 2 chunks:", {nm: f"{v:.1e}" for nm, v in errs.items()})
     assert all(v < G16_TOL for v in errs.values()), errs
     assert all(torch.equal(a, b) for a, b in zip(again, got))
+
+
+@pytest.mark.parametrize("cfg", [dict(n=4200, k=16, L=64, H=64, nh=2, M=3),      # narrow widths (zero-padded parameters, LayerNorm width 64)
+                                 dict(n=3000, k=24, L=128, H=128, nh=2, M=3)])    # in-degree padded to 32 with dummy edges
+def test_bf16_gradient_stream_with_padded_shapes_matches_oracle(cfg):
+    """The model switches to the bfloat16 gradient streams from 65 536 edge rows on: whole-model parity against the float64 oracle
+    at that size for the two padded shapes (their dummy columns / dummy edges must stay out of every gradient there too), input
+    gradients included (the edge-feature gradient leaves the 2-byte stream through a float32 copy)."""
+    from test_gpu_parity import _compare_with_oracle, TOL_TC
+    from cosmology_gnn_simulation_b200.graph_network import GRAD16_MIN_ROWS
+    k_pad = 1 << (cfg["k"] - 1).bit_length()
+    assert cfg["n"] * k_pad >= GRAD16_MIN_ROWS
+    _compare_with_oracle("edge", cfg, "bf16x3", TOL_TC, gtol=1e-2, in_gtol=3e-2)

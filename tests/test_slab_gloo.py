@@ -103,3 +103,33 @@ def test_slab_bounds_cover_everything():
         b = slab.slab_bounds(n, w)
         assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(w))
         assert max(b[i + 1] - b[i] for i in range(w)) - min(b[i + 1] - b[i] for i in range(w)) <= 1
+
+
+def _share_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from cosmology_gnn_simulation_b200 import slab
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gen = torch.Generator().manual_seed(3)
+    full = [torch.randn(6, 11, 3, generator=gen), torch.randn(11, 1, generator=gen), torch.randn(1, 11, 3, generator=gen)]
+    res = []
+    for t, pdim in zip(full, (1, 0, 1)):
+        b = slab.slab_bounds(t.shape[pdim], world)
+        mine = tuple([slice(None)] * pdim + [slice(b[rank], b[rank + 1])])
+        part = torch.full_like(t, float("nan"))               # a rank starts with its own share only
+        part[mine] = t[mine]
+        slab.share_over_ranks(part, pdim, world)
+        res.append(bool(torch.equal(part, t)))
+    # host tensor already where it should be / single rank: passes through untouched
+    res.append(slab.sharded_to_device(full[0], 1, rank, world, "cpu") is full[0])
+    torch.save(res, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_shares_of_a_host_tensor_reach_every_rank_world2(tmp_path):
+    """slab.share_over_ranks: the NVLink half of the sharded host-to-device transfer of preprocess_slab (uneven shares, one
+    block per frame)."""
+    out = str(tmp_path / "share")
+    mp.spawn(_share_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in range(2):
+        assert all(torch.load(f"{out}.{r}"))
