@@ -126,12 +126,21 @@ def sharded_to_device(t: torch.Tensor, particle_dim: int, rank: int, world: int,
         return t
     if world == 1 or not dist.is_initialized():
         return t.to(device, non_blocking=True)
-    b = slab_bounds(t.shape[particle_dim], world)
     out = torch.empty(t.shape, dtype=t.dtype, device=device)
-    mine = tuple([slice(None)] * particle_dim + [slice(b[rank], b[rank + 1])])
-    out[mine].copy_(t[mine], non_blocking=True)
+    copy_own_share(out, t, particle_dim, rank, world)
     share_over_ranks(out, particle_dim, world, group)
     return out
+
+
+def copy_own_share(out: torch.Tensor, t: torch.Tensor, particle_dim: int, rank: int, world: int) -> None:
+    """out[..., own share, ...] = t[..., own share, ...], one copy per leading index (frame): every source is then a CONTIGUOUS
+    slice of the (pinned) host tensor and goes out as a plain asynchronous DMA -- a strided [W, share, 3] view would be staged
+    through pageable memory first."""
+    import itertools
+    b = slab_bounds(t.shape[particle_dim], world)
+    for idx in itertools.product(*[range(s_) for s_ in t.shape[:particle_dim]]):
+        sl = idx + (slice(b[rank], b[rank + 1]),)
+        out[sl].copy_(t[sl], non_blocking=True)
 
 
 def share_over_ranks(out: torch.Tensor, particle_dim: int, world: int, group=None) -> None:

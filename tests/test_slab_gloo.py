@@ -117,7 +117,8 @@ def _share_worker(rank, world, port, out):
         b = slab.slab_bounds(t.shape[pdim], world)
         mine = tuple([slice(None)] * pdim + [slice(b[rank], b[rank + 1])])
         part = torch.full_like(t, float("nan"))               # a rank starts with its own share only
-        part[mine] = t[mine]
+        slab.copy_own_share(part, t, pdim, rank, world)
+        res.append(bool(torch.equal(part[mine], t[mine])) and int(torch.isnan(part).sum()) == t.numel() - t[mine].numel())
         slab.share_over_ranks(part, pdim, world)
         res.append(bool(torch.equal(part, t)))
     # host tensor already where it should be / single rank: passes through untouched
