@@ -70,7 +70,7 @@ def forward(params, x, edge_index, edge_attr, n_hidden, n_steps, gdtype, which):
             "temp_rate": model_ref.mlp(params, "decoder_temp_rate", h, n_hidden)}
 
 
-def run(n, k, M, L=128, seed=0):
+def run(n, k, M, L=128, seed=0, variants=None, quiet=False):
     pos = synthetic.positions(n, "uniform", 1.0, seed=seed)
     ext = knn_ref.knn_kdtree(pos, 1.0, k)
     ei = torch.from_numpy(knn_ref.edge_index_from_ext(ext, n))
@@ -89,8 +89,10 @@ def run(n, k, M, L=128, seed=0):
         return {k_: v.grad for k_, v in pp.items()}
 
     truth = grads(torch.float64, None, "")
-    print(f"# n={n} k={k} L={L} M={M} edge messages; rel-L2 of every parameter gradient against the float64 oracle")
-    print(f"{'variant':<28} {'worst':>9} {'median':>9}  worst tensor")
+    results = {}
+    if not quiet:
+        print(f"# n={n} k={k} L={L} M={M} edge messages; rel-L2 of every parameter gradient against the float64 oracle")
+        print(f"{'variant':<28} {'worst':>9} {'median':>9}  worst tensor")
     for label, dt, gd, which in (("fp32", torch.float32, None, ""),
                                  ("g-bf16 edge MLPs", torch.float32, torch.bfloat16, "edge"),
                                  ("g-bf16 edge+node MLPs", torch.float32, torch.bfloat16, "edge node"),
@@ -99,10 +101,15 @@ def run(n, k, M, L=128, seed=0):
                                  ("f64 + g-bf16 edge+node", torch.float64, torch.bfloat16, "edge node"),
                                  ("f64 + g-bf16 edge + de", torch.float64, torch.bfloat16, "edge de"),
                                  ("g-bf16 edge + de", torch.float32, torch.bfloat16, "edge de")):
+        if variants is not None and label not in variants:
+            continue
         g = grads(dt, gd, which)
         errs = sorted(((rel_l2(g[k_], truth[k_]), k_) for k_ in truth), reverse=True)
-        print(f"{label:<28} {errs[0][0]:9.2e} {errs[len(errs) // 2][0]:9.2e}  {errs[0][1]}")
-        sys.stdout.flush()
+        results[label] = (errs[0][0], errs[len(errs) // 2][0], errs[0][1])
+        if not quiet:
+            print(f"{label:<28} {errs[0][0]:9.2e} {errs[len(errs) // 2][0]:9.2e}  {errs[0][1]}")
+            sys.stdout.flush()
+    return results
 
 
 if __name__ == "__main__":
