@@ -191,3 +191,22 @@ def test_halo_row_copies_match_torch_indexing():
         want = dst.clone().index_add_(0, idx, src[:m])
         ops.halo_unpack_add(src[:m].contiguous(), idx, dst)
         assert torch.equal(dst, want)
+
+
+def test_own_share_of_a_pinned_host_sequence_reaches_the_device():
+    """slab.copy_own_share: the PCIe half of preprocess_slab's sharded host-to-device transfer (one contiguous copy per frame)."""
+    from cosmology_gnn_simulation_b200 import slab
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator().manual_seed(5)
+    for shape, pdim in (((6, 1001, 3), 1), ((1001, 1), 0), ((1, 1001, 3), 1)):
+        t = torch.randn(*shape, generator=gen).pin_memory()
+        for world in (2, 3):
+            b = slab.slab_bounds(shape[pdim], world)
+            for rank in range(world):
+                out = torch.full(shape, float("nan"), device=dev)
+                slab.copy_own_share(out, t, pdim, rank, world)
+                torch.cuda.synchronize()
+                mine = tuple([slice(None)] * pdim + [slice(b[rank], b[rank + 1])])
+                got = out.cpu()
+                assert torch.equal(got[mine], t[mine])
+                assert int(torch.isnan(got).sum()) == t.numel() - t[mine].numel()
